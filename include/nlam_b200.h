@@ -1,0 +1,135 @@
+/*
+ * nlam_b200.h -- C ABI of libnlam_b200.so: the B200 (sm_100a) kernels behind
+ * Neural-LAM's InteractionNet message-passing hot path.
+ *
+ * The reference has NO native interface for this path (it is pure Python on
+ * top of PyG/ATen); every entry point below replaces a piece
+ * of Python in /root/reference and cites it.  All pointers are DEVICE
+ * pointers unless said otherwise; sizes are element counts; `stream` is a
+ * cudaStream_t passed as void*.  No function allocates, synchronises or keeps
+ * mutable global state (re-entrant; CUDA-graph capturable); workspaces are
+ * caller-provided.  Every function returns 0 on success; otherwise
+ * nlam_last_error() (thread-local) describes the failure.
+ *
+ * Row-MLP: out[b,r,:] = [residual +] LN( W2 * SiLU( W1 * concat_s src_s[b, idx_s[r], :] + b1 ) + b2 )
+ * which covers, with different gather descriptors,
+ *   - InteractionNet.message  (interaction_net.py:117-121; PyG gather of x_j/x_i)
+ *   - the aggregation MLP     (interaction_net.py:106-109)
+ *   - utils.make_mlp modules  (utils.py:191-214): embedders, grid MLP, output map
+ *   - SplitMLPs               (interaction_net.py:134-163): per-tile weight set.
+ */
+#ifndef NLAM_B200_H
+#define NLAM_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NLAM_MAX_SRC 3
+#define NLAM_TILE_ROWS 64 /* rows of a row-MLP tile (chunk tables use it) */
+
+/* precision modes */
+#define NLAM_FP32 0 /* fp32 FFMA everywhere (parity mode, rtol 1e-4) */
+#define NLAM_BF16 1 /* bf16 tcgen05 MMA, fp32 accumulate/storage (2e-2)  */
+
+/* One gathered input of a row-MLP: row r of batch b is
+ *   ptr + b*batch_stride + (idx ? idx[r] : r)*ld,  `width` floats. */
+typedef struct nlam_src {
+  const float* ptr;
+  const int32_t* idx;   /* [rows] or NULL */
+  int64_t batch_stride; /* 0 = shared by all batch items (stride-0 expand,
+                           ar_model.py:204-209) */
+  int32_t ld;
+  int32_t width;
+} nlam_src;
+
+/* Weights of make_mlp([K, d_hidden, d_out]) (+LayerNorm), nn.Linear layout
+ * (out, in).  With n_chunks > 1 (SplitMLPs) each pointer addresses n_chunks
+ * stacked, contiguous copies and tile t uses set tile_chunk[t]. */
+typedef struct nlam_mlp_weights {
+  const float* w1; /* [d_hidden, K] */
+  const float* b1; /* [d_hidden]    */
+  const float* w2; /* [d_out, d_hidden] */
+  const float* b2; /* [d_out]       */
+  const float* ln_g; /* [d_out] or NULL (no LayerNorm) */
+  const float* ln_b;
+} nlam_mlp_weights;
+
+typedef struct nlam_rowmlp {
+  int32_t n_src;
+  nlam_src src[NLAM_MAX_SRC];
+  int32_t batch;
+  int32_t rows; /* rows per batch item */
+  int32_t d_hidden;
+  int32_t d_out;
+  nlam_mlp_weights w;
+  int32_t n_chunks;           /* 1 = single weight set */
+  const int32_t* tile_ptr;    /* [n_tiles+1] row ranges (<= NLAM_TILE_ROWS rows
+                                 each, never straddling a chunk) or NULL =
+                                 uniform tiles */
+  const int32_t* tile_chunk;  /* [n_tiles] or NULL */
+  const int32_t* chunk_ptr;   /* [n_chunks+1] row offsets of the chunks or NULL */
+  int32_t n_tiles;
+  int32_t residual_src;       /* -1, or s: out += src_s row (needs width==d_out) */
+  float* out;                 /* [batch, rows, d_out] contiguous */
+  int32_t precision;          /* NLAM_FP32 | NLAM_BF16 */
+} nlam_rowmlp;
+
+/* Backward of a row-MLP (recomputes the forward from the same inputs).
+ *   dOut[b,r,:] = (g0 ? g0[b,r,:] : 0) + (g1 ? g1_scale[g1_idx[r]] * g1[b, g1_idx[r], :] : 0)
+ * d_src[s] (may be NULL) receives the un-reduced per-row gradient of source s,
+ * dense [batch, rows, width_s]; for s == residual_src dOut is added.
+ * d_params is one flat buffer per chunk: [dW1 | db1 | dW2 | db2 | dLNg | dLNb]
+ * (LN parts absent without LayerNorm), overwritten (not accumulated). */
+typedef struct nlam_rowmlp_bwd {
+  nlam_rowmlp fwd;
+  const float* g0;       /* [batch, rows, d_out] or NULL */
+  const float* g1;       /* [batch, n1, d_out] or NULL  */
+  const int32_t* g1_idx; /* [rows] */
+  const float* g1_scale; /* [n1] or NULL (mean aggregation: 1/max(deg,1)) */
+  int64_t g1_batch_stride;
+  float* d_src[NLAM_MAX_SRC];
+  float* d_params;
+  float* workspace;       /* nlam_rowmlp_bwd_workspace() floats */
+  size_t workspace_floats;
+} nlam_rowmlp_bwd;
+
+/* out[b,i,:] (+)= scale[i] * sum_{p in [ptr[i],ptr[i+1])} src[b, idx[p], :]
+ * Deterministic segment sum in list order: PyG scatter-sum/mean
+ * (interaction_net.py:124-131) with a receiver-sorted CSR, and the transposed
+ * (sender-sorted) CSR for the backward of the x_j gather. */
+typedef struct nlam_segsum {
+  const float* src;
+  int64_t src_batch_stride;
+  const int32_t* ptr; /* [n_out+1] */
+  const int32_t* idx; /* [ptr[n_out]] */
+  const float* scale; /* [n_out] or NULL */
+  float* out;         /* [batch, n_out, width] contiguous */
+  int32_t batch, n_out, width;
+  int32_t accumulate; /* 0: overwrite, 1: add to out */
+} nlam_segsum;
+
+const char* nlam_last_error(void);
+int nlam_version(void);
+
+/* Stable counting sort of the M edges by `key` (receiver or sender id):
+ * ptr[n_keys+1], perm[M] = edge ids grouped by key, ascending within a key
+ * (== numpy argsort(kind="stable")); inv_deg[n_keys] = 1/max(deg,1) (may be
+ * NULL).  workspace: n_keys+1 int32.  Replaces the scatter index handling of
+ * PyG for the edge_index produced by interaction_net.py:55-61. */
+int nlam_csr_build(const int32_t* key, int64_t n_edges, int32_t n_keys, int32_t* ptr,
+                   int32_t* perm, float* inv_deg, int32_t* workspace, void* stream);
+
+int nlam_rowmlp_fwd(const nlam_rowmlp* desc, void* stream);
+size_t nlam_rowmlp_bwd_workspace(const nlam_rowmlp* desc);
+size_t nlam_rowmlp_param_floats(const nlam_rowmlp* desc); /* per chunk */
+int nlam_rowmlp_bwd_run(const nlam_rowmlp_bwd* desc, void* stream);
+int nlam_segsum_run(const nlam_segsum* desc, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NLAM_B200_H */

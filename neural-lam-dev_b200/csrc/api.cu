@@ -1,0 +1,44 @@
+// C ABI entry points (include/nlam_b200.h) -> kernel launchers.
+#include <stdarg.h>
+#include <string.h>
+
+#include "common.cuh"
+
+namespace nlam {
+static thread_local char g_err[512] = "";
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+}  // namespace nlam
+
+using namespace nlam;
+
+extern "C" const char* nlam_last_error(void) { return g_err; }
+extern "C" int nlam_version(void) { return 1; }
+
+extern "C" int nlam_rowmlp_fwd(const nlam_rowmlp* d, void* stream) {
+  NLAM_CHECK(d, "rowmlp_fwd: NULL descriptor");
+  if (d->precision == NLAM_FP32) return simt_rowmlp_fwd(*d, (cudaStream_t)stream);
+  set_error("rowmlp_fwd: precision mode %d not built", d->precision);
+  return 1;
+}
+
+extern "C" size_t nlam_rowmlp_bwd_workspace(const nlam_rowmlp* d) {
+  return d ? simt_rowmlp_bwd_workspace(*d) : 0;
+}
+
+extern "C" size_t nlam_rowmlp_param_floats(const nlam_rowmlp* d) {
+  if (!d) return 0;
+  ParamLayout lay{k_total_of(*d), d->d_hidden, d->d_out, d->w.ln_g != nullptr};
+  return (size_t)lay.total();
+}
+
+extern "C" int nlam_rowmlp_bwd_run(const nlam_rowmlp_bwd* d, void* stream) {
+  NLAM_CHECK(d, "rowmlp_bwd: NULL descriptor");
+  if (d->fwd.precision == NLAM_FP32) return simt_rowmlp_bwd(*d, (cudaStream_t)stream);
+  set_error("rowmlp_bwd: precision mode %d not built", d->fwd.precision);
+  return 1;
+}

@@ -1,0 +1,67 @@
+// Shared declarations for libnlam_b200 (sm_100a).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/nlam_b200.h"
+
+namespace nlam {
+
+void set_error(const char* fmt, ...);
+
+#define NLAM_CHECK(cond, ...)        \
+  do {                               \
+    if (!(cond)) {                   \
+      nlam::set_error(__VA_ARGS__);  \
+      return 1;                      \
+    }                                \
+  } while (0)
+
+#define NLAM_CUDA(expr)                                                        \
+  do {                                                                         \
+    cudaError_t _e = (expr);                                                   \
+    if (_e != cudaSuccess) {                                                   \
+      nlam::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e),  \
+                      __FILE__, __LINE__);                                     \
+      return 1;                                                                \
+    }                                                                          \
+  } while (0)
+
+// ---- layout of the flat per-chunk parameter(-gradient) block
+struct ParamLayout {
+  int k_total, d_hidden, d_out, has_ln;
+  __host__ __device__ int off_w1() const { return 0; }
+  __host__ __device__ int off_b1() const { return d_hidden * k_total; }
+  __host__ __device__ int off_w2() const { return off_b1() + d_hidden; }
+  __host__ __device__ int off_b2() const { return off_w2() + d_out * d_hidden; }
+  __host__ __device__ int off_lng() const { return off_b2() + d_out; }
+  __host__ __device__ int off_lnb() const { return off_lng() + d_out; }
+  __host__ __device__ int total() const { return off_b2() + d_out + (has_ln ? 2 * d_out : 0); }
+};
+
+inline int k_total_of(const nlam_rowmlp& d) {
+  int k = 0;
+  for (int s = 0; s < d.n_src; ++s) k += d.src[s].width;
+  return k;
+}
+
+inline int pick_dp(const nlam_rowmlp& d) {
+  int need = d.d_hidden > d.d_out ? d.d_hidden : d.d_out;
+  int k3 = (k_total_of(d) + 2) / 3;
+  if (k3 > need) need = k3;
+  for (int s = 0; s < d.n_src; ++s)
+    if (d.src[s].width > need) need = d.src[s].width;
+  if (need <= 16) return 16;
+  if (need <= 32) return 32;
+  if (need <= 64) return 64;
+  if (need <= 128) return 128;
+  return -1;
+}
+
+// fp32 SIMT path
+int simt_rowmlp_fwd(const nlam_rowmlp& d, cudaStream_t st);
+int simt_rowmlp_bwd(const nlam_rowmlp_bwd& d, cudaStream_t st);
+size_t simt_rowmlp_bwd_workspace(const nlam_rowmlp& d);
+
+}  // namespace nlam

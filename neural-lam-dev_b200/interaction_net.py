@@ -1,0 +1,128 @@
+"""Drop-in `InteractionNet` (Battaglia et al. 2016) with the constructor /
+forward signature, child-module names, `state_dict` keys, non-persistent
+`edge_index` buffer and `num_rec` attribute of
+/root/reference/neural_lam/interaction_net.py:10-163 -- but `forward` is a
+single autograd op over the sm_100a kernels in csrc/ (gather, fused edge MLP,
+deterministic CSR segment sum, fused node MLP; backward recomputes edge
+activations and scatters sender gradients through a transposed CSR) instead of
+PyG's MessagePassing.propagate + torch_scatter.
+
+Index semantics are reproduced literally: senders and
+receivers are re-based by their own minimum id, `num_rec = max(receiver)+1`,
+senders index rows of `send_rep` after that re-basing.
+"""
+import torch
+from torch import nn
+
+from . import ops, utils
+
+
+class _GraphPlan:
+    """Per-device integer side tables derived from `edge_index` (built on the
+    GPU by nlam_csr_build; never saved, never trained)."""
+
+    def __init__(self, edge_index, num_rec, edge_chunk_sizes, aggr_chunk_sizes):
+        dev = edge_index.device
+        self.device = dev
+        self.num_rec = num_rec
+        self.n_edges = edge_index.shape[1]
+        self.send32 = (edge_index[0] - num_rec).to(torch.int32).contiguous()
+        self.recv32 = edge_index[1].to(torch.int32).contiguous()
+        self.n_send_idx = int(self.send32.max().item()) + 1 if self.n_edges > 0 else 0
+        # receiver-sorted CSR (aggregation) and sender-sorted CSR (grad of x_j gather)
+        self.rowptr, self.perm, self.inv_deg = ops.csr_build(self.recv32, num_rec, True)
+        self.t_rowptr, self.t_perm, _ = ops.csr_build(self.send32, self.n_send_idx, False)
+        self.edge_tiles = (ops.TileTable(edge_chunk_sizes, dev)
+                           if edge_chunk_sizes is not None else None)
+        self.aggr_tiles = (ops.TileTable(aggr_chunk_sizes, dev)
+                           if aggr_chunk_sizes is not None else None)
+
+
+class InteractionNet(nn.Module):
+    """See module docstring; arguments as interaction_net.py:19-47."""
+
+    def __init__(self, edge_index, input_dim, update_edges=True, hidden_layers=1,
+                 hidden_dim=None, edge_chunk_sizes=None, aggr_chunk_sizes=None, aggr="sum"):
+        assert aggr in ("sum", "mean"), f"Unknown aggregation method: {aggr}"
+        super().__init__()
+        self.aggr = aggr
+        if hidden_dim is None:
+            hidden_dim = input_dim
+
+        # interaction_net.py:55-62 -- integer arithmetic kept bit-exact
+        edge_index = edge_index - edge_index.min(dim=1, keepdim=True)[0]
+        self.num_rec = edge_index[1].max() + 1
+        edge_index[0] = edge_index[0] + self.num_rec
+        self.register_buffer("edge_index", edge_index, persistent=False)
+
+        edge_mlp_recipe = [3 * input_dim] + [hidden_dim] * (hidden_layers + 1)
+        aggr_mlp_recipe = [2 * input_dim] + [hidden_dim] * (hidden_layers + 1)
+        if edge_chunk_sizes is None:
+            self.edge_mlp = utils.make_mlp(edge_mlp_recipe)
+        else:
+            self.edge_mlp = SplitMLPs(
+                [utils.make_mlp(edge_mlp_recipe) for _ in edge_chunk_sizes], edge_chunk_sizes)
+        if aggr_chunk_sizes is None:
+            self.aggr_mlp = utils.make_mlp(aggr_mlp_recipe)
+        else:
+            self.aggr_mlp = SplitMLPs(
+                [utils.make_mlp(aggr_mlp_recipe) for _ in aggr_chunk_sizes], aggr_chunk_sizes)
+        self.update_edges = update_edges
+        self._edge_chunk_sizes = list(edge_chunk_sizes) if edge_chunk_sizes is not None else None
+        self._aggr_chunk_sizes = list(aggr_chunk_sizes) if aggr_chunk_sizes is not None else None
+        self._num_rec_int = int(self.num_rec)  # no host read-back per call
+        self._plan = None
+
+    def _get_plan(self):
+        dev = self.edge_index.device
+        if self._plan is None or self._plan.device != dev:
+            if dev.type != "cuda":
+                raise RuntimeError(
+                    "neural_lam_b200.InteractionNet runs on CUDA only (module is on "
+                    f"{dev}); there is no CPU fallback")
+            self._plan = _GraphPlan(self.edge_index, self._num_rec_int,
+                                    self._edge_chunk_sizes, self._aggr_chunk_sizes)
+        return self._plan
+
+    def forward(self, send_rep, rec_rep, edge_rep):
+        """send_rep (B, N_send, d), rec_rep (B, N_rec, d), edge_rep (B, M, d)
+        [the batch dim is optional, as in the reference] ->
+        rec_rep or (rec_rep, edge_rep) (interaction_net.py:86-115)."""
+        squeeze = rec_rep.dim() == 2
+        if squeeze:
+            send_rep, rec_rep, edge_rep = (t.unsqueeze(0) for t in (send_rep, rec_rep, edge_rep))
+        We = ops.weights_of(self.edge_mlp)
+        Wa = ops.weights_of(self.aggr_mlp)
+        meta = {
+            "plan": self._get_plan(),
+            "edge_chunks": We.n_chunks,
+            "aggr_chunks": Wa.n_chunks,
+            "aggr": self.aggr,
+            "update_edges": self.update_edges,
+            "precision": ops.get_precision(),
+        }
+        out = ops._InteractionNetFn.apply(meta, *We.t, *Wa.t, send_rep, rec_rep, edge_rep)
+        if self.update_edges:
+            rec_out, edge_out = out
+            return (rec_out[0], edge_out[0]) if squeeze else (rec_out, edge_out)
+        return out[0] if squeeze else out
+
+
+class SplitMLPs(nn.Module):
+    """Feeds chunks of the input (split along dim -2) through separate MLPs
+    (interaction_net.py:134-163); one kernel launch, per-tile weight set."""
+
+    def __init__(self, mlps, chunk_sizes):
+        super().__init__()
+        assert len(mlps) == len(chunk_sizes), "Number of MLPs must match the number of chunks"
+        self.mlps = nn.ModuleList(mlps)
+        self.chunk_sizes = chunk_sizes
+        self._tiles = None
+
+    def _tile_table(self, device):
+        if self._tiles is None or self._tiles.tile_ptr.device != device:
+            self._tiles = ops.TileTable(list(self.chunk_sizes), device)
+        return self._tiles
+
+    def forward(self, x):
+        return ops.split_mlp_forward(self, x)

@@ -1,0 +1,395 @@
+"""Host side of the custom ops: builds C-ABI descriptors from tensors and wires
+them into autograd.  PyTorch is only the tensor / autograd carrier; every
+FLOP of the hot path runs in csrc/ kernels.
+
+Ops
+---
+mlp_forward(module, x)         utils.make_mlp modules (utils.py:191-214)
+split_mlp_forward(module, x)   SplitMLPs (interaction_net.py:134-163)
+interaction_net(...)           InteractionNet.forward (interaction_net.py:86-131)
+"""
+import ctypes
+
+import numpy as np
+import torch
+from torch import nn
+
+from . import lib as L
+
+_state = {"precision": "fp32"}
+_PREC = {"fp32": L.FP32, "bf16": L.BF16}
+
+
+def set_precision(mode):
+    """'fp32' (FFMA, parity mode) or 'bf16' (tcgen05 MMA, fp32 accumulate)."""
+    assert mode in _PREC
+    _state["precision"] = mode
+
+
+def get_precision():
+    return _state["precision"]
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _check_cuda(t, what):
+    if not t.is_cuda:
+        raise RuntimeError(
+            f"{what}: tensor is on {t.device}; the neural_lam_b200 kernels run on CUDA "
+            "only (there is no CPU fallback)")
+    if t.dtype != torch.float32:
+        raise RuntimeError(f"{what}: expected float32, got {t.dtype}")
+
+
+def _rows3d(t, what):
+    """Normalise to a 3-D (B, n, w) tensor whose rows are contiguous.  A
+    stride-0 batch dim (expand_to_batch) is kept as is."""
+    _check_cuda(t, what)
+    if t.dim() != 3:
+        raise ValueError(f"{what}: expected (B, N, d), got {tuple(t.shape)}")
+    w = t.shape[2]
+    ok = (t.stride(2) == 1 or w == 1) and t.stride(1) >= w and t.stride(0) >= 0
+    if t.shape[1] == 1 and not ok:
+        ok = t.stride(2) == 1
+    if not ok:
+        t = t.contiguous()
+    return t
+
+
+def _src(t, idx):
+    s = L.Src()
+    s.ptr = t.data_ptr()
+    s.idx = idx.data_ptr() if idx is not None else None
+    s.batch_stride = t.stride(0) if t.shape[0] > 1 else 0
+    s.ld = t.stride(1) if t.shape[1] > 1 else t.shape[2]
+    s.width = t.shape[2]
+    return s
+
+
+class TileTable:
+    """Row tiles that never straddle a chunk (SplitMLPs weight sets)."""
+
+    def __init__(self, chunk_sizes, device):
+        tp, tc = [0], []
+        cp = [0]
+        for c, n in enumerate(chunk_sizes):
+            start = cp[-1]
+            for r0 in range(0, n, L.TILE_ROWS):
+                tp.append(start + min(n, r0 + L.TILE_ROWS))
+                tc.append(c)
+            cp.append(start + n)
+        self.n_tiles = len(tc)
+        self.n_chunks = len(chunk_sizes)
+        self.rows = cp[-1]
+        mk = lambda a: torch.tensor(np.asarray(a, dtype=np.int32), device=device)
+        self.tile_ptr, self.tile_chunk, self.chunk_ptr = mk(tp), mk(tc), mk(cp)
+
+
+class Weights:
+    """The six tensors of make_mlp([K, dh, dout]) (+LN); stacked on a leading
+    chunk dim for SplitMLPs."""
+
+    def __init__(self, w1, b1, w2, b2, ln_g, ln_b, n_chunks):
+        self.t = (w1, b1, w2, b2, ln_g, ln_b)
+        self.n_chunks = n_chunks
+        self.d_hidden, self.k = w1.shape[-2], w1.shape[-1]
+        self.d_out = w2.shape[-2]
+        self.has_ln = ln_g is not None
+
+    def fill(self, desc):
+        for name, t in zip(("w1", "b1", "w2", "b2", "ln_g", "ln_b"), self.t):
+            setattr(desc.w, name, t.data_ptr() if t is not None else None)
+
+    def param_floats(self):
+        n = self.d_hidden * self.k + self.d_hidden + self.d_out * self.d_hidden + self.d_out
+        return n + (2 * self.d_out if self.has_ln else 0)
+
+    def split_grads(self, flat):
+        """flat (n_chunks, P) -> grads shaped like self.t."""
+        C, dh, k, do = self.n_chunks, self.d_hidden, self.k, self.d_out
+        sizes = [dh * k, dh, do * dh, do] + ([do, do] if self.has_ln else [])
+        parts = torch.split(flat, sizes, dim=1)
+        shapes = [(dh, k), (dh,), (do, dh), (do,), (do,), (do,)]
+        out = []
+        for i, t in enumerate(self.t):
+            if t is None:
+                out.append(None)
+            else:
+                g = parts[i].reshape((C,) + shapes[i])
+                out.append(g if t.dim() == len(shapes[i]) + 1 else g[0])
+        return out
+
+
+def _mlp_layers(mlp):
+    layers = list(mlp)
+    ok = (len(layers) in (3, 4) and isinstance(layers[0], nn.Linear)
+          and isinstance(layers[1], nn.SiLU) and isinstance(layers[2], nn.Linear)
+          and (len(layers) == 3 or isinstance(layers[3], nn.LayerNorm)))
+    if not ok:
+        raise NotImplementedError(
+            "fused MLP kernels cover make_mlp blueprints with one hidden layer "
+            "(Linear, SiLU, Linear[, LayerNorm]); got " + repr(mlp))
+    ln = layers[3] if len(layers) == 4 else None
+    return layers[0], layers[2], ln
+
+
+def weights_of(module):
+    """Weights of a make_mlp Sequential or a SplitMLPs."""
+    mlps = getattr(module, "mlps", None)
+    if mlps is None:
+        l1, l2, ln = _mlp_layers(module)
+        return Weights(l1.weight, l1.bias, l2.weight, l2.bias,
+                       ln.weight if ln is not None else None,
+                       ln.bias if ln is not None else None, 1)
+    trip = [_mlp_layers(m) for m in mlps]
+    st = lambda ts: torch.stack(list(ts))
+    has_ln = trip[0][2] is not None
+    return Weights(st(t[0].weight for t in trip), st(t[0].bias for t in trip),
+                   st(t[1].weight for t in trip), st(t[1].bias for t in trip),
+                   st(t[2].weight for t in trip) if has_ln else None,
+                   st(t[2].bias for t in trip) if has_ln else None, len(trip))
+
+
+def _fill_desc(desc, srcs, W, batch, rows, residual, tiles, out, precision):
+    desc.n_src = len(srcs)
+    for i, (t, idx) in enumerate(srcs):
+        desc.src[i] = _src(t, idx)
+    desc.batch, desc.rows = batch, rows
+    desc.d_hidden, desc.d_out = W.d_hidden, W.d_out
+    W.fill(desc)
+    desc.n_chunks = W.n_chunks
+    if tiles is not None:
+        assert tiles.rows == rows and tiles.n_chunks == W.n_chunks
+        desc.tile_ptr = tiles.tile_ptr.data_ptr()
+        desc.tile_chunk = tiles.tile_chunk.data_ptr()
+        desc.chunk_ptr = tiles.chunk_ptr.data_ptr()
+        desc.n_tiles = tiles.n_tiles
+    else:
+        assert W.n_chunks == 1
+        desc.n_tiles = (rows + L.TILE_ROWS - 1) // L.TILE_ROWS
+    desc.residual_src = 0 if residual else -1
+    desc.out = out.data_ptr() if out is not None else None
+    desc.precision = _PREC[precision]
+
+
+def rowmlp_fwd_raw(srcs, W, batch, rows, residual, tiles, precision):
+    """srcs: list of (3-D tensor, int32 row index or None)."""
+    lib = L.load()
+    dev = srcs[0][0].device
+    out = torch.empty((batch, rows, W.d_out), device=dev, dtype=torch.float32)
+    desc = L.RowMlp()
+    _fill_desc(desc, srcs, W, batch, rows, residual, tiles, out, precision)
+    L.check(lib.nlam_rowmlp_fwd(ctypes.byref(desc), _stream()), "nlam_rowmlp_fwd")
+    return out
+
+
+def rowmlp_bwd_raw(srcs, W, batch, rows, residual, tiles, precision, g0, need_src,
+                   g1=None, g1_idx=None, g1_scale=None):
+    """Returns (list of per-row source grads or None, d_params (n_chunks, P))."""
+    lib = L.load()
+    dev = srcs[0][0].device
+    bd = L.RowMlpBwd()
+    _fill_desc(bd.fwd, srcs, W, batch, rows, residual, tiles, None, precision)
+    keep = []
+    if g0 is not None:
+        g0 = g0.contiguous()
+        _check_cuda(g0, "grad_output")
+        bd.g0 = g0.data_ptr()
+    if g1 is not None:
+        g1 = _rows3d(g1, "g1")
+        bd.g1 = g1.data_ptr()
+        bd.g1_idx = g1_idx.data_ptr()
+        bd.g1_scale = g1_scale.data_ptr() if g1_scale is not None else None
+        bd.g1_batch_stride = g1.stride(0) if g1.shape[0] > 1 else 0
+        assert g1.stride(1) == W.d_out or g1.shape[1] == 1
+    d_srcs = []
+    for i, ((t, _), need) in enumerate(zip(srcs, need_src)):
+        if need:
+            g = torch.empty((batch, rows, t.shape[2]), device=dev, dtype=torch.float32)
+            bd.d_src[i] = g.data_ptr()
+            d_srcs.append(g)
+        else:
+            d_srcs.append(None)
+    d_params = torch.empty((W.n_chunks, W.param_floats()), device=dev, dtype=torch.float32)
+    bd.d_params = d_params.data_ptr()
+    nws = lib.nlam_rowmlp_bwd_workspace(ctypes.byref(bd.fwd))
+    ws = torch.empty((max(int(nws), 4),), device=dev, dtype=torch.float32)
+    bd.workspace = ws.data_ptr()
+    bd.workspace_floats = ws.numel()
+    keep.extend([g0, g1, ws])
+    L.check(lib.nlam_rowmlp_bwd_run(ctypes.byref(bd), _stream()), "nlam_rowmlp_bwd_run")
+    return d_srcs, d_params
+
+
+def segsum_raw(src, ptr, idx, n_out, scale=None, out=None, accumulate=False):
+    """src (B, n, w) dense rows -> (B, n_out, w)."""
+    lib = L.load()
+    src = src.contiguous()
+    B, _, w = src.shape
+    if out is None:
+        assert not accumulate
+        out = torch.empty((B, n_out, w), device=src.device, dtype=torch.float32)
+    d = L.SegSum()
+    d.src = src.data_ptr()
+    d.src_batch_stride = src.stride(0)
+    d.ptr, d.idx = ptr.data_ptr(), idx.data_ptr()
+    d.scale = scale.data_ptr() if scale is not None else None
+    d.out = out.data_ptr()
+    d.batch, d.n_out, d.width = B, n_out, w
+    d.accumulate = 1 if accumulate else 0
+    L.check(lib.nlam_segsum_run(ctypes.byref(d), _stream()), "nlam_segsum_run")
+    return out
+
+
+def csr_build(key32, n_keys, want_inv_deg=False):
+    """Stable sort of edge ids by key -> (ptr[n_keys+1], perm[M], inv_deg|None)."""
+    lib = L.load()
+    dev = key32.device
+    m = key32.numel()
+    ptr = torch.empty((n_keys + 1,), device=dev, dtype=torch.int32)
+    perm = torch.empty((max(m, 1),), device=dev, dtype=torch.int32)
+    inv = torch.empty((max(n_keys, 1),), device=dev, dtype=torch.float32) if want_inv_deg else None
+    ws = torch.empty((n_keys + 1,), device=dev, dtype=torch.int32)
+    L.check(lib.nlam_csr_build(key32.data_ptr(), m, n_keys, ptr.data_ptr(), perm.data_ptr(),
+                               inv.data_ptr() if inv is not None else None, ws.data_ptr(),
+                               _stream()), "nlam_csr_build")
+    return ptr, perm[:m], inv
+
+
+# ------------------------------------------------------------------ autograd
+class _RowMLPFn(torch.autograd.Function):
+    """out = [x +] MLP(x) on direct rows (no gather)."""
+
+    @staticmethod
+    def forward(ctx, meta, w1, b1, w2, b2, ln_g, ln_b, x):
+        W = Weights(w1, b1, w2, b2, ln_g, ln_b, meta["n_chunks"])
+        x3 = _rows3d(x, "mlp input")
+        B, rows, _ = x3.shape
+        out = rowmlp_fwd_raw([(x3, None)], W, B, rows, meta["residual"], meta["tiles"],
+                             meta["precision"])
+        ctx.meta = meta
+        ctx.save_for_backward(w1, b1, w2, b2, ln_g, ln_b, x3)
+        return out
+
+    @staticmethod
+    def backward(ctx, gout):
+        w1, b1, w2, b2, ln_g, ln_b, x3 = ctx.saved_tensors
+        meta = ctx.meta
+        W = Weights(w1, b1, w2, b2, ln_g, ln_b, meta["n_chunks"])
+        B, rows, _ = x3.shape
+        d_srcs, d_params = rowmlp_bwd_raw(
+            [(x3, None)], W, B, rows, meta["residual"], meta["tiles"], meta["precision"],
+            gout, [ctx.needs_input_grad[7]])
+        gw = W.split_grads(d_params)
+        return (None, *gw, d_srcs[0])
+
+
+def mlp_forward(module, x, residual=False):
+    """Fused forward of a make_mlp module on x (..., K); `residual=True`
+    returns x + MLP(x) (base_graph_model.py:143-145)."""
+    W = weights_of(module)
+    lead = x.shape[:-1]
+    x3 = x.reshape(1, -1, x.shape[-1]) if x.dim() != 3 else x
+    meta = {"n_chunks": 1, "residual": residual, "tiles": None, "precision": get_precision()}
+    out = _RowMLPFn.apply(meta, *W.t, x3)
+    return out.reshape(*lead, W.d_out)
+
+
+def split_mlp_forward(module, x):
+    """SplitMLPs.forward (interaction_net.py:151-163) as one kernel launch."""
+    W = weights_of(module)
+    lead = x.shape[:-1]
+    x3 = x.reshape(1, *x.shape[-2:]) if x.dim() == 2 else x.reshape(-1, *x.shape[-2:])
+    tiles = module._tile_table(x.device)
+    meta = {"n_chunks": W.n_chunks, "residual": False, "tiles": tiles,
+            "precision": get_precision()}
+    out = _RowMLPFn.apply(meta, *W.t, x3)
+    return out.reshape(*lead, W.d_out)
+
+
+class _InteractionNetFn(torch.autograd.Function):
+    """Whole InteractionNet layer (interaction_net.py:86-131):
+    gather -> edge MLP (+edge residual) -> segment sum/mean -> node MLP + residual."""
+
+    @staticmethod
+    def forward(ctx, meta, *args):
+        ew, aw = args[0:6], args[6:12]
+        send, rec, edge = args[12:15]
+        plan = meta["plan"]
+        We = Weights(*ew, meta["edge_chunks"])
+        Wa = Weights(*aw, meta["aggr_chunks"])
+        send3, rec3, edge3 = (_rows3d(send, "send_rep"), _rows3d(rec, "rec_rep"),
+                              _rows3d(edge, "edge_rep"))
+        B = max(send3.shape[0], rec3.shape[0], edge3.shape[0])
+        prec = meta["precision"]
+        M, n_rec = plan.n_edges, plan.num_rec
+        if rec3.shape[1] != n_rec or edge3.shape[1] != M or send3.shape[1] < plan.n_send_idx:
+            raise RuntimeError(
+                f"InteractionNet: got send/rec/edge rows {send3.shape[1]}/{rec3.shape[1]}/"
+                f"{edge3.shape[1]}, edge_index needs >={plan.n_send_idx}/{n_rec}/{M}")
+        # message + edge residual
+        edge_out = rowmlp_fwd_raw(
+            [(edge3, None), (send3, plan.send32), (rec3, plan.recv32)], We, B, M,
+            False, plan.edge_tiles, prec)
+        # edge_out holds the messages m_k; aggregate (sum / mean over receivers)
+        aggr = segsum_raw(edge_out, plan.rowptr, plan.perm, n_rec,
+                          scale=plan.inv_deg if meta["aggr"] == "mean" else None)
+        rec_out = rowmlp_fwd_raw([(rec3, None), (aggr, None)], Wa, B, n_rec, True,
+                                 plan.aggr_tiles, prec)
+        ctx.meta = meta
+        ctx.save_for_backward(*ew, *aw, send3, rec3, edge3, aggr)
+        if meta["update_edges"]:
+            new_edge = edge3 + edge_out  # E' = E + m  (:112)
+            return rec_out, new_edge
+        return rec_out
+
+    @staticmethod
+    def backward(ctx, *grads):
+        saved = ctx.saved_tensors
+        ew, aw = saved[0:6], saved[6:12]
+        send3, rec3, edge3, aggr = saved[12:16]
+        meta = ctx.meta
+        plan = meta["plan"]
+        We = Weights(*ew, meta["edge_chunks"])
+        Wa = Weights(*aw, meta["aggr_chunks"])
+        prec = meta["precision"]
+        B = max(send3.shape[0], rec3.shape[0], edge3.shape[0])
+        M, n_rec = plan.n_edges, plan.num_rec
+        d_rec_out = grads[0]
+        d_edge_out = grads[1] if meta["update_edges"] else None
+        dev = rec3.device
+        if d_rec_out is None:
+            d_rec_out = torch.zeros((B, n_rec, Wa.d_out), device=dev)
+        # node stage: R' = R + aggr_mlp([R | A])
+        (dR, dA), dPa = rowmlp_bwd_raw(
+            [(rec3, None), (aggr, None)], Wa, B, n_rec, True, plan.aggr_tiles, prec,
+            d_rec_out, [True, True])
+        # edge stage: dm_k = dA[r(k)] (/deg) ; E' = E + m handled after
+        need_send, need_rec, need_edge = ctx.needs_input_grad[13:16]
+        (dzE, dzS, dzR), dPe = rowmlp_bwd_raw(
+            [(edge3, None), (send3, plan.send32), (rec3, plan.recv32)], We, B, M, False,
+            plan.edge_tiles, prec, d_edge_out, [need_edge, need_send, need_rec],
+            g1=dA, g1_idx=plan.recv32,
+            g1_scale=plan.inv_deg if meta["aggr"] == "mean" else None)
+        d_edge = None
+        if need_edge:
+            d_edge = dzE if d_edge_out is None else dzE + d_edge_out
+        d_send = None
+        if need_send:
+            n_send = send3.shape[1]
+            d_send = segsum_raw(dzS, plan.t_rowptr, plan.t_perm, plan.n_send_idx)
+            if n_send > plan.n_send_idx:  # trailing senders without any edge
+                pad = torch.zeros((B, n_send - plan.n_send_idx, dzS.shape[2]), device=dev)
+                d_send = torch.cat((d_send, pad), dim=1)
+        d_rec = None
+        if need_rec:
+            d_rec = segsum_raw(dzR, plan.rowptr, plan.perm, n_rec, out=dR, accumulate=True)
+        def fit(g, t):  # batch-1 inputs broadcast against a larger batch
+            if g is not None and t.shape[0] == 1 and g.shape[0] > 1:
+                g = g.sum(0, keepdim=True)
+            return g
+
+        return (None, *We.split_grads(dPe), *Wa.split_grads(dPa), fit(d_send, send3),
+                fit(d_rec, rec3), fit(d_edge, edge3))
