@@ -1,0 +1,63 @@
+"""CPU: the C-ABI library builds, loads and exports every symbol that
+include/nlam_b200.h declares (no compute without a GPU), and the host logic
+fails loudly instead of falling back."""
+import os
+import re
+
+import pytest
+import torch
+
+import __graft_entry__ as entry
+from helpers import ROOT
+
+
+@pytest.fixture(scope="module")
+def built():
+    entry.build()
+    from neural_lam_b200 import lib
+    return lib
+
+
+def test_header_symbols_exported(built):
+    header = open(os.path.join(ROOT, "include", "nlam_b200.h")).read()
+    declared = set(re.findall(r"\b(nlam_[a-z0-9_]+)\s*\(", header))
+    assert declared, "no declarations found"
+    assert declared == set(built.SYMBOLS), (declared ^ set(built.SYMBOLS))
+    l = built.load()
+    for name in declared:
+        assert hasattr(l, name)
+    assert l.nlam_version() >= 1
+
+
+def test_struct_sizes_match_header(built):
+    # LP64 layout of the by-pointer descriptors (catches ctypes/header drift)
+    import ctypes
+    assert ctypes.sizeof(built.Src) == 32
+    assert ctypes.sizeof(built.MlpWeights) == 48
+    assert ctypes.sizeof(built.RowMlp) == 8 + 3 * 32 + 16 + 48 + 8 + 24 + 8 + 8 + 8
+    assert ctypes.sizeof(built.SegSum) == 64
+
+
+def test_no_cpu_fallback(built):
+    from neural_lam_b200.interaction_net import InteractionNet
+    ei = torch.tensor([[3, 4, 5], [0, 1, 2]])
+    net = InteractionNet(ei, 16)
+    assert torch.equal(net.edge_index, torch.tensor([[3, 4, 5], [0, 1, 2]]))
+    assert int(net.num_rec) == 3
+    x = torch.randn(1, 3, 16)
+    with pytest.raises(RuntimeError, match="CUDA only"):
+        net(x, x, x)
+
+
+def test_state_dict_keys_match_reference_contract(built):
+    """SURVEY.md Appendix C."""
+    from neural_lam_b200.interaction_net import InteractionNet
+    ei = torch.tensor([[3, 4, 5, 5], [0, 1, 2, 2]])
+    keys = list(InteractionNet(ei, 8).state_dict())
+    want = [f"{m}.{i}.{p}" for m in ("edge_mlp", "aggr_mlp") for i in (0, 2, 3)
+            for p in ("weight", "bias")]
+    assert keys == want
+    net = InteractionNet(ei, 8, edge_chunk_sizes=[3, 1], aggr_chunk_sizes=[2, 1])
+    keys = list(net.state_dict())
+    assert "edge_mlp.mlps.1.2.weight" in keys and "aggr_mlp.mlps.0.3.bias" in keys
+    assert "edge_index" not in keys  # non-persistent buffer
