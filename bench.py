@@ -1,0 +1,324 @@
+"""Benchmark of the InteractionNet / GraphLAM training hot path.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+                    [--precision fp32|bf16] [--batch B]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+A "step" is one GraphLAM training step (AR rollout forward, loss, backward,
+gradient mean over ranks, AdamW) on one synthetic MEPS-shaped batch per rank
+(BASELINE.json configs[1]: 1-level mesh, hidden_dim 64, 4 processor layers,
+268 x 238 grid, 17 state variables, random-init weights).  Rank 0 prints ONE
+JSON line (contract: see the task statement / DESIGN.md "Measurement").
+
+`--impl reference` times the reference's CPU path (oracle/port.py, the
+restatement pinned to the unmodified reference by oracle/make_golden.py -- the
+reference itself and PyG cannot travel to the GPU box) on the host cores, one
+sample per step.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "GraphLAM train samples/s"
+UNIT = "samples/s"
+WORKLOAD = ("GraphLAM 1-level mesh, hidden_dim=64, 4 processor layers, synthetic MEPS "
+            "268x238 grid, 17 state vars, ar_steps=1 (BASELINE.json configs[1])")
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--precision", default=os.environ.get("NLAM_PRECISION", "fp32"),
+                    choices=["fp32", "bf16"])
+    ap.add_argument("--batch", type=int, default=4, help="samples per GPU per step")
+    ap.add_argument("--hidden-dim", type=int, default=64)
+    ap.add_argument("--processor-layers", type=int, default=4)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def make_case(root, a):
+    from neural_lam_b200 import create_graph, synthetic
+
+    ds = synthetic.meps_datastore(root, seed=0)
+    args = synthetic.ModelArgs(hidden_dim=a.hidden_dim, processor_layers=a.processor_layers,
+                               graph="1level", loss="wmse")
+    create_graph.create_graph(os.path.join(root, "graph", "1level"),
+                              ds.get_xy("state", stacked=False), n_max_levels=1,
+                              hierarchical=False)
+    return ds, args
+
+
+def config_dict(a, extra=None):
+    cfg = {"workload": WORKLOAD, "global_batch": a.batch * a.gpus, "batch_per_gpu": a.batch,
+           "ar_steps": 1, "hidden_dim": a.hidden_dim, "processor_layers": a.processor_layers,
+           "parallelism": f"dp{a.gpus}" if a.gpus > 1 else "single"}
+    if extra:
+        cfg.update(extra)
+    return cfg
+
+
+# ------------------------------------------------------------------ clocks
+class ClockSampler:
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+              "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.lines = []
+        self.proc = None
+        self.index = index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits",
+                 "-i", str(self.index), "-lms", "100"], stdout=subprocess.PIPE,
+                stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            parts = [p.strip() for p in ln.split(",")]
+            if len(parts) < 8:
+                continue
+            try:
+                sm.append(float(parts[0]))
+                mx.append(float(parts[1]))
+            except ValueError:
+                continue
+            for name, val in zip(names, parts[4:8]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None,
+                "sm_max_mhz": max(mx) if mx else None, "samples": len(sm),
+                "reasons": sorted(reasons)}
+
+
+# ------------------------------------------------------------------ CPU arm
+def time_cpu_oracle(a, steps, warmup):
+    """Reference CPU path (oracle port) on the host cores: samples/s for one
+    sample per step, fwd + bwd + AdamW."""
+    import torch
+
+    from neural_lam_b200 import synthetic
+    from oracle import port
+
+    cores = os.cpu_count()
+    torch.set_num_threads(cores)
+    with tempfile.TemporaryDirectory() as root:
+        ds, args = make_case(root, a)
+        torch.manual_seed(42)
+        model = port.GraphLAM(args, None, ds)
+    opt = model.configure_optimizers()
+    batch = synthetic.synthetic_batch(ds, 1, 1, seed=1)
+    times = []
+    for i in range(warmup + steps):
+        t0 = time.perf_counter()
+        opt.zero_grad()
+        loss = model.training_step(batch)
+        loss.backward()
+        opt.step()
+        times.append(time.perf_counter() - t0)
+    timed = times[warmup:]
+    total = sum(timed)
+    return {"value": len(timed) / total, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": f"{len(timed)} train steps (fwd+bwd+AdamW) of batch 1 after {warmup} warm-up, "
+                      "oracle/port.py (reference restatement) in fp32 on CPU",
+            "ms_per_step": 1e3 * total / len(timed)}
+
+
+def run_reference(a):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    res = time_cpu_oracle(a, a.steps, min(a.warmup, 2))
+    line = {
+        "metric": METRIC, "value": res["value"], "unit": UNIT, "n_gpus": a.gpus,
+        "steps": a.steps, "warmup": a.warmup, "ms_per_step": res["ms_per_step"],
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic", "config": config_dict(a, {"reference_sample_batch": 1}),
+        "impl": "reference",
+        "cpu_baseline": {k: res[k] for k in ("value", "unit", "cores", "kind", "sample")},
+        "e2e": {"value": res["value"], "unit": UNIT, "h2d_bytes_per_step": 0,
+                "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------ GPU arm
+def run_ours(a):
+    import torch
+    import torch.distributed as dist
+
+    import __graft_entry__ as entry
+    entry.build()
+    from neural_lam_b200 import config as nl_config
+    from neural_lam_b200 import lib, models, ops, synthetic, train
+
+    rank, world, device = train.init_distributed()
+    assert device.type == "cuda", "bench.py needs a GPU (no CPU fallback for the product path)"
+    assert world == a.gpus, f"--gpus {a.gpus} but WORLD_SIZE={world}"
+    ops.set_precision(a.precision)
+    with tempfile.TemporaryDirectory() as root:
+        ds, args = make_case(root, a)
+        torch.manual_seed(42)
+        model = models.GraphLAM(args, nl_config.default_config(), ds)
+    model = model.to(device)
+    trainer = train.DataParallelTrainer(model, rank, world)
+
+    # rotating set of distinct batches, > 2x L2 in total, so that no step finds its
+    # inputs in L2 from the previous one (activations per step are GBs anyway)
+    n_rot = 4
+    host = [synthetic.synthetic_batch(ds, a.batch, 1, seed=1000 * rank + i, pin_memory=True)
+            for i in range(n_rot)]
+    dev_batches = [tuple(t.to(device) for t in hb) for hb in host]
+    in_bytes = sum(t.numel() * t.element_size() for t in host[0])
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    L = lib.load()
+    # ---- warm-up (builds CSR plans, allocator pools); find the dominant kernel
+    timer = ops.KernelTimer()
+    for i in range(max(a.warmup, 3)):
+        if i == max(a.warmup, 3) - 1:
+            ops.set_timer(timer)
+        trainer.step(dev_batches[i % n_rot])
+    torch.cuda.synchronize()
+    ops.set_timer(None)
+    summ = timer.summary()
+    dominant = max(summ, key=lambda t: summ[t][1])
+    step_kernel_ms = sum(v[1] for v in summ.values())
+
+    # ---- timed region: device-resident inputs
+    timer = ops.KernelTimer(only=dominant)
+    ops.set_timer(timer)
+    clocks = ClockSampler(device.index or 0)
+    sync_all()
+    clocks.start()
+    launches0 = L.nlam_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(a.steps):
+        loss = trainer.step(dev_batches[i % n_rot])
+    e1.record()
+    sync_all()
+    launches = L.nlam_launch_count() - launches0
+    clk = clocks.stop()
+    ops.set_timer(None)
+    ms = e0.elapsed_time(e1)
+    t = torch.tensor([ms], device=device)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    value = a.steps * a.batch * world / (ms / 1e3)
+
+    n_l, dom_ms, dom_bytes, dom_flops = timer.summary()[dominant]
+    peaks = {"hbm_gbs": 6650.0, "bf16_tflops_sustained": 1400.0, "src": "fallback"}
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            mp = json.load(f)
+        peaks = {"hbm_gbs": mp["hbm_gbs"], "bf16_tflops_sustained": mp["bf16_tflops_sustained"],
+                 "src": "measured"}
+    except (OSError, KeyError, ValueError):
+        pass
+    avg_s = dom_ms / 1e3 / n_l
+    gbs = dom_bytes / avg_s / 1e9
+    roofline = {"bound": "hbm", "achieved": gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                "frac": gbs / peaks["hbm_gbs"], "traffic": None, "kernel": dominant,
+                "launches_timed": n_l, "avg_us": avg_s * 1e6,
+                "algorithmic_bytes_per_launch": dom_bytes,
+                "tflops": dom_flops / avg_s / 1e12, "peak_src": peaks["src"],
+                "share_of_step_kernel_time": summ[dominant][1] / step_kernel_ms}
+
+    # ---- end to end: pinned host batch -> H2D -> step -> loss read back, every step
+    for i in range(2):
+        trainer.step_from_host(host[i % n_rot])
+    sync_all()
+    t0 = time.perf_counter()
+    e0.record()
+    for i in range(a.steps):
+        loss_host = trainer.step_from_host(host[i % n_rot])
+    e1.record()
+    sync_all()
+    wall_ms = (time.perf_counter() - t0) * 1e3
+    ms_e2e = max(e0.elapsed_time(e1), 0.0)
+    t = torch.tensor([ms_e2e], device=device)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_e2e = float(t.item())
+    e2e = {"value": a.steps * a.batch * world / (ms_e2e / 1e3), "unit": UNIT,
+           "h2d_bytes_per_step": in_bytes, "d2h_bytes_per_step": 4,
+           "ms_per_step": ms_e2e / a.steps, "wall_ms_per_step": wall_ms / a.steps,
+           "last_loss": loss_host}
+
+    cpu = None
+    if rank == 0 and world == 1 and not a.no_cpu_baseline:
+        cpu = time_cpu_oracle(a, 3, 1)
+        cpu = {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")}
+
+    if rank == 0:
+        act_mb = 4 * a.batch * (255136 + 79236 + 4 * 51520) * a.hidden_dim / 1e6
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps,
+            "warmup": max(a.warmup, 3), "ms_per_step": ms / a.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32" if a.precision == "fp32" else "bf16",
+            "data": "synthetic",
+            "config": config_dict(a, {
+                "precision": a.precision,
+                "l2": f"{n_rot} rotating input batches ({n_rot * in_bytes / 1e6:.0f} MB) and "
+                      f"~{act_mb:.0f} MB of edge activations per step, both > 126 MB L2; "
+                      "no explicit flush"}),
+            "clocks": clk, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
+            "cpu_baseline": cpu, "impl": "ours", "loss": float(loss.item()),
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    a = parse()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_ours(a)
+
+
+if __name__ == "__main__":
+    main()

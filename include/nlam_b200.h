@@ -114,6 +114,9 @@ typedef struct nlam_segsum {
 
 const char* nlam_last_error(void);
 int nlam_version(void);
+/* Number of kernels this library has launched in this process (monotonic;
+ * bench.py reports the delta over its timed region as "gpu_launches"). */
+int64_t nlam_launch_count(void);
 
 /* Stable counting sort of the M edges by `key` (receiver or sender id):
  * ptr[n_keys+1], perm[M] = edge ids grouped by key, ascending within a key

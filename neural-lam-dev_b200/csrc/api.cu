@@ -1,5 +1,7 @@
 // C ABI entry points (include/nlam_b200.h) -> kernel launchers.
 #include <stdarg.h>
+
+#include <atomic>
 #include <string.h>
 
 #include "common.cuh"
@@ -12,9 +14,13 @@ void set_error(const char* fmt, ...) {
   vsnprintf(g_err, sizeof(g_err), fmt, ap);
   va_end(ap);
 }
+static std::atomic<long long> g_launches{0};
+void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 }  // namespace nlam
 
 using namespace nlam;
+
+extern "C" int64_t nlam_launch_count(void) { return (int64_t)nlam::g_launches.load(); }
 
 extern "C" const char* nlam_last_error(void) { return g_err; }
 extern "C" int nlam_version(void) { return 1; }

@@ -9,6 +9,7 @@
 namespace nlam {
 
 void set_error(const char* fmt, ...);
+void count_launch(int n = 1);
 
 #define NLAM_CHECK(cond, ...)        \
   do {                               \

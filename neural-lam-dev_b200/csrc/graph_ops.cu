@@ -132,14 +132,18 @@ extern "C" int nlam_csr_build(const int32_t* key, int64_t n_edges, int32_t n_key
   if (n_edges > 0) {
     csr_count_kernel<<<nb, 256, 0, st>>>(key, n_edges, workspace);
     NLAM_CUDA(cudaGetLastError());
+    count_launch();
   }
   csr_scan_kernel<<<1, 1024, 0, st>>>(workspace, n_keys, ptr, inv_deg);
   NLAM_CUDA(cudaGetLastError());
+  count_launch();
   if (n_edges > 0) {
     csr_fill_kernel<<<nb, 256, 0, st>>>(key, n_edges, ptr, workspace, perm);
     NLAM_CUDA(cudaGetLastError());
+    count_launch();
     csr_sort_kernel<<<(n_keys + 127) / 128, 128, 0, st>>>(ptr, n_keys, perm);
     NLAM_CUDA(cudaGetLastError());
+    count_launch();
   }
   return 0;
 }
@@ -158,5 +162,6 @@ extern "C" int nlam_segsum_run(const nlam_segsum* d, void* stream) {
   else
     segsum_kernel<1><<<nb, 256, 0, st>>>(*d);
   NLAM_CUDA(cudaGetLastError());
+  count_launch();
   return 0;
 }

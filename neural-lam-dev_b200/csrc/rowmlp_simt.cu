@@ -683,6 +683,7 @@ static int launch_fwd(const KParams& p, cudaStream_t st) {
   dim3 grid(n_tiles_of(p.d), p.d.batch);
   rowmlp_fwd_kernel<DP><<<grid, NT, C::SMEM, st>>>(p);
   NLAM_CUDA(cudaGetLastError());
+  count_launch();
   return 0;
 }
 
@@ -749,14 +750,17 @@ static int launch_bwd(const KParams& p, const WParams& wp, const RParams& rp, cu
   dim3 grid(n_tiles_of(p.d), p.d.batch);
   rowmlp_bwd_kernel<DP><<<grid, NT, C::SMEM, st>>>(p);
   NLAM_CUDA(cudaGetLastError());
+  count_launch();
   int kb = 0;
   for (int j = 0; j < wp.n_jobs; ++j) kb += wp.job[j].kblocks;
   dim3 wgrid(wp.splits, kb, wp.n_chunks);
   wgrad_kernel<DP><<<wgrid, NT, 0, st>>>(wp);
   NLAM_CUDA(cudaGetLastError());
+  count_launch();
   dim3 rgrid((rp.p_total + 255) / 256, rp.n_chunks);
   reduce_params_kernel<<<rgrid, 256, 0, st>>>(rp);
   NLAM_CUDA(cudaGetLastError());
+  count_launch();
   return 0;
 }
 

@@ -1,0 +1,114 @@
+"""Auto-regressive rollout, loss and optimizer of the training hot path
+(/root/reference/neural_lam/models/ar_model.py:21-131, 191-309), as a plain
+`nn.Module`: Lightning (logging, checkpoints, eval plots) is out of scope, the
+training loop is neural_lam_b200.train."""
+import torch
+from torch import nn
+
+from .. import metrics
+from ..loss_weighting import get_state_feature_weighting
+
+
+class ARModel(nn.Module):
+    def __init__(self, args, config, datastore):
+        super().__init__()
+        self.args = args
+        self._datastore = datastore
+        num_state_vars = datastore.get_num_data_vars(category="state")
+        num_forcing_vars = datastore.get_num_data_vars(category="forcing")
+        da_static = datastore.get_dataarray(category="static", split=None)
+        da_stats = datastore.get_standardization_dataarray(category="state")
+
+        def f32(a):
+            return torch.tensor(a, dtype=torch.float32)
+
+        # (grid_index, static_feature) order, ar_model.py:51-60
+        self.register_buffer(
+            "grid_static_features",
+            f32(da_static.transpose("grid_index", "static_feature").values),
+            persistent=False)
+        for name, da in (("state_mean", da_stats.state_mean), ("state_std", da_stats.state_std),
+                         ("diff_mean", da_stats.state_diff_mean),
+                         ("diff_std", da_stats.state_diff_std)):
+            self.register_buffer(name, f32(da.values), persistent=False)
+
+        self.feature_weights = f32(get_state_feature_weighting(config=config, datastore=datastore))
+        self.output_std = bool(args.output_std)
+        if self.output_std:
+            self.grid_output_dim = 2 * num_state_vars
+        else:
+            self.grid_output_dim = num_state_vars
+            # inverse of the multiplicative wMSE weighting, ar_model.py:96-103
+            self.register_buffer("per_var_std", self.diff_std / torch.sqrt(self.feature_weights),
+                                 persistent=False)
+        self.num_grid_nodes, grid_static_dim = self.grid_static_features.shape
+        self.grid_dim = (2 * self.grid_output_dim + grid_static_dim + num_forcing_vars * (
+            args.num_past_forcing_steps + args.num_future_forcing_steps + 1))
+        self.loss = metrics.get_metric(args.loss)
+
+        boundary_mask = f32(datastore.boundary_mask.values).unsqueeze(1)
+        self.register_buffer("boundary_mask", boundary_mask, persistent=False)
+        self.register_buffer("interior_mask", 1.0 - boundary_mask, persistent=False)
+        self.restore_opt = getattr(args, "restore_opt", False)
+        self._num_interior = int(self.interior_mask.sum().item())
+
+    def configure_optimizers(self):
+        """AdamW(lr, betas=(0.9, 0.95)), default weight decay (ar_model.py:191-195)."""
+        return torch.optim.AdamW(self.parameters(), lr=self.args.lr, betas=(0.9, 0.95),
+                                 fused=next(self.parameters()).is_cuda)
+
+    @property
+    def interior_mask_bool(self):
+        return self.interior_mask[:, 0].to(torch.bool)
+
+    @staticmethod
+    def expand_to_batch(x, batch_size):
+        """Stride-0 batch view (ar_model.py:204-209)."""
+        return x.unsqueeze(0).expand(batch_size, -1, -1)
+
+    def predict_step(self, prev_state, prev_prev_state, forcing):
+        raise NotImplementedError("No prediction step implemented")
+
+    def unroll_prediction(self, init_states, forcing_features, true_states):
+        """ar_model.py:220-267: sequential rollout; the boundary is overwritten
+        with the true state before feeding back."""
+        prev_prev_state, prev_state = init_states[:, 0], init_states[:, 1]
+        predictions, pred_stds = [], []
+        for i in range(forcing_features.shape[1]):
+            pred_state, pred_std = self.predict_step(prev_state, prev_prev_state,
+                                                     forcing_features[:, i])
+            new_state = (self.boundary_mask * true_states[:, i]
+                         + self.interior_mask * pred_state)
+            predictions.append(new_state)
+            if self.output_std:
+                pred_stds.append(pred_std)
+            prev_prev_state, prev_state = prev_state, new_state
+        prediction = torch.stack(predictions, dim=1)
+        pred_std = torch.stack(pred_stds, dim=1) if self.output_std else self.per_var_std
+        return prediction, pred_std
+
+    def common_step(self, batch):
+        """ar_model.py:269-285."""
+        init_states, target_states, forcing_features, batch_times = batch
+        prediction, pred_std = self.unroll_prediction(init_states, forcing_features,
+                                                      target_states)
+        return prediction, target_states, pred_std, batch_times
+
+    def training_step(self, batch):
+        """Mean over batch and unrolled steps of the masked loss (ar_model.py:287-309)."""
+        prediction, target, pred_std, _ = self.common_step(batch)
+        if self.loss in (metrics.wmse, metrics.mse) and not self.output_std:
+            return self._masked_squared_loss(prediction, target, pred_std)
+        return torch.mean(self.loss(prediction, target, pred_std, mask=self.interior_mask_bool))
+
+    def _masked_squared_loss(self, prediction, target, pred_std):
+        """mean_{B,T}( mean_{interior nodes}( sum_vars ((pred-target)/std)^2 ) ) -- the
+        same number as metrics.wmse/mse with mask=interior_mask_bool
+        (metrics.py:21-84), written as a multiply by the 0/1 interior mask so
+        that no boolean-index gather (a device->host sync) is needed."""
+        inv_var = 1.0 / (pred_std**2) if self.loss is metrics.wmse else None
+        sq = (prediction - target) ** 2
+        if inv_var is not None:
+            sq = sq * inv_var
+        n_bt = prediction.shape[0] * prediction.shape[1]
+        return (sq * self.interior_mask).sum() / float(n_bt * self._num_interior)

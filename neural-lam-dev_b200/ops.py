@@ -34,6 +34,60 @@ def _stream():
     return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
+class KernelTimer:
+    """Optional per-launch CUDA-event timing (on the launching stream) used by
+    bench.py for the roofline of the dominant kernel.  `only`: restrict to one
+    tag so the timed region is not perturbed by the others."""
+
+    def __init__(self, only=None):
+        self.only = only
+        self.records = {}  # tag -> {"events": [(start, end)], "bytes": int, "flops": int}
+
+    def want(self, tag):
+        return self.only is None or tag == self.only
+
+    def start(self, tag, nbytes, flops):
+        rec = self.records.setdefault(tag, {"events": [], "bytes": nbytes, "flops": flops})
+        ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+        ev[0].record()
+        rec["events"].append(ev)
+        return ev[1]
+
+    def summary(self):
+        """tag -> (launches, total_ms, bytes_per_launch, flops_per_launch); call after a sync."""
+        out = {}
+        for tag, rec in self.records.items():
+            ms = sum(a.elapsed_time(b) for a, b in rec["events"])
+            out[tag] = (len(rec["events"]), ms, rec["bytes"], rec["flops"])
+        return out
+
+
+_timer = {"t": None}
+
+
+def set_timer(timer):
+    _timer["t"] = timer
+
+
+def _src_bytes(t, idx, batch):
+    """Algorithmic bytes of one source: every distinct row once."""
+    nb = 1 if (t.shape[0] == 1 or t.stride(0) == 0) else batch
+    return 4 * nb * t.shape[1] * t.shape[2] + (4 * idx.numel() if idx is not None else 0)
+
+
+def _rowmlp_cost(kind, srcs, W, batch, rows, extra_row_floats):
+    """(tag, algorithmic bytes, flops) of one row-MLP launch.  bytes: distinct
+    input rows + gather indices + weights + rows written/read besides the
+    inputs; flops: 2*rows*(K*dh + dh*dout) forward, 3x for dgrad+recompute."""
+    k = sum(t.shape[2] for t, _ in srcs)
+    tag = f"{kind}|rows={rows}|K={k}|dh={W.d_hidden}|dout={W.d_out}|B={batch}"
+    nbytes = sum(_src_bytes(t, i, batch) for t, i in srcs)
+    nbytes += 4 * W.n_chunks * W.param_floats()
+    nbytes += 4 * batch * rows * extra_row_floats
+    flops = 2 * batch * rows * (k * W.d_hidden + W.d_hidden * W.d_out)
+    return tag, nbytes, flops
+
+
 def _check_cuda(t, what):
     if not t.is_cuda:
         raise RuntimeError(
@@ -181,7 +235,14 @@ def rowmlp_fwd_raw(srcs, W, batch, rows, residual, tiles, precision):
     out = torch.empty((batch, rows, W.d_out), device=dev, dtype=torch.float32)
     desc = L.RowMlp()
     _fill_desc(desc, srcs, W, batch, rows, residual, tiles, out, precision)
+    end = None
+    if _timer["t"] is not None:
+        tag, nbytes, flops = _rowmlp_cost(f"rowmlp_fwd_{precision}", srcs, W, batch, rows, W.d_out)
+        if _timer["t"].want(tag):
+            end = _timer["t"].start(tag, nbytes, flops)
     L.check(lib.nlam_rowmlp_fwd(ctypes.byref(desc), _stream()), "nlam_rowmlp_fwd")
+    if end is not None:
+        end.record()
     return out
 
 
@@ -219,7 +280,18 @@ def rowmlp_bwd_raw(srcs, W, batch, rows, residual, tiles, precision, g0, need_sr
     bd.workspace = ws.data_ptr()
     bd.workspace_floats = ws.numel()
     keep.extend([g0, g1, ws])
+    end = None
+    if _timer["t"] is not None:
+        # rows moved besides the inputs: dOut read, per-source grads written,
+        # a/dy/dh saved and re-read by the weight-gradient kernel
+        extra = W.d_out + sum(t.shape[2] for (t, _), n in zip(srcs, need_src) if n)
+        extra += 2 * (2 * W.d_hidden + W.d_out)
+        tag, nbytes, flops = _rowmlp_cost(f"rowmlp_bwd_{precision}", srcs, W, batch, rows, extra)
+        if _timer["t"].want(tag):
+            end = _timer["t"].start(tag, nbytes, 3 * flops)
     L.check(lib.nlam_rowmlp_bwd_run(ctypes.byref(bd), _stream()), "nlam_rowmlp_bwd_run")
+    if end is not None:
+        end.record()
     return d_srcs, d_params
 
 
@@ -239,7 +311,16 @@ def segsum_raw(src, ptr, idx, n_out, scale=None, out=None, accumulate=False):
     d.out = out.data_ptr()
     d.batch, d.n_out, d.width = B, n_out, w
     d.accumulate = 1 if accumulate else 0
+    end = None
+    if _timer["t"] is not None:
+        tag = f"segsum|n_out={n_out}|m={idx.numel()}|w={w}|B={B}"
+        if _timer["t"].want(tag):
+            nbytes = 4 * B * w * (idx.numel() + n_out * (2 if accumulate else 1)) \
+                + 4 * (idx.numel() + n_out)
+            end = _timer["t"].start(tag, nbytes, B * w * idx.numel())
     L.check(lib.nlam_segsum_run(ctypes.byref(d), _stream()), "nlam_segsum_run")
+    if end is not None:
+        end.record()
     return out
 
 

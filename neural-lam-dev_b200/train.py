@@ -1,0 +1,139 @@
+"""Data-parallel training step: the part of Lightning's
+`Trainer(strategy="ddp")` (/root/reference/neural_lam/train_model.py:276-296)
+that is on the hot path -- per-rank batch, gradient MEAN all-reduce over
+NCCL/NVLink overlapped with the rest of backward, identical AdamW on every
+rank (ar_model.py:191-195).  One process per GPU; the graph and the weights
+are replicated (they are small), samples are sharded.
+
+Gradients live in ONE flat fp32 buffer (parameters' .grad are views into it),
+split into two buckets in backward order: the decoder/processor bucket is
+all-reduced on a side stream as soon as its last gradient is written, while
+the encoder part of backward is still running; the encoder bucket follows at
+the end.  With 0.9-5 MB of gradients both transfers are latency-bound.
+"""
+import os
+
+import torch
+import torch.distributed as dist
+
+
+def init_distributed():
+    """Read RANK/LOCAL_RANK/WORLD_SIZE/MASTER_* (torchrun) and set the device.
+    Returns (rank, world_size, device)."""
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if torch.cuda.is_available():
+        torch.cuda.set_device(local)
+        device = torch.device("cuda", local)
+        backend = "nccl"
+    else:
+        device = torch.device("cpu")
+        backend = "gloo"
+    if world > 1 and not dist.is_initialized():
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("MASTER_PORT", "29500")
+        kw = {"device_id": device} if backend == "nccl" else {}
+        dist.init_process_group(backend=backend, rank=rank, world_size=world, **kw)
+    return rank, world, device
+
+
+class FlatGradBuckets:
+    """Flat gradient storage + bucketed mean all-reduce with backward overlap.
+
+    `early_names`: parameter-name prefixes whose gradients are complete before
+    backward reaches the encoder (everything downstream of the g2m encoder).
+    """
+
+    def __init__(self, named_params, world_size, early_prefixes=(), overlap=True):
+        self.world = world_size
+        params = [(n, p) for n, p in named_params if p.requires_grad]
+        early = [(n, p) for n, p in params if n.startswith(tuple(early_prefixes))] \
+            if early_prefixes else []
+        late = [(n, p) for n, p in params if not (early_prefixes and
+                                                  n.startswith(tuple(early_prefixes)))]
+        self.order = early + late
+        total = sum(p.numel() for _, p in self.order)
+        dev = self.order[0][1].device
+        self.flat = torch.zeros(total, device=dev, dtype=torch.float32)
+        off = 0
+        for _, p in self.order:
+            p.grad = self.flat[off:off + p.numel()].view_as(p)
+            off += p.numel()
+        self.n_early = sum(p.numel() for _, p in early)
+        self.overlap = overlap and world_size > 1 and self.n_early > 0 and dev.type == "cuda"
+        self._pending = 0
+        self._early_params = [p for _, p in early]
+        self._early_work = None
+        self.side = torch.cuda.Stream(device=dev) if self.overlap else None
+        if self.overlap:
+            for p in self._early_params:
+                p.register_post_accumulate_grad_hook(self._hook)
+
+    def zero(self):
+        self.flat.zero_()
+        self._pending = len(self._early_params)
+        self._early_work = None
+
+    def _hook(self, _param):
+        self._pending -= 1
+        if self._pending == 0:
+            # all early gradients are written on the compute stream: reduce them
+            # on the side stream while backward continues
+            self.side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(self.side):
+                self._early_work = dist.all_reduce(
+                    self.flat[:self.n_early], op=dist.ReduceOp.AVG, async_op=True)
+
+    def reduce(self):
+        """Finish the gradient mean over ranks (call after backward)."""
+        if self.world == 1:
+            return
+        if self.flat.is_cuda:
+            if self._early_work is not None:
+                dist.all_reduce(self.flat[self.n_early:], op=dist.ReduceOp.AVG)
+                self._early_work.wait()
+                torch.cuda.current_stream().wait_stream(self.side)
+            else:
+                dist.all_reduce(self.flat, op=dist.ReduceOp.AVG)
+        else:  # gloo has no AVG
+            dist.all_reduce(self.flat, op=dist.ReduceOp.SUM)
+            self.flat.div_(self.world)
+
+
+# gradients of these sub-modules are final before backward enters the encoder
+EARLY_PREFIXES = ("output_map", "m2g_gnn", "m2g_embedder", "processor", "m2m_embedder",
+                  "mesh_down", "mesh_up", "mesh_same", "mesh_init", "mesh_read",
+                  "mesh_embedders", "mesh_same_embedders", "mesh_up_embedders",
+                  "mesh_down_embedders")
+
+
+class DataParallelTrainer:
+    """`step(batch)`: forward (AR rollout + loss), backward, gradient mean over
+    ranks, AdamW.  `step_from_host(batch)`: same, starting from pinned host
+    tensors and ending with the loss on the host (the end-to-end call)."""
+
+    def __init__(self, model, rank=0, world_size=1, overlap=True):
+        self.model = model
+        self.rank, self.world = rank, world_size
+        self.device = next(model.parameters()).device
+        if world_size > 1:
+            # same initial weights everywhere (DDP broadcasts rank 0's)
+            for p in model.parameters():
+                dist.broadcast(p.data, src=0)
+        self.buckets = FlatGradBuckets(list(model.named_parameters()), world_size,
+                                       EARLY_PREFIXES, overlap)
+        self.optimizer = model.configure_optimizers()
+
+    def step(self, batch):
+        self.buckets.zero()
+        loss = self.model.training_step(batch)
+        loss.backward()
+        self.buckets.reduce()
+        self.optimizer.step()
+        return loss.detach()
+
+    def step_from_host(self, host_batch):
+        batch = tuple(t.to(self.device, non_blocking=True) for t in host_batch)
+        loss = self.step(batch)
+        return float(loss.item())  # device -> host read of the step's result
