@@ -28,7 +28,11 @@ extern "C" int nlam_version(void) { return 1; }
 extern "C" int nlam_rowmlp_fwd(const nlam_rowmlp* d, void* stream) {
   NLAM_CHECK(d, "rowmlp_fwd: NULL descriptor");
   if (d->precision == NLAM_FP32) return simt_rowmlp_fwd(*d, (cudaStream_t)stream);
-  set_error("rowmlp_fwd: precision mode %d not built", d->precision);
+  if (d->precision == NLAM_BF16) {
+    if (tc::tc_supported(*d)) return tc_rowmlp_fwd(*d, (cudaStream_t)stream);
+    return simt_rowmlp_fwd(*d, (cudaStream_t)stream);  // widths the MMA path does not take
+  }
+  set_error("rowmlp_fwd: unknown precision mode %d", d->precision);
   return 1;
 }
 
@@ -44,7 +48,8 @@ extern "C" size_t nlam_rowmlp_param_floats(const nlam_rowmlp* d) {
 
 extern "C" int nlam_rowmlp_bwd_run(const nlam_rowmlp_bwd* d, void* stream) {
   NLAM_CHECK(d, "rowmlp_bwd: NULL descriptor");
-  if (d->fwd.precision == NLAM_FP32) return simt_rowmlp_bwd(*d, (cudaStream_t)stream);
-  set_error("rowmlp_bwd: precision mode %d not built", d->fwd.precision);
+  if (d->fwd.precision == NLAM_FP32 || d->fwd.precision == NLAM_BF16)
+    return simt_rowmlp_bwd(*d, (cudaStream_t)stream);
+  set_error("rowmlp_bwd: unknown precision mode %d", d->fwd.precision);
   return 1;
 }

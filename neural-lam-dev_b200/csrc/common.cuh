@@ -65,4 +65,10 @@ int simt_rowmlp_fwd(const nlam_rowmlp& d, cudaStream_t st);
 int simt_rowmlp_bwd(const nlam_rowmlp_bwd& d, cudaStream_t st);
 size_t simt_rowmlp_bwd_workspace(const nlam_rowmlp& d);
 
+// bf16 tcgen05 path
+namespace tc {
+bool tc_supported(const nlam_rowmlp& d);
+}
+int tc_rowmlp_fwd(const nlam_rowmlp& d, cudaStream_t st);
+
 }  // namespace nlam

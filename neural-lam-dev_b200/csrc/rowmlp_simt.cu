@@ -17,13 +17,13 @@
 // .message / aggr_mlp (interaction_net.py:106,117-121), SplitMLPs (:134-163).
 #include <math.h>
 
-#include "common.cuh"
+#include "rowmlp_common.cuh"
 
 namespace nlam {
 
 constexpr int TM = NLAM_TILE_ROWS;  // rows per tile
 constexpr int NT = 256;             // threads per CTA
-constexpr float LN_EPS = 1e-5f;     // nn.LayerNorm default (utils.py:212)
+
 
 template <int DP>
 struct Cfg {
@@ -38,26 +38,6 @@ struct Cfg {
   static constexpr size_t SMEM = sizeof(float) * (size_t)(TM * AS + TM * HS + WSZ);
 };
 
-struct KParams {
-  nlam_rowmlp d;
-  int k_total;  // sum of source widths
-  int koff[NLAM_MAX_SRC + 1];
-  int vec_ok[NLAM_MAX_SRC];  // 128-bit gather allowed
-  int out_vec_ok;
-  ParamLayout lay;
-  // backward only
-  const float* g0;
-  const float* g1;
-  const int32_t* g1_idx;
-  const float* g1_scale;
-  long long g1_batch_stride;
-  float* d_src[NLAM_MAX_SRC];
-  float* a_save;
-  float* dy_save;
-  float* dh_save;
-  float* ln_partial;  // [batch][n_tiles][2][d_out]
-};
-
 __device__ __forceinline__ float silu_f(float x) { return x / (1.0f + expf(-x)); }
 __device__ __forceinline__ float silu_grad_f(float x) {
   float s = 1.0f / (1.0f + expf(-x));
@@ -68,19 +48,6 @@ template <int DP>
 __device__ __forceinline__ int col_of(int tx, int c) {
   using C = Cfg<DP>;
   return (tx + 16 * (c / C::VEC)) * C::VEC + (c % C::VEC);
-}
-
-__device__ __forceinline__ void tile_range(const nlam_rowmlp& d, int tile, int& row0, int& cnt,
-                                           int& chunk) {
-  if (d.tile_ptr) {
-    row0 = d.tile_ptr[tile];
-    cnt = d.tile_ptr[tile + 1] - row0;
-    chunk = d.tile_chunk ? d.tile_chunk[tile] : 0;
-  } else {
-    row0 = tile * TM;
-    cnt = min(TM, d.rows - row0);
-    chunk = 0;
-  }
 }
 
 // Stage the gathered + concatenated input rows of a tile in shared memory.
@@ -232,7 +199,7 @@ __global__ void __launch_bounds__(NT) rowmlp_fwd_kernel(const __grid_constant__ 
   const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
   const int b = blockIdx.y;
   int row0, cnt, chunk;
-  tile_range(p.d, blockIdx.x, row0, cnt, chunk);
+  tile_range<TM>(p.d, blockIdx.x, row0, cnt, chunk);
   if (cnt <= 0) return;
   const int dh = p.d.d_hidden, dout = p.d.d_out;
   const float* w1 = p.d.w.w1 + (size_t)chunk * dh * p.k_total;
@@ -324,7 +291,7 @@ __global__ void __launch_bounds__(NT) rowmlp_bwd_kernel(const __grid_constant__ 
   const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
   const int b = blockIdx.y;
   int row0, cnt, chunk;
-  tile_range(p.d, blockIdx.x, row0, cnt, chunk);
+  tile_range<TM>(p.d, blockIdx.x, row0, cnt, chunk);
   if (cnt <= 0) return;
   const int dh = p.d.d_hidden, dout = p.d.d_out;
   const float* w1 = p.d.w.w1 + (size_t)chunk * dh * p.k_total;
@@ -641,36 +608,6 @@ __global__ void reduce_params_kernel(const __grid_constant__ RParams p) {
 }
 
 // -------------------------------------------------------------------- host side
-static int n_tiles_of(const nlam_rowmlp& d) {
-  return d.tile_ptr ? d.n_tiles : (d.rows + TM - 1) / TM;
-}
-
-static int fill_params(const nlam_rowmlp& d, KParams& p) {
-  p.d = d;
-  NLAM_CHECK(d.n_src >= 1 && d.n_src <= NLAM_MAX_SRC, "rowmlp: n_src=%d out of range", d.n_src);
-  NLAM_CHECK(d.batch >= 1 && d.rows >= 0, "rowmlp: bad batch/rows");
-  NLAM_CHECK(d.n_chunks >= 1, "rowmlp: n_chunks must be >= 1");
-  NLAM_CHECK(d.n_chunks == 1 || (d.tile_ptr && d.tile_chunk && d.chunk_ptr),
-             "rowmlp: chunked weights need tile_ptr/tile_chunk/chunk_ptr");
-  int k = 0;
-  for (int s = 0; s < d.n_src; ++s) {
-    p.koff[s] = k;
-    const nlam_src& src = d.src[s];
-    NLAM_CHECK(src.ptr && src.width > 0 && src.ld >= src.width, "rowmlp: bad source %d", s);
-    p.vec_ok[s] = (src.width % 4 == 0) && (k % 4 == 0) && (src.ld % 4 == 0) &&
-                  (src.batch_stride % 4 == 0) && (((uintptr_t)src.ptr) % 16 == 0);
-    k += src.width;
-  }
-  for (int s = d.n_src; s <= NLAM_MAX_SRC; ++s) p.koff[s] = k;
-  p.k_total = k;
-  NLAM_CHECK(d.residual_src == -1 || d.residual_src == 0, "rowmlp: residual_src must be -1 or 0");
-  NLAM_CHECK(d.residual_src < 0 || d.src[0].width == d.d_out,
-             "rowmlp: residual source width %d != d_out %d", d.src[0].width, d.d_out);
-  p.out_vec_ok = (d.d_out % 4 == 0) && (((uintptr_t)d.out) % 16 == 0);
-  p.lay = ParamLayout{k, d.d_hidden, d.d_out, d.w.ln_g != nullptr};
-  return 0;
-}
-
 template <int DP>
 static int launch_fwd(const KParams& p, cudaStream_t st) {
   using C = Cfg<DP>;

@@ -1,0 +1,380 @@
+// bf16 tensor-core (tcgen05) row-MLP forward for sm_100a.
+//
+//   out[b,r,:] = [src_0 +] LN( W2 . SiLU( W1 . concat_s src_s[b, idx_s[r], :] + b1 ) + b2 )
+//
+// A persistent CTA (256 threads) loops over tiles of 128 rows:
+//   gather   fp32 rows (128-bit coalesced loads, per-source row index) -> bf16,
+//            written straight into the UMMA A-operand layout (K-major, 128B swizzle)
+//   GEMM 1   tcgen05.mma M=128 x N=d_hidden x K, accumulator in TMEM  (one thread issues)
+//   epi 1    tcgen05.ld -> +b1 -> SiLU -> bf16 -> A operand of GEMM 2 (shared memory)
+//   GEMM 2   tcgen05.mma into a second TMEM accumulator
+//   epi 2    tcgen05.ld -> +b2 -> LayerNorm (thread owns a half row; two-pass,
+//            partial sums exchanged through shared memory) -> fp32 staging tile
+//   store    coalesced 128-bit row stores (+ fp32 residual re-read from global)
+// W1/W2 are converted to bf16 once per CTA and stay resident in shared memory;
+// the hidden activations never touch HBM.  Two CTAs per SM (d <= 64) overlap
+// one tile's gather/store with the other's MMA/epilogue.
+//
+// Reference semantics: utils.make_mlp (utils.py:191-214), InteractionNet.message /
+// aggr_mlp (interaction_net.py:106,117-121), SplitMLPs (:134-163).
+#include "rowmlp_common.cuh"
+#include "tc_common.cuh"
+
+namespace nlam {
+namespace tc {
+
+constexpr int TM = 128;  // rows per tile == UMMA M
+constexpr int NT = 256;
+
+struct Geo {
+  int n1, n2;          // padded d_hidden / d_out (16, 32, 64 or 128)
+  int k1;              // K of GEMM 1 padded to 16
+  int k2;              // K of GEMM 2 (= d_hidden padded to 16)
+  int kb1, kb2;        // 64-wide K blocks
+  int tmem_cols;       // power of two >= 32
+  int stg_ld;          // floats per staging row (n2 + 4)
+  uint32_t off_w1, off_w2, off_par, off_lnx, off_bar;  // byte offsets
+  uint32_t smem_bytes;
+  int total_tiles;     // batch * tiles
+  int tiles_per_batch;
+};
+
+__device__ __forceinline__ float silu_fast(float x) { return __fdividef(x, 1.0f + __expf(-x)); }
+
+// W[n][k] fp32 (nn.Linear layout) -> bf16 K-major SW128 blocks of [n_pad rows][64]
+__device__ void stage_weight(const float* __restrict__ W, int n_real, int k_real, int n_pad,
+                             int k_pad, uint8_t* dst) {
+  const int nch = k_pad >> 3;
+  const uint32_t blk = (uint32_t)n_pad * 128u;
+  for (int u = threadIdx.x; u < n_pad * nch; u += NT) {
+    const int n = u / nch, c = u % nch, k0 = c * 8;
+    float v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+      v[j] = (n < n_real && k0 + j < k_real) ? __ldg(W + (size_t)n * k_real + k0 + j) : 0.f;
+    uint4 pk = make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]),
+                          pack_bf16(v[6], v[7]));
+    *reinterpret_cast<uint4*>(dst + sw128_off(n, k0, blk)) = pk;
+  }
+}
+
+__global__ void __launch_bounds__(NT, 2)
+rowmlp_tc_fwd_kernel(const __grid_constant__ KParams p, const __grid_constant__ Geo g) {
+  extern __shared__ __align__(1024) uint8_t sm[];
+  if (smem_u32(sm) & 1023u) __trap();  // SWIZZLE_128B operands need 1024-byte alignment
+  // region 0 is time-shared: A operand of GEMM 1 -> A operand of GEMM 2 ->
+  // fp32 staging tile + LayerNorm exchange buffer
+  uint8_t* sA = sm;
+  uint8_t* sA2 = sm;
+  uint8_t* sW1 = sm + g.off_w1;
+  uint8_t* sW2 = sm + g.off_w2;
+  float* sPar = reinterpret_cast<float*>(sm + g.off_par);  // b1[n1] b2[n2] gamma[n2] beta[n2]
+  float* sLnx = reinterpret_cast<float*>(sm + g.off_lnx);  // [2][TM][2]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sm + g.off_bar);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2);
+  float* stg = reinterpret_cast<float*>(sA);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int dh = p.d.d_hidden, dout = p.d.d_out;
+
+  if (warp == 0) tmem_alloc(tmem_slot, (uint32_t)g.tmem_cols);
+  if (tid == 32) {
+    mbar_init(&bars[0], 1);
+    mbar_init(&bars[1], 1);
+    mbar_fence_init();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tH = tmem_base, tY = tmem_base + (uint32_t)g.n1;
+  uint32_t ph0 = 0, ph1 = 0;
+  int loaded_chunk = -1;
+
+  const uint32_t idesc1 = make_idesc_bf16(TM, g.n1);
+  const uint32_t idesc2 = make_idesc_bf16(TM, g.n2);
+  const uint32_t a_blk = TM * 128u;
+  const int nch1 = g.k1 >> 3;
+
+  // epilogue ownership: TMEM lane quarter q, row r, column half hf
+  const int q = warp & 3, hf = warp >> 2, r = q * 32 + lane;
+  const int cp1 = g.n1 >= 32 ? g.n1 / 2 : g.n1, cp2 = g.n2 >= 32 ? g.n2 / 2 : g.n2;
+  const bool act1 = g.n1 >= 32 || hf == 0, act2 = g.n2 >= 32 || hf == 0;
+  const bool split2 = g.n2 >= 32;
+  const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
+
+  for (int t = blockIdx.x; t < g.total_tiles; t += gridDim.x) {
+    const int b = t / g.tiles_per_batch, tile = t % g.tiles_per_batch;
+    int row0, cnt, chunk;
+    tile_range<TM>(p.d, tile, row0, cnt, chunk);
+
+    if (chunk != loaded_chunk) {  // (re)load the weight set of this chunk
+      stage_weight(p.d.w.w1 + (size_t)chunk * dh * p.k_total, dh, p.k_total, g.n1, g.k1, sW1);
+      stage_weight(p.d.w.w2 + (size_t)chunk * dout * dh, dout, dh, g.n2, g.k2, sW2);
+      for (int i = tid; i < g.n1 + 3 * g.n2; i += NT) {
+        float v = 0.f;
+        if (i < g.n1) {
+          if (i < dh) v = __ldg(p.d.w.b1 + (size_t)chunk * dh + i);
+        } else {
+          const int j = (i - g.n1) % g.n2, which = (i - g.n1) / g.n2;
+          if (j < dout) {
+            if (which == 0) v = __ldg(p.d.w.b2 + (size_t)chunk * dout + j);
+            if (which == 1) v = p.d.w.ln_g ? __ldg(p.d.w.ln_g + (size_t)chunk * dout + j) : 1.f;
+            if (which == 2) v = p.d.w.ln_g ? __ldg(p.d.w.ln_b + (size_t)chunk * dout + j) : 0.f;
+          }
+        }
+        sPar[i] = v;
+      }
+      loaded_chunk = chunk;
+    }
+
+    // ---------------- gather: fp32 rows -> bf16 A operand
+    for (int u = tid; u < TM * nch1; u += NT) {
+      const int row = u / nch1, k0 = (u % nch1) * 8;
+      float v[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] = 0.f;
+      if (row < cnt && k0 < p.k_total) {
+        int s = 0;
+        while (s + 1 < p.d.n_src && k0 >= p.koff[s + 1]) ++s;
+        const nlam_src& src = p.d.src[s];
+        const int col = k0 - p.koff[s];
+        const int ridx = src.idx ? __ldg(src.idx + row0 + row) : row0 + row;
+        const float* rp = src.ptr + (long long)b * src.batch_stride + (long long)ridx * src.ld + col;
+        if (p.vec_ok[s] && col + 8 <= src.width) {
+          const float4 x = __ldg(reinterpret_cast<const float4*>(rp));
+          const float4 y = __ldg(reinterpret_cast<const float4*>(rp) + 1);
+          v[0] = x.x, v[1] = x.y, v[2] = x.z, v[3] = x.w;
+          v[4] = y.x, v[5] = y.y, v[6] = y.z, v[7] = y.w;
+        } else {
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            if (col + j < src.width) v[j] = __ldg(rp + j);
+        }
+      }
+      uint4 pk = make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]),
+                            pack_bf16(v[6], v[7]));
+      *reinterpret_cast<uint4*>(sA + sw128_off(row, k0, a_blk)) = pk;
+    }
+    fence_async_smem();
+    __syncthreads();
+
+    // ---------------- GEMM 1: H = A . W1^T
+    if (tid == 0) {
+      tc_fence_after();
+      const uint32_t a0 = smem_u32(sA), w0 = smem_u32(sW1);
+      const uint32_t w_blk = (uint32_t)g.n1 * 128u;
+      for (int ks = 0; ks < g.k1 / 16; ++ks) {
+        const uint32_t kb = ks >> 2, kin = (ks & 3) * 32;
+        umma_bf16(tH, make_desc_k_sw128(a0 + kb * a_blk + kin),
+                  make_desc_k_sw128(w0 + kb * w_blk + kin), idesc1, ks > 0);
+      }
+      umma_commit(&bars[0]);
+    }
+    mbar_wait(&bars[0], ph0);
+    ph0 ^= 1;
+    tc_fence_after();
+
+    // ---------------- epilogue 1: a = SiLU(H + b1) -> bf16 A2
+    if (act1) {
+      for (int cc = 0; cc < cp1; cc += 16) {
+        const int c0 = hf * cp1 + cc;
+        float v[16];
+        tmem_ld16(tH + lane_addr + (uint32_t)c0, v);
+#pragma unroll
+        for (int j = 0; j < 16; ++j) v[j] = silu_fast(v[j] + sPar[c0 + j]);
+#pragma unroll
+        for (int h8 = 0; h8 < 2; ++h8) {
+          uint4 pk = make_uint4(pack_bf16(v[h8 * 8 + 0], v[h8 * 8 + 1]),
+                                pack_bf16(v[h8 * 8 + 2], v[h8 * 8 + 3]),
+                                pack_bf16(v[h8 * 8 + 4], v[h8 * 8 + 5]),
+                                pack_bf16(v[h8 * 8 + 6], v[h8 * 8 + 7]));
+          *reinterpret_cast<uint4*>(sA2 + sw128_off(r, c0 + h8 * 8, a_blk)) = pk;
+        }
+      }
+    }
+    fence_async_smem();
+    tc_fence_before();
+    __syncthreads();
+
+    // ---------------- GEMM 2: Y = A2 . W2^T
+    if (tid == 0) {
+      tc_fence_after();
+      const uint32_t a0 = smem_u32(sA2), w0 = smem_u32(sW2);
+      const uint32_t w_blk = (uint32_t)g.n2 * 128u;
+      for (int ks = 0; ks < g.k2 / 16; ++ks) {
+        const uint32_t kb = ks >> 2, kin = (ks & 3) * 32;
+        umma_bf16(tY, make_desc_k_sw128(a0 + kb * a_blk + kin),
+                  make_desc_k_sw128(w0 + kb * w_blk + kin), idesc2, ks > 0);
+      }
+      umma_commit(&bars[1]);
+    }
+    mbar_wait(&bars[1], ph1);
+    ph1 ^= 1;
+    tc_fence_after();
+
+    // ---------------- epilogue 2: y + b2 -> LayerNorm -> fp32 staging tile
+    const float* sB2 = sPar + g.n1;
+    const float* sG = sB2 + g.n2;
+    const float* sBe = sG + g.n2;
+    float mean = 0.f, rstd = 1.f;
+    if (p.d.w.ln_g) {
+      float s = 0.f;
+      if (act2)
+        for (int cc = 0; cc < cp2; cc += 16) {
+          const int c0 = hf * cp2 + cc;
+          float v[16];
+          tmem_ld16(tY + lane_addr + (uint32_t)c0, v);
+#pragma unroll
+          for (int j = 0; j < 16; ++j)
+            if (c0 + j < dout) s += v[j] + sB2[c0 + j];
+        }
+      sLnx[(0 * TM + r) * 2 + hf] = s;
+      __syncthreads();
+      mean = (sLnx[(0 * TM + r) * 2] + (split2 ? sLnx[(0 * TM + r) * 2 + 1] : 0.f)) / (float)dout;
+      float qq = 0.f;
+      if (act2)
+        for (int cc = 0; cc < cp2; cc += 16) {
+          const int c0 = hf * cp2 + cc;
+          float v[16];
+          tmem_ld16(tY + lane_addr + (uint32_t)c0, v);
+#pragma unroll
+          for (int j = 0; j < 16; ++j)
+            if (c0 + j < dout) {
+              const float dl = v[j] + sB2[c0 + j] - mean;
+              qq += dl * dl;
+            }
+        }
+      sLnx[(1 * TM + r) * 2 + hf] = qq;
+      __syncthreads();
+      const float var =
+          (sLnx[(1 * TM + r) * 2] + (split2 ? sLnx[(1 * TM + r) * 2 + 1] : 0.f)) / (float)dout;
+      rstd = rsqrtf(var + LN_EPS);
+    }
+    if (act2)
+      for (int cc = 0; cc < cp2; cc += 16) {
+        const int c0 = hf * cp2 + cc;
+        float v[16];
+        tmem_ld16(tY + lane_addr + (uint32_t)c0, v);
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          float y = v[j] + sB2[c0 + j];
+          if (p.d.w.ln_g) y = (y - mean) * rstd * sG[c0 + j] + sBe[c0 + j];
+          v[j] = y;
+        }
+        float4* dst = reinterpret_cast<float4*>(stg + (size_t)r * g.stg_ld + c0);
+#pragma unroll
+        for (int j4 = 0; j4 < 4; ++j4)
+          dst[j4] = make_float4(v[j4 * 4], v[j4 * 4 + 1], v[j4 * 4 + 2], v[j4 * 4 + 3]);
+      }
+    tc_fence_before();
+    __syncthreads();
+
+    // ---------------- coalesced store (+ fp32 residual)
+    {
+      float* out = p.d.out + ((size_t)b * p.d.rows + row0) * dout;
+      const nlam_src& s0 = p.d.src[0];
+      const bool res = p.d.residual_src == 0;
+      if (p.out_vec_ok && (!res || p.vec_ok[0])) {
+        const int w4 = dout >> 2;
+        for (int u = tid; u < cnt * w4; u += NT) {
+          const int row = u / w4, c4 = u % w4;
+          float4 v = *reinterpret_cast<const float4*>(stg + (size_t)row * g.stg_ld + c4 * 4);
+          if (res) {
+            const int ridx = s0.idx ? __ldg(s0.idx + row0 + row) : row0 + row;
+            const float4 e = __ldg(reinterpret_cast<const float4*>(
+                                       s0.ptr + (long long)b * s0.batch_stride +
+                                       (long long)ridx * s0.ld) + c4);
+            v.x += e.x, v.y += e.y, v.z += e.z, v.w += e.w;
+          }
+          *reinterpret_cast<float4*>(out + (size_t)row * dout + c4 * 4) = v;
+        }
+      } else {
+        for (int u = tid; u < cnt * dout; u += NT) {
+          const int row = u / dout, c = u % dout;
+          float v = stg[(size_t)row * g.stg_ld + c];
+          if (res) {
+            const int ridx = s0.idx ? __ldg(s0.idx + row0 + row) : row0 + row;
+            v += __ldg(s0.ptr + (long long)b * s0.batch_stride + (long long)ridx * s0.ld + c);
+          }
+          out[(size_t)row * dout + c] = v;
+        }
+      }
+    }
+    __syncthreads();  // staging (aliases A) is free again
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem_base, (uint32_t)g.tmem_cols);
+}
+
+static int pad_n(int n) { return n <= 16 ? 16 : n <= 32 ? 32 : n <= 64 ? 64 : n <= 128 ? 128 : -1; }
+
+// Can the tensor-core path take this problem?  (else: fp32 FFMA path)
+bool tc_supported(const nlam_rowmlp& d) {
+  if (pad_n(d.d_hidden) < 0 || pad_n(d.d_out) < 0) return false;
+  int k = 0;
+  for (int s = 0; s < d.n_src; ++s) {
+    if (d.n_src > 1 && d.src[s].width % 8 != 0) return false;
+    k += d.src[s].width;
+  }
+  return k <= 384;
+}
+
+int make_geo(const KParams& p, Geo& g) {
+  const nlam_rowmlp& d = p.d;
+  g.n1 = pad_n(d.d_hidden), g.n2 = pad_n(d.d_out);
+  g.k1 = (p.k_total + 15) / 16 * 16;
+  g.k2 = (d.d_hidden + 15) / 16 * 16;
+  g.kb1 = (g.k1 + 63) / 64, g.kb2 = (g.k2 + 63) / 64;
+  int cols = g.n1 + g.n2;
+  g.tmem_cols = 32;
+  while (g.tmem_cols < cols) g.tmem_cols *= 2;
+  g.stg_ld = g.n2 + 4;
+  const uint32_t a_bytes = (uint32_t)g.kb1 * TM * 128u;
+  const uint32_t a2_bytes = (uint32_t)g.kb2 * TM * 128u;
+  const uint32_t stg_bytes = (uint32_t)TM * g.stg_ld * 4u;
+  const uint32_t lnx_bytes = 2u * TM * 2u * 4u;
+  uint32_t r0 = a_bytes > a2_bytes ? a_bytes : a2_bytes;
+  if (stg_bytes + lnx_bytes > r0) r0 = stg_bytes + lnx_bytes;
+  auto al = [](uint32_t x) { return (x + 1023u) & ~1023u; };
+  g.off_lnx = stg_bytes;
+  uint32_t o = al(r0);
+  g.off_w1 = o, o += al((uint32_t)g.kb1 * g.n1 * 128u);
+  g.off_w2 = o, o += al((uint32_t)g.kb2 * g.n2 * 128u);
+  g.off_par = o, o += (uint32_t)(g.n1 + 3 * g.n2) * 4u;
+  g.off_bar = o, o += 64;
+  g.smem_bytes = o;
+  g.tiles_per_batch = n_tiles_of(d, TM);
+  g.total_tiles = g.tiles_per_batch * d.batch;
+  NLAM_CHECK(g.smem_bytes <= 232448, "rowmlp(bf16): needs %u bytes of shared memory", g.smem_bytes);
+  return 0;
+}
+
+}  // namespace tc
+
+int tc_rowmlp_fwd(const nlam_rowmlp& d, cudaStream_t st) {
+  KParams p{};
+  if (fill_params(d, p)) return 1;
+  if (d.rows == 0) return 0;
+  NLAM_CHECK(d.out, "rowmlp: out is NULL");
+  tc::Geo g{};
+  if (tc::make_geo(p, g)) return 1;
+  static int max_set = 0;
+  if ((int)g.smem_bytes > max_set) {
+    NLAM_CUDA(cudaFuncSetAttribute(tc::rowmlp_tc_fwd_kernel,
+                                   cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem_bytes));
+    max_set = (int)g.smem_bytes;
+  }
+  int per_sm = g.smem_bytes <= 113 * 1024 ? 2 : 1;
+  if (g.tmem_cols * per_sm > 512) per_sm = 1;
+  int grid = 148 * per_sm;
+  if (grid > g.total_tiles) grid = g.total_tiles;
+  tc::rowmlp_tc_fwd_kernel<<<grid, tc::NT, g.smem_bytes, st>>>(p, g);
+  NLAM_CUDA(cudaGetLastError());
+  count_launch();
+  return 0;
+}
+
+}  // namespace nlam
