@@ -17,14 +17,10 @@
 //
 // Reference semantics: utils.make_mlp (utils.py:191-214), InteractionNet.message /
 // aggr_mlp (interaction_net.py:106,117-121), SplitMLPs (:134-163).
-#include "rowmlp_common.cuh"
-#include "tc_common.cuh"
+#include "rowmlp_tc.cuh"
 
 namespace nlam {
 namespace tc {
-
-constexpr int TM = 128;  // rows per tile == UMMA M
-constexpr int NT = 256;
 
 struct Geo {
   int n1, n2;          // padded d_hidden / d_out (16, 32, 64 or 128)
@@ -38,25 +34,6 @@ struct Geo {
   int total_tiles;     // batch * tiles
   int tiles_per_batch;
 };
-
-__device__ __forceinline__ float silu_fast(float x) { return __fdividef(x, 1.0f + __expf(-x)); }
-
-// W[n][k] fp32 (nn.Linear layout) -> bf16 K-major SW128 blocks of [n_pad rows][64]
-__device__ void stage_weight(const float* __restrict__ W, int n_real, int k_real, int n_pad,
-                             int k_pad, uint8_t* dst) {
-  const int nch = k_pad >> 3;
-  const uint32_t blk = (uint32_t)n_pad * 128u;
-  for (int u = threadIdx.x; u < n_pad * nch; u += NT) {
-    const int n = u / nch, c = u % nch, k0 = c * 8;
-    float v[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j)
-      v[j] = (n < n_real && k0 + j < k_real) ? __ldg(W + (size_t)n * k_real + k0 + j) : 0.f;
-    uint4 pk = make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]),
-                          pack_bf16(v[6], v[7]));
-    *reinterpret_cast<uint4*>(dst + sw128_off(n, k0, blk)) = pk;
-  }
-}
 
 __global__ void __launch_bounds__(NT, 2)
 rowmlp_tc_fwd_kernel(const __grid_constant__ KParams p, const __grid_constant__ Geo g) {
@@ -111,51 +88,12 @@ rowmlp_tc_fwd_kernel(const __grid_constant__ KParams p, const __grid_constant__ 
     if (chunk != loaded_chunk) {  // (re)load the weight set of this chunk
       stage_weight(p.d.w.w1 + (size_t)chunk * dh * p.k_total, dh, p.k_total, g.n1, g.k1, sW1);
       stage_weight(p.d.w.w2 + (size_t)chunk * dout * dh, dout, dh, g.n2, g.k2, sW2);
-      for (int i = tid; i < g.n1 + 3 * g.n2; i += NT) {
-        float v = 0.f;
-        if (i < g.n1) {
-          if (i < dh) v = __ldg(p.d.w.b1 + (size_t)chunk * dh + i);
-        } else {
-          const int j = (i - g.n1) % g.n2, which = (i - g.n1) / g.n2;
-          if (j < dout) {
-            if (which == 0) v = __ldg(p.d.w.b2 + (size_t)chunk * dout + j);
-            if (which == 1) v = p.d.w.ln_g ? __ldg(p.d.w.ln_g + (size_t)chunk * dout + j) : 1.f;
-            if (which == 2) v = p.d.w.ln_g ? __ldg(p.d.w.ln_b + (size_t)chunk * dout + j) : 0.f;
-          }
-        }
-        sPar[i] = v;
-      }
+      stage_params(p.d, chunk, g.n1, g.n2, sPar);
       loaded_chunk = chunk;
     }
 
     // ---------------- gather: fp32 rows -> bf16 A operand
-    for (int u = tid; u < TM * nch1; u += NT) {
-      const int row = u / nch1, k0 = (u % nch1) * 8;
-      float v[8];
-#pragma unroll
-      for (int j = 0; j < 8; ++j) v[j] = 0.f;
-      if (row < cnt && k0 < p.k_total) {
-        int s = 0;
-        while (s + 1 < p.d.n_src && k0 >= p.koff[s + 1]) ++s;
-        const nlam_src& src = p.d.src[s];
-        const int col = k0 - p.koff[s];
-        const int ridx = src.idx ? __ldg(src.idx + row0 + row) : row0 + row;
-        const float* rp = src.ptr + (long long)b * src.batch_stride + (long long)ridx * src.ld + col;
-        if (p.vec_ok[s] && col + 8 <= src.width) {
-          const float4 x = __ldg(reinterpret_cast<const float4*>(rp));
-          const float4 y = __ldg(reinterpret_cast<const float4*>(rp) + 1);
-          v[0] = x.x, v[1] = x.y, v[2] = x.z, v[3] = x.w;
-          v[4] = y.x, v[5] = y.y, v[6] = y.z, v[7] = y.w;
-        } else {
-#pragma unroll
-          for (int j = 0; j < 8; ++j)
-            if (col + j < src.width) v[j] = __ldg(rp + j);
-        }
-      }
-      uint4 pk = make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]),
-                            pack_bf16(v[6], v[7]));
-      *reinterpret_cast<uint4*>(sA + sw128_off(row, k0, a_blk)) = pk;
-    }
+    gather_rows(p, b, row0, cnt, 0, g.k1, sA);
     fence_async_smem();
     __syncthreads();
 
@@ -309,7 +247,6 @@ rowmlp_tc_fwd_kernel(const __grid_constant__ KParams p, const __grid_constant__ 
   if (warp == 0) tmem_dealloc(tmem_base, (uint32_t)g.tmem_cols);
 }
 
-static int pad_n(int n) { return n <= 16 ? 16 : n <= 32 ? 32 : n <= 64 ? 64 : n <= 128 ? 128 : -1; }
 
 // Can the tensor-core path take this problem?  (else: fp32 FFMA path)
 bool tc_supported(const nlam_rowmlp& d) {

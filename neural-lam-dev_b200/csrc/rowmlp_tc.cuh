@@ -1,0 +1,97 @@
+// Shared pieces of the bf16 tensor-core row-MLP kernels (forward, dgrad, wgrad).
+#pragma once
+#include "rowmlp_common.cuh"
+#include "tc_common.cuh"
+
+namespace nlam {
+namespace tc {
+
+constexpr int TM = 128;  // rows per tile == UMMA M
+constexpr int NT = 256;
+
+
+inline int pad_n(int n) { return n <= 16 ? 16 : n <= 32 ? 32 : n <= 64 ? 64 : n <= 128 ? 128 : -1; }
+
+__device__ __forceinline__ float silu_fast(float x) { return __fdividef(x, 1.0f + __expf(-x)); }
+
+// W[n][k] fp32 (nn.Linear layout) -> bf16 K-major SW128 blocks of [n_pad rows][64]
+__device__ void stage_weight(const float* __restrict__ W, int n_real, int k_real, int n_pad,
+                             int k_pad, uint8_t* dst) {
+  const int nch = k_pad >> 3;
+  const uint32_t blk = (uint32_t)n_pad * 128u;
+  for (int u = threadIdx.x; u < n_pad * nch; u += NT) {
+    const int n = u / nch, c = u % nch, k0 = c * 8;
+    float v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+      v[j] = (n < n_real && k0 + j < k_real) ? __ldg(W + (size_t)n * k_real + k0 + j) : 0.f;
+    uint4 pk = make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]),
+                          pack_bf16(v[6], v[7]));
+    *reinterpret_cast<uint4*>(dst + sw128_off(n, k0, blk)) = pk;
+  }
+}
+
+
+__device__ __forceinline__ float silu_grad_fast(float x) {
+  const float s = __fdividef(1.0f, 1.0f + __expf(-x));
+  return s * (1.0f + x * (1.0f - s));
+}
+
+// fp32 source rows -> bf16 A operand (K-major SW128, 128 rows per 64-wide block).
+// Covers concatenated-input columns [k_begin, k_end) (multiples of 8); the
+// destination block index is relative to k_begin's block.
+__device__ __forceinline__ void gather_rows(const KParams& p, int b, int row0, int cnt,
+                                            int k_begin, int k_end, uint8_t* sA) {
+  const int nch = (k_end - k_begin) >> 3;
+  const uint32_t a_blk = TM * 128u;
+  for (int u = threadIdx.x; u < TM * nch; u += NT) {
+    const int row = u / nch, k0 = k_begin + (u % nch) * 8;
+    float v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = 0.f;
+    if (row < cnt && k0 < p.k_total) {
+      int s = 0;
+      while (s + 1 < p.d.n_src && k0 >= p.koff[s + 1]) ++s;
+      const nlam_src& src = p.d.src[s];
+      const int col = k0 - p.koff[s];
+      const int ridx = src.idx ? __ldg(src.idx + row0 + row) : row0 + row;
+      const float* rp = src.ptr + (long long)b * src.batch_stride + (long long)ridx * src.ld + col;
+      if (p.vec_ok[s] && col + 8 <= src.width) {
+        const float4 x = __ldg(reinterpret_cast<const float4*>(rp));
+        const float4 y = __ldg(reinterpret_cast<const float4*>(rp) + 1);
+        v[0] = x.x, v[1] = x.y, v[2] = x.z, v[3] = x.w;
+        v[4] = y.x, v[5] = y.y, v[6] = y.z, v[7] = y.w;
+      } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          if (col + j < src.width) v[j] = __ldg(rp + j);
+      }
+    }
+    uint4 pk = make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]),
+                          pack_bf16(v[6], v[7]));
+    *reinterpret_cast<uint4*>(sA + sw128_off(row, k0 - (k_begin & ~63), a_blk)) = pk;
+  }
+}
+
+// b1[n1] | b2[n2] | gamma[n2] | beta[n2], zero / identity padded
+__device__ __forceinline__ void stage_params(const nlam_rowmlp& d, int chunk, int n1, int n2,
+                                             float* sPar) {
+  const int dh = d.d_hidden, dout = d.d_out;
+  for (int i = threadIdx.x; i < n1 + 3 * n2; i += NT) {
+    float v = 0.f;
+    if (i < n1) {
+      if (i < dh) v = __ldg(d.w.b1 + (size_t)chunk * dh + i);
+    } else {
+      const int j = (i - n1) % n2, which = (i - n1) / n2;
+      if (j < dout) {
+        if (which == 0) v = __ldg(d.w.b2 + (size_t)chunk * dout + j);
+        if (which == 1) v = d.w.ln_g ? __ldg(d.w.ln_g + (size_t)chunk * dout + j) : 1.f;
+        if (which == 2) v = d.w.ln_g ? __ldg(d.w.ln_b + (size_t)chunk * dout + j) : 0.f;
+      }
+    }
+    sPar[i] = v;
+  }
+}
+
+}  // namespace tc
+}  // namespace nlam
