@@ -37,7 +37,9 @@ extern "C" int nlam_rowmlp_fwd(const nlam_rowmlp* d, void* stream) {
 }
 
 extern "C" size_t nlam_rowmlp_bwd_workspace(const nlam_rowmlp* d) {
-  return d ? simt_rowmlp_bwd_workspace(*d) : 0;
+  if (!d) return 0;
+  if (d->precision == NLAM_BF16 && tc::tc_supported(*d)) return tc_rowmlp_bwd_workspace(*d);
+  return simt_rowmlp_bwd_workspace(*d);
 }
 
 extern "C" size_t nlam_rowmlp_param_floats(const nlam_rowmlp* d) {
@@ -48,6 +50,8 @@ extern "C" size_t nlam_rowmlp_param_floats(const nlam_rowmlp* d) {
 
 extern "C" int nlam_rowmlp_bwd_run(const nlam_rowmlp_bwd* d, void* stream) {
   NLAM_CHECK(d, "rowmlp_bwd: NULL descriptor");
+  if (d->fwd.precision == NLAM_BF16 && tc::tc_supported(d->fwd))
+    return tc_rowmlp_bwd(*d, (cudaStream_t)stream);
   if (d->fwd.precision == NLAM_FP32 || d->fwd.precision == NLAM_BF16)
     return simt_rowmlp_bwd(*d, (cudaStream_t)stream);
   set_error("rowmlp_bwd: unknown precision mode %d", d->fwd.precision);

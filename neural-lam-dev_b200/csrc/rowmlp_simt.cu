@@ -607,6 +607,19 @@ __global__ void reduce_params_kernel(const __grid_constant__ RParams p) {
   p.out[(size_t)chunk * p.p_total + j] = s;
 }
 
+int launch_reduce_params(const float* partial, int splits, int n_chunks, int p_total, float* out,
+                         cudaStream_t st) {
+  RParams rp{};
+  rp.partial = partial, rp.splits = splits, rp.n_chunks = n_chunks;
+  rp.p_total = p_total, rp.p_main = p_total;
+  rp.out = out;
+  dim3 rgrid((p_total + 255) / 256, n_chunks);
+  reduce_params_kernel<<<rgrid, 256, 0, st>>>(rp);
+  NLAM_CUDA(cudaGetLastError());
+  count_launch();
+  return 0;
+}
+
 // -------------------------------------------------------------------- host side
 template <int DP>
 static int launch_fwd(const KParams& p, cudaStream_t st) {

@@ -71,7 +71,6 @@ rowmlp_tc_fwd_kernel(const __grid_constant__ KParams p, const __grid_constant__ 
   const uint32_t idesc1 = make_idesc_bf16(TM, g.n1);
   const uint32_t idesc2 = make_idesc_bf16(TM, g.n2);
   const uint32_t a_blk = TM * 128u;
-  const int nch1 = g.k1 >> 3;
 
   // epilogue ownership: TMEM lane quarter q, row r, column half hf
   const int q = warp & 3, hf = warp >> 2, r = q * 32 + lane;

@@ -15,7 +15,7 @@ inline int pad_n(int n) { return n <= 16 ? 16 : n <= 32 ? 32 : n <= 64 ? 64 : n 
 __device__ __forceinline__ float silu_fast(float x) { return __fdividef(x, 1.0f + __expf(-x)); }
 
 // W[n][k] fp32 (nn.Linear layout) -> bf16 K-major SW128 blocks of [n_pad rows][64]
-__device__ void stage_weight(const float* __restrict__ W, int n_real, int k_real, int n_pad,
+__device__ __forceinline__ void stage_weight(const float* __restrict__ W, int n_real, int k_real, int n_pad,
                              int k_pad, uint8_t* dst) {
   const int nch = k_pad >> 3;
   const uint32_t blk = (uint32_t)n_pad * 128u;
@@ -75,9 +75,9 @@ __device__ __forceinline__ void gather_rows(const KParams& p, int b, int row0, i
 
 // b1[n1] | b2[n2] | gamma[n2] | beta[n2], zero / identity padded
 __device__ __forceinline__ void stage_params(const nlam_rowmlp& d, int chunk, int n1, int n2,
-                                             float* sPar) {
+                                             float* sPar, int n_vec = 3) {
   const int dh = d.d_hidden, dout = d.d_out;
-  for (int i = threadIdx.x; i < n1 + 3 * n2; i += NT) {
+  for (int i = threadIdx.x; i < n1 + n_vec * n2; i += NT) {
     float v = 0.f;
     if (i < n1) {
       if (i < dh) v = __ldg(d.w.b1 + (size_t)chunk * dh + i);

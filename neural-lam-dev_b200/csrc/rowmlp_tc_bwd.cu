@@ -1,0 +1,799 @@
+// bf16 tensor-core (tcgen05) row-MLP BACKWARD for sm_100a: two kernels.
+//
+// dgrad (per 128-row tile, recompute-based -- only layer inputs were saved):
+//   gather z -> GEMM1 (H) -> a = SiLU(H+b1)            [a tile -> HBM image]
+//   GEMM2 (Y) -> LayerNorm stats, dOut rows (fp32, staged coalesced) ->
+//   dY = LN'(dOut)                                       [dY tile -> HBM image]
+//   GEMM3: dA = dY . W2   (W2 tile re-used as MN-major B operand)
+//   dH = dA * SiLU'(H+b1)                                [dH tile -> HBM image]
+//   GEMM4: dZ = dH . W1   (W1 blocks re-used as MN-major B), 64 input columns
+//   at a time, double-buffered in TMEM; rows stored coalesced per source.
+//   Column sums for db1, db2, dLN gamma/beta: 16-shuffle warp transposes of the
+//   fp32 epilogue registers, accumulated per CTA across tiles (no atomics).
+// wgrad (per tile): dW1^T += z^T . dH, dW2^T += a^T . dY as M=128 UMMAs whose
+//   A/B operands are the SAME bf16 tiles viewed MN-major; fp32 accumulators stay
+//   in TMEM across all tiles of a persistent CTA, then go to a per-CTA partial
+//   that a fixed-order reduction sums (deterministic).
+//
+// Reference: autograd of utils.make_mlp / InteractionNet.message / aggr_mlp
+// (utils.py:191-214, interaction_net.py:106,117-121).
+#include "rowmlp_tc.cuh"
+
+namespace nlam {
+
+// defined in rowmlp_simt.cu
+int launch_reduce_params(const float* partial, int splits, int n_chunks, int p_total,
+                         float* out, cudaStream_t st);
+
+namespace tc {
+
+struct BGeo {
+  int n1, n2, nmax;
+  int k1, k2, ko;        // K of GEMM1 (pad 16), GEMM2 (= pad16(dh)), GEMM3 (= pad16(dout))
+  int kb1, kb2, kbo;     // 64-wide blocks of z, of the hidden tile, of the dY tile
+  int rb;                // z blocks gathered per round
+  int tmem_cols, cY, cZ;
+  uint32_t off_t, off_w1, off_w2, off_par, off_lnx, off_bar, smem_bytes;
+  int total_tiles, tiles_per_batch;
+  int need_dz;           // any source gradient requested
+  // scratch
+  uint8_t* a_img;
+  uint8_t* dy_img;
+  uint8_t* dh_img;
+  float* partial;        // [slots][n_chunks][p_total]
+  int p_total;
+  // wgrad
+  int w_tmem_cols, w_mchunks;
+  uint32_t w_off_a, w_off_dy, w_off_dh, w_off_bar, w_smem_bytes;
+};
+
+// swizzled fp32 staging tile [128][n] (n multiple of 16): 16-byte chunk c4 of row r
+__device__ __forceinline__ int stg_idx(int r, int c4, int n) {
+  const int nc = n >> 2;
+  const int m = (nc < 8 ? nc : 8) - 1;
+  return r * n + ((c4 ^ (r & m)) << 2);
+}
+
+// Column sums over the 32 lanes of a warp of a 16-column chunk held one row per
+// lane; lane l ends up with the total of column (l & 15).  16 shuffles.
+__device__ __forceinline__ float warp_colsum16(const float (&v)[16], int lane) {
+  float w8[8], w4[4], w2[2];
+  const bool b3 = lane & 8, b2 = lane & 4, b1 = lane & 2, b0 = lane & 1;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const float send = b3 ? v[i] : v[i + 8];
+    const float recv = __shfl_xor_sync(0xffffffffu, send, 8);
+    w8[i] = (b3 ? v[i + 8] : v[i]) + recv;
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float send = b2 ? w8[i] : w8[i + 4];
+    const float recv = __shfl_xor_sync(0xffffffffu, send, 4);
+    w4[i] = (b2 ? w8[i + 4] : w8[i]) + recv;
+  }
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const float send = b1 ? w4[i] : w4[i + 2];
+    const float recv = __shfl_xor_sync(0xffffffffu, send, 2);
+    w2[i] = (b1 ? w4[i + 2] : w4[i]) + recv;
+  }
+  const float send = b0 ? w2[0] : w2[1];
+  const float recv = __shfl_xor_sync(0xffffffffu, send, 1);
+  float w1 = (b0 ? w2[1] : w2[0]) + recv;
+  w1 += __shfl_xor_sync(0xffffffffu, w1, 16);
+  return w1;
+}
+
+// MN-major SW128 descriptor: tile stored [K rows][64 MN elements] (128-byte
+// rows, same physical layout as the K-major tiles), 8-row K groups 1024 B apart
+// (SBO), 64-element MN blocks `lbo_bytes` apart (LBO).
+__device__ __forceinline__ uint64_t make_desc_mn_sw128(uint32_t smem_addr, uint32_t lbo_bytes) {
+  return (uint64_t)((smem_addr >> 4) & 0x3FFF) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16) |
+         (64ull << 32) | (1ull << 46) | (2ull << 61);
+}
+
+__device__ __forceinline__ void copy_tile_out(const uint8_t* s, uint8_t* g, int bytes) {
+  const uint4* src = reinterpret_cast<const uint4*>(s);
+  uint4* dst = reinterpret_cast<uint4*>(g);
+  for (int i = threadIdx.x; i < bytes / 16; i += NT) dst[i] = src[i];
+}
+__device__ __forceinline__ void copy_tile_in(const uint8_t* g, uint8_t* s, int bytes) {
+  const uint4* src = reinterpret_cast<const uint4*>(g);
+  uint4* dst = reinterpret_cast<uint4*>(s);
+  for (int i = threadIdx.x; i < bytes / 16; i += NT) dst[i] = __ldg(src + i);
+}
+
+constexpr int MAXCH = 4;  // 16-column chunks per thread (n <= 128, two column halves)
+
+__global__ void __launch_bounds__(NT, 2)
+rowmlp_tc_dgrad_kernel(const __grid_constant__ KParams p, const __grid_constant__ BGeo g) {
+  extern __shared__ __align__(1024) uint8_t sm[];
+  if (smem_u32(sm) & 1023u) __trap();
+  uint8_t* sA = sm;                     // z blocks of one gather round | fp32 staging
+  float* stg = reinterpret_cast<float*>(sm);
+  uint8_t* sT = sm + g.off_t;           // a -> dY -> dH bf16 tile
+  uint8_t* sW1 = sm + g.off_w1;
+  uint8_t* sW2 = sm + g.off_w2;
+  float* sPar = reinterpret_cast<float*>(sm + g.off_par);
+  float* sLnx = reinterpret_cast<float*>(sm + g.off_lnx);  // [TM][2]
+  float* sRed = reinterpret_cast<float*>(sm + g.off_t);    // [8 warps][4][64], aliases sT
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sm + g.off_bar);  // [0] main, [1],[2] dZ
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int dh = p.d.d_hidden, dout = p.d.d_out;
+  const bool has_ln = p.d.w.ln_g != nullptr;
+
+  if (warp == 0) tmem_alloc(tmem_slot, (uint32_t)g.tmem_cols);
+  if (tid == 32) {
+    mbar_init(&bars[0], 1);
+    mbar_init(&bars[1], 1);
+    mbar_init(&bars[2], 1);
+    mbar_fence_init();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tH = tmem_base, tY = tmem_base + (uint32_t)g.cY, tZ = tmem_base + (uint32_t)g.cZ;
+  uint32_t ph_main = 0, ph_z = 0;
+  int loaded_chunk = -1;
+
+  const uint32_t a_blk = TM * 128u;
+  const uint32_t idesc1 = make_idesc_bf16(TM, g.n1);
+  const uint32_t idesc2 = make_idesc_bf16(TM, g.n2);
+  const uint32_t idesc3 = make_idesc_bf16(TM, g.n1, 0, 1);  // B = W2 viewed MN-major
+  const uint32_t idesc4 = make_idesc_bf16(TM, 64, 0, 1);    // B = W1 block viewed MN-major
+
+  const int q = warp & 3, hf = warp >> 2, r = q * 32 + lane;
+  const int cp1 = g.n1 >= 32 ? g.n1 / 2 : g.n1, cp2 = g.n2 >= 32 ? g.n2 / 2 : g.n2;
+  const bool act1 = g.n1 >= 32 || hf == 0, act2 = g.n2 >= 32 || hf == 0;
+  const bool split2 = g.n2 >= 32;
+  const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
+  const float* sB2 = sPar + g.n1;
+  const float* sG = sB2 + g.n2;
+
+  // per-CTA column-sum accumulators (lane l owns column c0 + (l & 15) of each chunk)
+  float acc_db1[MAXCH], acc_db2[MAXCH], acc_dg[MAXCH], acc_dbt[MAXCH];
+#pragma unroll
+  for (int i = 0; i < MAXCH; ++i) acc_db1[i] = acc_db2[i] = acc_dg[i] = acc_dbt[i] = 0.f;
+
+  auto flush_colsums = [&](int chunk) {
+    // sRed[warp][which][col in half]; quarters q = 0..3 are summed in fixed order
+    __syncthreads();
+    if (lane < 16) {
+#pragma unroll
+      for (int i = 0; i < MAXCH; ++i) {
+        sRed[(warp * 4 + 0) * 64 + i * 16 + lane] = acc_db1[i];
+        sRed[(warp * 4 + 1) * 64 + i * 16 + lane] = acc_db2[i];
+        sRed[(warp * 4 + 2) * 64 + i * 16 + lane] = acc_dg[i];
+        sRed[(warp * 4 + 3) * 64 + i * 16 + lane] = acc_dbt[i];
+      }
+    }
+    __syncthreads();
+    const ParamLayout lay = p.lay;
+    float* dst = g.partial + ((size_t)blockIdx.x * p.d.n_chunks + chunk) * g.p_total;
+    // which: 0 db1 (n1 cols), 1 db2, 2 dgamma, 3 dbeta (n2 cols)
+    for (int e = tid; e < 4 * 128; e += NT) {
+      const int which = e >> 7, col = e & 127;
+      const int n = which == 0 ? g.n1 : g.n2, cp = which == 0 ? cp1 : cp2;
+      const int real = which == 0 ? dh : dout;
+      if (col >= n || col >= real) continue;
+      if (which >= 2 && !has_ln) continue;
+      const int h = col / cp, cc = col % cp;  // column half and offset inside it
+      float s = 0.f;
+#pragma unroll
+      for (int qq = 0; qq < 4; ++qq) s += sRed[((h * 4 + qq) * 4 + which) * 64 + cc];
+      const int off = which == 0 ? lay.off_b1() : which == 1 ? lay.off_b2()
+                    : which == 2 ? lay.off_lng() : lay.off_lnb();
+      dst[off + col] = s;
+    }
+#pragma unroll
+    for (int i = 0; i < MAXCH; ++i) acc_db1[i] = acc_db2[i] = acc_dg[i] = acc_dbt[i] = 0.f;
+  };
+
+  for (int t = blockIdx.x; t < g.total_tiles; t += gridDim.x) {
+    const int b = t / g.tiles_per_batch, tile = t % g.tiles_per_batch;
+    int row0, cnt, chunk;
+    tile_range<TM>(p.d, tile, row0, cnt, chunk);
+    const size_t grow0 = (size_t)b * p.d.rows + row0;
+
+    if (chunk != loaded_chunk) {
+      if (loaded_chunk >= 0) flush_colsums(loaded_chunk);
+      stage_weight(p.d.w.w1 + (size_t)chunk * dh * p.k_total, dh, p.k_total, g.n1, g.k1, sW1);
+      stage_weight(p.d.w.w2 + (size_t)chunk * dout * dh, dout, dh, g.n2, g.k2, sW2);
+      stage_params(p.d, chunk, g.n1, g.n2, sPar, 2);  // beta is not needed backward
+      loaded_chunk = chunk;
+    }
+
+    // ---------------- gather rounds + GEMM 1 (H = z . W1^T)
+    for (int kb0 = 0; kb0 < g.kb1; kb0 += g.rb) {
+      const int kbe = min(g.kb1, kb0 + g.rb);
+      const int k_begin = kb0 * 64, k_end = min(g.k1, kbe * 64);
+      gather_rows(p, b, row0, cnt, k_begin, k_end, sA);
+      fence_async_smem();
+      __syncthreads();
+      if (tid == 0) {
+        tc_fence_after();
+        const uint32_t a0 = smem_u32(sA), w0 = smem_u32(sW1);
+        const uint32_t w_blk = (uint32_t)g.n1 * 128u;
+        for (int ks = k_begin / 16; ks < k_end / 16; ++ks) {
+          const uint32_t kb = ks >> 2, kin = (ks & 3) * 32;
+          umma_bf16(tH, make_desc_k_sw128(a0 + (kb - kb0) * a_blk + kin),
+                    make_desc_k_sw128(w0 + kb * w_blk + kin), idesc1, ks > 0);
+        }
+        umma_commit(&bars[0]);
+      }
+      mbar_wait(&bars[0], ph_main);
+      ph_main ^= 1;
+      tc_fence_after();
+    }
+
+    // ---------------- dOut rows -> fp32 staging (coalesced), rows >= cnt are zero
+    {
+      const int w4 = g.n2 >> 2;
+      for (int u = tid; u < TM * w4; u += NT) {
+        const int row = u / w4, c4 = u % w4, col = c4 * 4;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (row < cnt && col < dout) {
+          float gs = 1.f;
+          const float* g1p = nullptr;
+          if (p.g1) {
+            const int gi = __ldg(p.g1_idx + row0 + row);
+            if (p.g1_scale) gs = __ldg(p.g1_scale + gi);
+            g1p = p.g1 + (size_t)b * p.g1_batch_stride + (size_t)gi * dout + col;
+          }
+          const float* g0p = p.g0 ? p.g0 + (grow0 + row) * dout + col : nullptr;
+          float tmp[4] = {0.f, 0.f, 0.f, 0.f};
+          if ((dout & 3) == 0) {
+            if (g0p) {
+              const float4 a = __ldg(reinterpret_cast<const float4*>(g0p));
+              tmp[0] = a.x, tmp[1] = a.y, tmp[2] = a.z, tmp[3] = a.w;
+            }
+            if (g1p) {
+              const float4 a = __ldg(reinterpret_cast<const float4*>(g1p));
+              tmp[0] += gs * a.x, tmp[1] += gs * a.y, tmp[2] += gs * a.z, tmp[3] += gs * a.w;
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              if (col + j < dout) {
+                if (g0p) tmp[j] = __ldg(g0p + j);
+                if (g1p) tmp[j] += gs * __ldg(g1p + j);
+              }
+          }
+          v = make_float4(tmp[0], tmp[1], tmp[2], tmp[3]);
+        }
+        *reinterpret_cast<float4*>(stg + stg_idx(row, c4, g.n2)) = v;
+      }
+    }
+
+    // ---------------- epilogue 1: a = SiLU(H + b1) -> bf16 tile
+    if (act1) {
+      for (int cc = 0; cc < cp1; cc += 16) {
+        const int c0 = hf * cp1 + cc;
+        float v[16];
+        tmem_ld16(tH + lane_addr + (uint32_t)c0, v);
+#pragma unroll
+        for (int j = 0; j < 16; ++j) v[j] = silu_fast(v[j] + sPar[c0 + j]);
+#pragma unroll
+        for (int h8 = 0; h8 < 2; ++h8) {
+          uint4 pk = make_uint4(pack_bf16(v[h8 * 8 + 0], v[h8 * 8 + 1]),
+                                pack_bf16(v[h8 * 8 + 2], v[h8 * 8 + 3]),
+                                pack_bf16(v[h8 * 8 + 4], v[h8 * 8 + 5]),
+                                pack_bf16(v[h8 * 8 + 6], v[h8 * 8 + 7]));
+          *reinterpret_cast<uint4*>(sT + sw128_off(r, c0 + h8 * 8, a_blk)) = pk;
+        }
+      }
+    }
+    fence_async_smem();
+    tc_fence_before();
+    __syncthreads();
+
+    // ---------------- GEMM 2: Y = a . W2^T ; meanwhile the a tile goes to HBM
+    if (tid == 0) {
+      tc_fence_after();
+      const uint32_t a0 = smem_u32(sT), w0 = smem_u32(sW2);
+      const uint32_t w_blk = (uint32_t)g.n2 * 128u;
+      for (int ks = 0; ks < g.k2 / 16; ++ks) {
+        const uint32_t kb = ks >> 2, kin = (ks & 3) * 32;
+        umma_bf16(tY, make_desc_k_sw128(a0 + kb * a_blk + kin),
+                  make_desc_k_sw128(w0 + kb * w_blk + kin), idesc2, ks > 0);
+      }
+      umma_commit(&bars[0]);
+    }
+    copy_tile_out(sT, g.a_img + (size_t)t * g.kb2 * a_blk, g.kb2 * a_blk);
+    mbar_wait(&bars[0], ph_main);
+    ph_main ^= 1;
+    tc_fence_after();
+
+    // ---------------- epilogue 2: LayerNorm backward -> dY (bf16 tile) + column sums
+    float mean = 0.f, rstd = 1.f, m1 = 0.f, m2 = 0.f;
+    if (has_ln) {
+      float s = 0.f;
+      if (act2)
+        for (int cc = 0; cc < cp2; cc += 16) {
+          const int c0 = hf * cp2 + cc;
+          float v[16];
+          tmem_ld16(tY + lane_addr + (uint32_t)c0, v);
+#pragma unroll
+          for (int j = 0; j < 16; ++j)
+            if (c0 + j < dout) s += v[j] + sB2[c0 + j];
+        }
+      sLnx[r * 2 + hf] = s;
+      __syncthreads();
+      mean = (sLnx[r * 2] + (split2 ? sLnx[r * 2 + 1] : 0.f)) / (float)dout;
+      __syncthreads();
+      float qq = 0.f;
+      if (act2)
+        for (int cc = 0; cc < cp2; cc += 16) {
+          const int c0 = hf * cp2 + cc;
+          float v[16];
+          tmem_ld16(tY + lane_addr + (uint32_t)c0, v);
+#pragma unroll
+          for (int j = 0; j < 16; ++j)
+            if (c0 + j < dout) {
+              const float dl = v[j] + sB2[c0 + j] - mean;
+              qq += dl * dl;
+            }
+        }
+      sLnx[r * 2 + hf] = qq;
+      __syncthreads();
+      rstd = rsqrtf((sLnx[r * 2] + (split2 ? sLnx[r * 2 + 1] : 0.f)) / (float)dout + LN_EPS);
+      __syncthreads();
+      // row means of dyhat and dyhat*yhat; column sums for dgamma / dbeta
+      float s1 = 0.f, s2 = 0.f;
+      if (act2) {
+#pragma unroll
+        for (int ci = 0; ci < MAXCH; ++ci) {
+          const int cc = ci * 16;
+          if (cc < cp2) {
+            const int c0 = hf * cp2 + cc;
+            float v[16], dmv[16], pv[16];
+            tmem_ld16(tY + lane_addr + (uint32_t)c0, v);
+#pragma unroll
+            for (int j4 = 0; j4 < 4; ++j4) {
+              const float4 d4 =
+                  *reinterpret_cast<const float4*>(stg + stg_idx(r, (c0 >> 2) + j4, g.n2));
+              dmv[j4 * 4] = d4.x, dmv[j4 * 4 + 1] = d4.y, dmv[j4 * 4 + 2] = d4.z,
+                       dmv[j4 * 4 + 3] = d4.w;
+            }
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              const float yh = (v[j] + sB2[c0 + j] - mean) * rstd;
+              const float dyh = dmv[j] * sG[c0 + j];
+              pv[j] = (c0 + j < dout) ? dmv[j] * yh : 0.f;
+              if (c0 + j < dout) {
+                s1 += dyh;
+                s2 += dyh * yh;
+              }
+            }
+            acc_dg[ci] += warp_colsum16(pv, lane);
+            acc_dbt[ci] += warp_colsum16(dmv, lane);
+          }
+        }
+      }
+      sLnx[r * 2 + hf] = s1;
+      __syncthreads();
+      m1 = (sLnx[r * 2] + (split2 ? sLnx[r * 2 + 1] : 0.f)) / (float)dout;
+      __syncthreads();
+      sLnx[r * 2 + hf] = s2;
+      __syncthreads();
+      m2 = (sLnx[r * 2] + (split2 ? sLnx[r * 2 + 1] : 0.f)) / (float)dout;
+    }
+    __syncthreads();  // every thread is done copying the a tile out of sT
+    if (act2) {
+#pragma unroll
+      for (int ci = 0; ci < MAXCH; ++ci) {
+        const int cc = ci * 16;
+        if (cc < cp2) {
+          const int c0 = hf * cp2 + cc;
+          float v[16], dmv[16];
+#pragma unroll
+          for (int j4 = 0; j4 < 4; ++j4) {
+            const float4 d4 =
+                *reinterpret_cast<const float4*>(stg + stg_idx(r, (c0 >> 2) + j4, g.n2));
+            dmv[j4 * 4] = d4.x, dmv[j4 * 4 + 1] = d4.y, dmv[j4 * 4 + 2] = d4.z,
+                     dmv[j4 * 4 + 3] = d4.w;
+          }
+          if (has_ln) {
+            tmem_ld16(tY + lane_addr + (uint32_t)c0, v);
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              const float yh = (v[j] + sB2[c0 + j] - mean) * rstd;
+              const float dyh = dmv[j] * sG[c0 + j];
+              v[j] = (c0 + j < dout && r < cnt) ? rstd * (dyh - m1 - yh * m2) : 0.f;
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) v[j] = (c0 + j < dout) ? dmv[j] : 0.f;
+          }
+          acc_db2[ci] += warp_colsum16(v, lane);
+#pragma unroll
+          for (int h8 = 0; h8 < 2; ++h8) {
+            uint4 pk = make_uint4(pack_bf16(v[h8 * 8 + 0], v[h8 * 8 + 1]),
+                                  pack_bf16(v[h8 * 8 + 2], v[h8 * 8 + 3]),
+                                  pack_bf16(v[h8 * 8 + 4], v[h8 * 8 + 5]),
+                                  pack_bf16(v[h8 * 8 + 6], v[h8 * 8 + 7]));
+            *reinterpret_cast<uint4*>(sT + sw128_off(r, c0 + h8 * 8, a_blk)) = pk;
+          }
+        }
+      }
+    }
+    fence_async_smem();
+    tc_fence_before();
+    __syncthreads();
+
+    // ---------------- GEMM 3: dA = dY . W2 (into Y's columns) ; dY tile -> HBM
+    if (tid == 0) {
+      tc_fence_after();
+      const uint32_t a0 = smem_u32(sT), w0 = smem_u32(sW2);
+      const uint32_t lbo = (uint32_t)g.n2 * 128u;  // 64-wide blocks of the hidden dim
+      for (int ks = 0; ks < g.ko / 16; ++ks) {
+        const uint32_t kb = ks >> 2, kin = (ks & 3) * 32;
+        umma_bf16(tY, make_desc_k_sw128(a0 + kb * a_blk + kin),
+                  make_desc_mn_sw128(w0 + (uint32_t)ks * 2048u, lbo), idesc3, ks > 0);
+      }
+      umma_commit(&bars[0]);
+    }
+    copy_tile_out(sT, g.dy_img + (size_t)t * g.kbo * a_blk, g.kbo * a_blk);
+    mbar_wait(&bars[0], ph_main);
+    ph_main ^= 1;
+    tc_fence_after();
+    __syncthreads();  // dY tile fully copied before dH overwrites it
+
+    // ---------------- epilogue 3: dH = dA * SiLU'(H + b1) -> bf16 tile
+    if (act1) {
+#pragma unroll
+      for (int ci = 0; ci < MAXCH; ++ci) {
+        const int cc = ci * 16;
+        if (cc < cp1) {
+          const int c0 = hf * cp1 + cc;
+          float v[16], h[16];
+          tmem_ld16(tY + lane_addr + (uint32_t)c0, v);
+          tmem_ld16(tH + lane_addr + (uint32_t)c0, h);
+#pragma unroll
+          for (int j = 0; j < 16; ++j)
+            v[j] = (c0 + j < dh) ? v[j] * silu_grad_fast(h[j] + sPar[c0 + j]) : 0.f;
+          acc_db1[ci] += warp_colsum16(v, lane);
+#pragma unroll
+          for (int h8 = 0; h8 < 2; ++h8) {
+            uint4 pk = make_uint4(pack_bf16(v[h8 * 8 + 0], v[h8 * 8 + 1]),
+                                  pack_bf16(v[h8 * 8 + 2], v[h8 * 8 + 3]),
+                                  pack_bf16(v[h8 * 8 + 4], v[h8 * 8 + 5]),
+                                  pack_bf16(v[h8 * 8 + 6], v[h8 * 8 + 7]));
+            *reinterpret_cast<uint4*>(sT + sw128_off(r, c0 + h8 * 8, a_blk)) = pk;
+          }
+        }
+      }
+    }
+    fence_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    copy_tile_out(sT, g.dh_img + (size_t)t * g.kb2 * a_blk, g.kb2 * a_blk);
+
+    // ---------------- GEMM 4 + epilogue 4: dZ = dH . W1, 64 input columns at a time
+    if (g.need_dz) {
+      auto issue_dz = [&](int kb) {
+        tc_fence_after();
+        const uint32_t a0 = smem_u32(sT);
+        const uint32_t w0 = smem_u32(sW1) + (uint32_t)kb * (uint32_t)g.n1 * 128u;
+        for (int ks = 0; ks < g.k2 / 16; ++ks) {
+          const uint32_t kbb = ks >> 2, kin = (ks & 3) * 32;
+          umma_bf16(tZ + (uint32_t)(kb & 1) * 64u, make_desc_k_sw128(a0 + kbb * a_blk + kin),
+                    make_desc_mn_sw128(w0 + (uint32_t)ks * 2048u, 0), idesc4, ks > 0);
+        }
+        umma_commit(&bars[1 + (kb & 1)]);
+      };
+      if (tid == 0) issue_dz(0);
+      for (int kb = 0; kb < g.kb1; ++kb) {
+        if (tid == 0 && kb + 1 < g.kb1) issue_dz(kb + 1);
+        mbar_wait(&bars[1 + (kb & 1)], (ph_z >> (kb & 1)) & 1u);
+        ph_z ^= 1u << (kb & 1);
+        tc_fence_after();
+        // TMEM -> swizzled fp32 staging [128][64]
+        for (int cc = 0; cc < 32; cc += 16) {
+          const int c0 = hf * 32 + cc;
+          float v[16];
+          tmem_ld16(tZ + (uint32_t)(kb & 1) * 64u + lane_addr + (uint32_t)c0, v);
+#pragma unroll
+          for (int j4 = 0; j4 < 4; ++j4)
+            *reinterpret_cast<float4*>(stg + stg_idx(r, (c0 >> 2) + j4, 64)) =
+                make_float4(v[j4 * 4], v[j4 * 4 + 1], v[j4 * 4 + 2], v[j4 * 4 + 3]);
+        }
+        tc_fence_before();
+        __syncthreads();
+        // coalesced per-source row stores
+        for (int u = tid; u < cnt * 16; u += NT) {
+          const int row = u >> 4, c4 = u & 15, kg = kb * 64 + c4 * 4;
+          if (kg >= p.k_total) continue;
+          int s = 0;
+          while (s + 1 < p.d.n_src && kg >= p.koff[s + 1]) ++s;
+          float* dst = p.d_src[s];
+          if (!dst) continue;
+          const int w = p.d.src[s].width, col = kg - p.koff[s];
+          const float4 v = *reinterpret_cast<const float4*>(stg + stg_idx(row, c4, 64));
+          float tmp[4] = {v.x, v.y, v.z, v.w};
+          const bool res = (s == p.d.residual_src) && p.g0;
+          float* o = dst + (grow0 + row) * w + col;
+          if ((w & 3) == 0) {
+            if (res) {
+              const float4 e = __ldg(reinterpret_cast<const float4*>(p.g0 + (grow0 + row) * dout + col));
+              tmp[0] += e.x, tmp[1] += e.y, tmp[2] += e.z, tmp[3] += e.w;
+            }
+            *reinterpret_cast<float4*>(o) = make_float4(tmp[0], tmp[1], tmp[2], tmp[3]);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              if (col + j < w)
+                o[j] = tmp[j] + (res ? __ldg(p.g0 + (grow0 + row) * dout + col + j) : 0.f);
+          }
+        }
+        __syncthreads();
+      }
+    }
+    tc_fence_before();
+    __syncthreads();  // sT / staging free for the next tile
+  }
+  if (loaded_chunk >= 0) flush_colsums(loaded_chunk);
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem_base, (uint32_t)g.tmem_cols);
+}
+
+// -------------------------------------------------------------------- wgrad
+__global__ void __launch_bounds__(NT, 2)
+rowmlp_tc_wgrad_kernel(const __grid_constant__ KParams p, const __grid_constant__ BGeo g) {
+  extern __shared__ __align__(1024) uint8_t sm[];
+  if (smem_u32(sm) & 1023u) __trap();
+  uint8_t* sZ = sm;
+  uint8_t* sAi = sm + g.w_off_a;
+  uint8_t* sDY = sm + g.w_off_dy;
+  uint8_t* sDH = sm + g.w_off_dh;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sm + g.w_off_bar);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 1);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int dh = p.d.d_hidden, dout = p.d.d_out;
+  if (warp == 0) tmem_alloc(tmem_slot, (uint32_t)g.w_tmem_cols);
+  if (tid == 32) {
+    mbar_init(&bars[0], 1);
+    mbar_fence_init();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tW2 = tmem_base + (uint32_t)(g.w_mchunks * g.n1);
+  uint32_t ph = 0;
+  const uint32_t a_blk = TM * 128u;
+  const uint32_t idesc_w1 = make_idesc_bf16(TM, g.n1, 1, 1);
+  const uint32_t idesc_w2 = make_idesc_bf16(TM, g.n2, 1, 1);
+  const int q = warp & 3, hf = warp >> 2, r = q * 32 + lane;
+  const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
+  int cur_chunk = -1;
+  bool first = true;
+
+  auto flush = [&](int chunk) {
+    // accumulators -> per-CTA partial in final [n][k] orientation
+    tc_fence_after();
+    const ParamLayout lay = p.lay;
+    float* dst = g.partial + ((size_t)blockIdx.x * p.d.n_chunks + chunk) * g.p_total;
+    const int cpa = g.n1 >= 32 ? g.n1 / 2 : g.n1;
+    if (g.n1 >= 32 || hf == 0) {
+      for (int mc = 0; mc < g.w_mchunks; ++mc) {
+        const int kg = mc * 128 + r;  // input column
+        for (int cc = 0; cc < cpa; cc += 16) {
+          const int c0 = hf * cpa + cc;
+          float v[16];
+          tmem_ld16(tmem_base + (uint32_t)(mc * g.n1) + lane_addr + (uint32_t)c0, v);
+          if (kg < p.k_total) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j)
+              if (c0 + j < dh) dst[lay.off_w1() + (size_t)(c0 + j) * p.k_total + kg] = v[j];
+          }
+        }
+      }
+    }
+    const int cpb = g.n2 >= 32 ? g.n2 / 2 : g.n2;
+    if (g.n2 >= 32 || hf == 0) {
+      for (int cc = 0; cc < cpb; cc += 16) {
+        const int c0 = hf * cpb + cc;
+        float v[16];
+        tmem_ld16(tW2 + lane_addr + (uint32_t)c0, v);
+        if (r < dh) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j)
+            if (c0 + j < dout) dst[lay.off_w2() + (size_t)(c0 + j) * dh + r] = v[j];
+        }
+      }
+    }
+    tc_fence_before();
+    __syncthreads();
+  };
+
+  for (int t = blockIdx.x; t < g.total_tiles; t += gridDim.x) {
+    const int b = t / g.tiles_per_batch, tile = t % g.tiles_per_batch;
+    int row0, cnt, chunk;
+    tile_range<TM>(p.d, tile, row0, cnt, chunk);
+    if (chunk != cur_chunk) {
+      if (cur_chunk >= 0) flush(cur_chunk);
+      cur_chunk = chunk;
+      first = true;
+    }
+    gather_rows(p, b, row0, cnt, 0, g.k1, sZ);
+    copy_tile_in(g.a_img + (size_t)t * g.kb2 * a_blk, sAi, g.kb2 * a_blk);
+    copy_tile_in(g.dy_img + (size_t)t * g.kbo * a_blk, sDY, g.kbo * a_blk);
+    copy_tile_in(g.dh_img + (size_t)t * g.kb2 * a_blk, sDH, g.kb2 * a_blk);
+    fence_async_smem();
+    __syncthreads();
+    if (tid == 0) {
+      tc_fence_after();
+      const uint32_t z0 = smem_u32(sZ), a0 = smem_u32(sAi), y0 = smem_u32(sDY), h0 = smem_u32(sDH);
+      for (int mc = 0; mc < g.w_mchunks; ++mc)
+        for (int ks = 0; ks < TM / 16; ++ks)
+          umma_bf16(tmem_base + (uint32_t)(mc * g.n1),
+                    make_desc_mn_sw128(z0 + (uint32_t)mc * 2u * a_blk + (uint32_t)ks * 2048u, a_blk),
+                    make_desc_mn_sw128(h0 + (uint32_t)ks * 2048u, a_blk), idesc_w1,
+                    (!first || ks > 0) ? 1u : 0u);
+      for (int ks = 0; ks < TM / 16; ++ks)
+        umma_bf16(tW2, make_desc_mn_sw128(a0 + (uint32_t)ks * 2048u, a_blk),
+                  make_desc_mn_sw128(y0 + (uint32_t)ks * 2048u, a_blk), idesc_w2,
+                  (!first || ks > 0) ? 1u : 0u);
+      umma_commit(&bars[0]);
+    }
+    first = false;
+    mbar_wait(&bars[0], ph);
+    ph ^= 1;
+    tc_fence_after();
+    __syncthreads();
+  }
+  if (cur_chunk >= 0) flush(cur_chunk);
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem_base, (uint32_t)g.w_tmem_cols);
+}
+
+static int pow2_cols(int c) {
+  int v = 32;
+  while (v < c) v *= 2;
+  return v;
+}
+
+static int make_bgeo(const KParams& p, BGeo& g) {
+  const nlam_rowmlp& d = p.d;
+  g.n1 = pad_n(d.d_hidden), g.n2 = pad_n(d.d_out);
+  g.nmax = g.n1 > g.n2 ? g.n1 : g.n2;
+  g.k1 = (p.k_total + 15) / 16 * 16;
+  g.k2 = (d.d_hidden + 15) / 16 * 16;
+  g.ko = (d.d_out + 15) / 16 * 16;
+  g.kb1 = (g.k1 + 63) / 64, g.kb2 = (g.n1 + 63) / 64, g.kbo = (g.n2 + 63) / 64;
+  g.rb = 3;
+  g.cY = g.n1, g.cZ = g.n1 + g.nmax;
+  g.tmem_cols = pow2_cols(g.cZ + 128);
+  const uint32_t blk = TM * 128u;
+  const int rb = g.kb1 < g.rb ? g.kb1 : g.rb;
+  uint32_t r0 = (uint32_t)rb * blk;
+  const uint32_t stg_bytes = (uint32_t)TM * (g.n2 > 64 ? g.n2 : 64) * 4u;
+  if (stg_bytes > r0) r0 = stg_bytes;
+  auto al = [](uint32_t x) { return (x + 1023u) & ~1023u; };
+  uint32_t o = al(r0);
+  const int kbt = g.kb2 > g.kbo ? g.kb2 : g.kbo;
+  g.off_t = o, o += (uint32_t)kbt * blk;
+  g.off_w1 = o, o += al((uint32_t)g.kb1 * g.n1 * 128u);
+  g.off_w2 = o, o += al((uint32_t)g.kb2 * g.n2 * 128u);
+  g.off_par = o, o += (uint32_t)(g.n1 + 2 * g.n2) * 4u;
+  g.off_lnx = o, o += (uint32_t)TM * 2u * 4u;
+  g.off_bar = o, o += 64;
+  g.smem_bytes = o;
+  g.tiles_per_batch = n_tiles_of(d, TM);
+  g.total_tiles = g.tiles_per_batch * d.batch;
+  g.p_total = p.lay.total();
+  // wgrad
+  g.w_mchunks = (g.kb1 + 1) / 2;
+  g.w_tmem_cols = pow2_cols(g.w_mchunks * g.n1 + g.n2);
+  o = (uint32_t)g.kb1 * blk;
+  g.w_off_a = o, o += (uint32_t)g.kb2 * blk;
+  g.w_off_dy = o, o += (uint32_t)g.kbo * blk;
+  g.w_off_dh = o, o += (uint32_t)g.kb2 * blk;
+  o += blk;  // MN-major M=128 views may run one (ignored) block past a tile
+  g.w_off_bar = o, o += 64;
+  g.w_smem_bytes = o;
+  NLAM_CHECK(g.smem_bytes <= 232448 && g.w_smem_bytes <= 232448 && g.w_tmem_cols <= 512 &&
+                 g.tmem_cols <= 512,
+             "rowmlp_bwd(bf16): %u / %u bytes of shared memory, %d / %d TMEM columns", g.smem_bytes,
+             g.w_smem_bytes, g.tmem_cols, g.w_tmem_cols);
+  return 0;
+}
+
+static int grid_for(uint32_t smem, int tmem_cols, int total_tiles) {
+  int per_sm = smem <= 113 * 1024 ? 2 : 1;
+  if (tmem_cols * per_sm > 512) per_sm = 1;
+  int grid = 148 * per_sm;
+  return grid < total_tiles ? grid : total_tiles;
+}
+
+struct TcBwdWs {
+  size_t a_img, dy_img, dh_img, partial, total;  // float offsets
+  int slots;
+};
+static TcBwdWs tc_bwd_ws(const KParams& p, const BGeo& g) {
+  auto al = [](size_t x) { return (x + 255) / 256 * 256; };
+  TcBwdWs w;
+  const size_t blk_f = TM * 128 / 4;  // floats per 16 KB block
+  size_t o = 0;
+  w.a_img = o, o += al((size_t)g.total_tiles * g.kb2 * blk_f);
+  w.dy_img = o, o += al((size_t)g.total_tiles * g.kbo * blk_f);
+  w.dh_img = o, o += al((size_t)g.total_tiles * g.kb2 * blk_f);
+  const int gd = grid_for(g.smem_bytes, g.tmem_cols, g.total_tiles);
+  const int gw = grid_for(g.w_smem_bytes, g.w_tmem_cols, g.total_tiles);
+  w.slots = gd > gw ? gd : gw;
+  w.partial = o, o += al((size_t)w.slots * p.d.n_chunks * g.p_total);
+  w.total = o;
+  return w;
+}
+
+}  // namespace tc
+
+size_t tc_rowmlp_bwd_workspace(const nlam_rowmlp& d) {
+  KParams p{};
+  if (fill_params(d, p)) return 0;
+  tc::BGeo g{};
+  if (tc::make_bgeo(p, g)) return 0;
+  return tc::tc_bwd_ws(p, g).total;
+}
+
+int tc_rowmlp_bwd(const nlam_rowmlp_bwd& bd, cudaStream_t st) {
+  const nlam_rowmlp& d = bd.fwd;
+  KParams p{};
+  if (fill_params(d, p)) return 1;
+  NLAM_CHECK(bd.d_params, "rowmlp_bwd: d_params is NULL");
+  if (d.rows == 0) {
+    NLAM_CUDA(cudaMemsetAsync(bd.d_params, 0, sizeof(float) * (size_t)d.n_chunks * p.lay.total(), st));
+    return 0;
+  }
+  NLAM_CHECK(bd.g0 || bd.g1, "rowmlp_bwd: no output gradient given");
+  NLAM_CHECK(!bd.g1 || bd.g1_idx, "rowmlp_bwd: g1 needs g1_idx");
+  tc::BGeo g{};
+  if (tc::make_bgeo(p, g)) return 1;
+  const tc::TcBwdWs ws = tc::tc_bwd_ws(p, g);
+  NLAM_CHECK(bd.workspace && bd.workspace_floats >= ws.total,
+             "rowmlp_bwd: workspace too small (%zu < %zu floats)", bd.workspace_floats, ws.total);
+  NLAM_CHECK(((uintptr_t)bd.workspace) % 16 == 0, "rowmlp_bwd: workspace must be 16B aligned");
+  p.g0 = bd.g0, p.g1 = bd.g1, p.g1_idx = bd.g1_idx, p.g1_scale = bd.g1_scale;
+  p.g1_batch_stride = bd.g1_batch_stride;
+  g.need_dz = 0;
+  for (int s = 0; s < NLAM_MAX_SRC; ++s) {
+    p.d_src[s] = s < d.n_src ? bd.d_src[s] : nullptr;
+    if (p.d_src[s]) g.need_dz = 1;
+  }
+  g.a_img = reinterpret_cast<uint8_t*>(bd.workspace + ws.a_img);
+  g.dy_img = reinterpret_cast<uint8_t*>(bd.workspace + ws.dy_img);
+  g.dh_img = reinterpret_cast<uint8_t*>(bd.workspace + ws.dh_img);
+  g.partial = bd.workspace + ws.partial;
+  NLAM_CUDA(cudaMemsetAsync(g.partial, 0,
+                            sizeof(float) * (size_t)ws.slots * d.n_chunks * g.p_total, st));
+  static int max_d = 0, max_w = 0;
+  if ((int)g.smem_bytes > max_d) {
+    NLAM_CUDA(cudaFuncSetAttribute(tc::rowmlp_tc_dgrad_kernel,
+                                   cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem_bytes));
+    max_d = (int)g.smem_bytes;
+  }
+  if ((int)g.w_smem_bytes > max_w) {
+    NLAM_CUDA(cudaFuncSetAttribute(tc::rowmlp_tc_wgrad_kernel,
+                                   cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.w_smem_bytes));
+    max_w = (int)g.w_smem_bytes;
+  }
+  const int gd = tc::grid_for(g.smem_bytes, g.tmem_cols, g.total_tiles);
+  tc::rowmlp_tc_dgrad_kernel<<<gd, tc::NT, g.smem_bytes, st>>>(p, g);
+  NLAM_CUDA(cudaGetLastError());
+  count_launch();
+  const int gw = tc::grid_for(g.w_smem_bytes, g.w_tmem_cols, g.total_tiles);
+  tc::rowmlp_tc_wgrad_kernel<<<gw, tc::NT, g.w_smem_bytes, st>>>(p, g);
+  NLAM_CUDA(cudaGetLastError());
+  count_launch();
+  return launch_reduce_params(g.partial, ws.slots, d.n_chunks, g.p_total, bd.d_params, st);
+}
+
+}  // namespace nlam

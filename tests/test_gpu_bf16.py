@@ -1,0 +1,170 @@
+"""GPU parity of the bf16 tensor-core (tcgen05) mode: bf16 MMA operands, fp32
+accumulation / storage.  Tolerance stated by BASELINE.json north_star: 2e-2
+(relative to the largest magnitude of the reference tensor)."""
+import tempfile
+
+import pytest
+import torch
+
+from helpers import build_model_case, inet_loss, load_golden, make_inet_inputs
+
+pytestmark = pytest.mark.gpu
+TOL = 2e-2
+INET = load_golden("interaction_net.pt")
+MODELS = load_golden("models.pt")
+
+
+@pytest.fixture(scope="module")
+def dev():
+    import __graft_entry__ as entry
+    entry.build()
+    assert torch.cuda.is_available()
+    return torch.device("cuda:0")
+
+
+@pytest.fixture()
+def bf16():
+    from neural_lam_b200 import ops
+    ops.set_precision("bf16")
+    yield
+    ops.set_precision("fp32")
+
+
+def _close(a, b, what, tol=TOL):
+    a, b = a.detach().float().cpu(), b.detach().float().cpu()
+    assert not torch.isnan(a).any(), f"{what}: NaN"
+    scale = b.abs().max().item() + 1e-30
+    err = (a - b).abs().max().item()
+    assert err <= tol * scale, f"{what}: max err {err:.3e} > {tol} * {scale:.3e}"
+
+
+@pytest.mark.parametrize("blueprint,ln,rows,B", [
+    ([3, 64, 64], True, 1000, 1), ([56, 64, 64], True, 700, 2), ([64, 64, 17], False, 513, 2),
+    ([128, 128, 128], True, 300, 2), ([32, 32, 32], True, 64, 1), ([16, 16, 16], True, 200, 1),
+    ([64, 64, 64], True, 129, 3),
+])
+def test_mlp_bf16(dev, bf16, blueprint, ln, rows, B):
+    from neural_lam_b200 import utils
+    from oracle import port
+    torch.manual_seed(0)
+    ref = port.make_mlp(blueprint, layer_norm=ln)
+    mlp = utils.make_mlp(blueprint, layer_norm=ln)
+    mlp.load_state_dict(ref.state_dict())
+    mlp = mlp.to(dev)
+    x = torch.randn(B, rows, blueprint[0])
+    w = torch.randn(B, rows, blueprint[-1])
+    xr, xg = x.clone().requires_grad_(), x.clone().to(dev).requires_grad_()
+    yr, yg = ref(xr), mlp(xg)
+    _close(yg, yr, "out")
+    (yr * w).sum().backward()
+    (yg * w.to(dev)).sum().backward()
+    _close(xg.grad, xr.grad, "dx")
+    for (n, p), (_, q) in zip(ref.named_parameters(), mlp.named_parameters()):
+        _close(q.grad, p.grad, f"d{n}")
+
+
+@pytest.mark.parametrize("name", sorted(INET))
+def test_interaction_net_bf16_vs_reference_golden(dev, bf16, name):
+    from neural_lam_b200.interaction_net import InteractionNet
+    case, ref = INET[name]["case"], INET[name]["ref"]
+    kw = {k: case[k] for k in ("edge_chunk_sizes", "aggr_chunk_sizes") if k in case}
+    net = InteractionNet(case["edge_index"].clone(), case["d"],
+                         update_edges=case["update_edges"], aggr=case["aggr"], **kw)
+    net.load_state_dict(ref["state_dict"])
+    net = net.to(dev)
+    (send_leaf, rec_leaf, edge_leaf), (send, rec, edge) = make_inet_inputs(case, device=dev)
+    out = net(send, rec, edge)
+    outs = out if isinstance(out, tuple) else (out,)
+    for i, (o, r) in enumerate(zip(outs, ref["outputs"])):
+        _close(o, r, f"{name} output {i}")
+    inet_loss(outs).backward()
+    _close(rec_leaf.grad, ref["grad_rec"], "grad rec")
+    _close(edge_leaf.grad, ref["grad_edge"], "grad edge")
+    if not case["same"]:
+        _close(send_leaf.grad, ref["grad_send"], "grad send")
+    for n, p in net.named_parameters():
+        _close(p.grad, ref["param_grads"][n], f"grad {n}")
+
+
+@pytest.mark.parametrize("d,M,n_send,n_rec,B,update,aggr", [
+    (64, 20000, 3000, 2500, 2, True, "sum"),
+    (64, 9000, 4000, 700, 1, False, "mean"),
+    (128, 6000, 900, 900, 2, True, "sum"),
+])
+def test_interaction_net_bf16_vs_oracle(dev, bf16, d, M, n_send, n_rec, B, update, aggr):
+    from neural_lam_b200.interaction_net import InteractionNet
+    from oracle import port
+    g = torch.Generator().manual_seed(d + M)
+    s = torch.randint(0, n_send, (M,), generator=g) + n_rec
+    r = torch.randint(0, n_rec, (M,), generator=g)
+    s[0], r[0], s[1], r[1] = n_rec, 0, n_rec + n_send - 1, n_rec - 1
+    ei = torch.stack((s, r))
+    torch.manual_seed(3)
+    ref = port.InteractionNet(ei.clone(), d, update_edges=update, aggr=aggr)
+    net = InteractionNet(ei.clone(), d, update_edges=update, aggr=aggr)
+    net.load_state_dict(ref.state_dict())
+    net = net.to(dev)
+    xs = [torch.randn(B, n, d, generator=g) for n in (n_send, n_rec, M)]
+    a = [x.clone().requires_grad_() for x in xs]
+    b = [x.clone().to(dev).requires_grad_() for x in xs]
+    o_ref, o = ref(*a), net(*b)
+    o_ref = o_ref if isinstance(o_ref, tuple) else (o_ref,)
+    o = o if isinstance(o, tuple) else (o,)
+    for x, y in zip(o, o_ref):
+        _close(x, y, "output")
+    inet_loss(o_ref).backward()
+    inet_loss(o).backward()
+    for x, y, n in zip(b, a, ("send", "rec", "edge")):
+        _close(x.grad, y.grad, f"grad {n}")
+    for (n, p), (_, q) in zip(ref.named_parameters(), net.named_parameters()):
+        _close(q.grad, p.grad, f"grad {n}")
+
+
+@pytest.mark.parametrize("name", sorted(MODELS))
+def test_train_step_bf16_vs_reference(dev, bf16, name):
+    """Full train step in bf16 mode against the reference's fp32 golden loss /
+    prediction / gradients."""
+    from neural_lam_b200 import config as nl_config
+    from neural_lam_b200 import models
+    entry = MODELS[name]
+    case = entry["case"]
+    with tempfile.TemporaryDirectory() as root:
+        ds, args, batch = build_model_case(case, root)
+        model = models.MODELS[case["model"]](args, nl_config.default_config(), ds)
+    model.load_state_dict(entry["state_dict"])
+    model = model.to(dev)
+    batch = tuple(t.to(dev) for t in batch)
+    loss = model.training_step(batch)
+    _close(loss, entry["loss"], f"{name} loss")
+    loss.backward()
+    with torch.no_grad():
+        pred, _ = model.predict_step(batch[0][:, 1], batch[0][:, 0], batch[2][:, 0])
+    if case.get("summary_only"):
+        _close(pred[:, ::997], entry["pred_slice"], f"{name} pred")
+        for n, p in model.named_parameters():
+            _close(p.grad.norm(), entry["grad_norms"][n], f"{name} |grad {n}|", tol=5e-2)
+    else:
+        _close(pred, entry["pred_step"], f"{name} pred")
+        for n, p in model.named_parameters():
+            _close(p.grad, entry["param_grads"][n], f"{name} grad {n}", tol=5e-2)
+
+
+def test_bf16_deterministic(dev, bf16):
+    from neural_lam_b200.interaction_net import InteractionNet
+    g = torch.Generator().manual_seed(0)
+    M, n, d = 30000, 2000, 64
+    ei = torch.stack((torch.randint(0, n, (M,), generator=g), torch.randint(0, n, (M,), generator=g)))
+    torch.manual_seed(0)
+    net = InteractionNet(ei, d).to(dev)
+    x = torch.randn(2, n, d, device=dev)
+    e = torch.randn(2, M, d, device=dev)
+    outs = []
+    for _ in range(2):
+        xx, ee = x.clone().requires_grad_(), e.clone().requires_grad_()
+        r, eo = net(xx, xx, ee)
+        (r.sum() + eo.square().sum()).backward()
+        outs.append([r.detach().clone(), xx.grad.clone(), ee.grad.clone()]
+                    + [p.grad.clone() for p in net.parameters()])
+        net.zero_grad()
+    for a, b in zip(*outs):
+        assert torch.equal(a, b)
