@@ -589,22 +589,30 @@ struct RParams {
   float* out;
 };
 __global__ void reduce_params_kernel(const __grid_constant__ RParams p) {
-  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  // 8 consecutive lanes share one output element: each sums a fixed subset of the
+  // partials, then the 8 sub-sums are combined in a fixed shuffle order.
+  const int j = (blockIdx.x * blockDim.x + threadIdx.x) >> 3;
+  const int sub = threadIdx.x & 7;
   const int chunk = blockIdx.y;
-  if (j >= p.p_total) return;
   float s = 0.f;
-  if (j < p.p_main) {
-    for (int sp = 0; sp < p.splits; ++sp)
-      s += p.partial[((size_t)sp * p.n_chunks + chunk) * p.p_total + j];
-  } else {
-    const int q = j - p.p_main;  // [2][d_out]
-    for (int b = 0; b < p.batch; ++b)
-      for (int t = 0; t < p.n_tiles; ++t) {
+  if (j < p.p_total) {
+    if (j < p.p_main) {
+      for (int sp = sub; sp < p.splits; sp += 8)
+        s += p.partial[((size_t)sp * p.n_chunks + chunk) * p.p_total + j];
+    } else {
+      const int q = j - p.p_main;  // [2][d_out]
+      const int n = p.batch * p.n_tiles;
+      for (int i = sub; i < n; i += 8) {
+        const int t = i % p.n_tiles;
         if (p.tile_chunk && p.tile_chunk[t] != chunk) continue;
-        s += p.ln_partial[((size_t)b * p.n_tiles + t) * 2 * p.d_out + q];
+        s += p.ln_partial[(size_t)i * 2 * p.d_out + q];
       }
+    }
   }
-  p.out[(size_t)chunk * p.p_total + j] = s;
+  s += __shfl_xor_sync(0xffffffffu, s, 1);
+  s += __shfl_xor_sync(0xffffffffu, s, 2);
+  s += __shfl_xor_sync(0xffffffffu, s, 4);
+  if (j < p.p_total && sub == 0) p.out[(size_t)chunk * p.p_total + j] = s;
 }
 
 int launch_reduce_params(const float* partial, int splits, int n_chunks, int p_total, float* out,
@@ -613,7 +621,7 @@ int launch_reduce_params(const float* partial, int splits, int n_chunks, int p_t
   rp.partial = partial, rp.splits = splits, rp.n_chunks = n_chunks;
   rp.p_total = p_total, rp.p_main = p_total;
   rp.out = out;
-  dim3 rgrid((p_total + 255) / 256, n_chunks);
+  dim3 rgrid((p_total * 8 + 255) / 256, n_chunks);
   reduce_params_kernel<<<rgrid, 256, 0, st>>>(rp);
   NLAM_CUDA(cudaGetLastError());
   count_launch();
@@ -707,7 +715,7 @@ static int launch_bwd(const KParams& p, const WParams& wp, const RParams& rp, cu
   wgrad_kernel<DP><<<wgrid, NT, 0, st>>>(wp);
   NLAM_CUDA(cudaGetLastError());
   count_launch();
-  dim3 rgrid((rp.p_total + 255) / 256, rp.n_chunks);
+  dim3 rgrid((rp.p_total * 8 + 255) / 256, rp.n_chunks);
   reduce_params_kernel<<<rgrid, 256, 0, st>>>(rp);
   NLAM_CUDA(cudaGetLastError());
   count_launch();

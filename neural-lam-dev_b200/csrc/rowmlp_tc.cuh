@@ -39,37 +39,66 @@ __device__ __forceinline__ float silu_grad_fast(float x) {
 
 // fp32 source rows -> bf16 A operand (K-major SW128, 128 rows per 64-wide block).
 // Covers concatenated-input columns [k_begin, k_end) (multiples of 8); the
-// destination block index is relative to k_begin's block.
+// destination block index is relative to k_begin's block.  Work unit = one
+// 8-element (16-byte bf16) chunk of one row; units are processed in batches of
+// GU with all row-index loads, then all 128-bit data loads, issued before any
+// use, so that GU*2 loads per thread are in flight (memory-level parallelism).
+constexpr int GU = 6;
 __device__ __forceinline__ void gather_rows(const KParams& p, int b, int row0, int cnt,
                                             int k_begin, int k_end, uint8_t* sA) {
   const int nch = (k_end - k_begin) >> 3;
+  const int total = TM * nch;
   const uint32_t a_blk = TM * 128u;
-  for (int u = threadIdx.x; u < TM * nch; u += NT) {
-    const int row = u / nch, k0 = k_begin + (u % nch) * 8;
-    float v[8];
+  for (int base = threadIdx.x; base < total; base += NT * GU) {
+    const float* rp[GU];
+    int rowv[GU], k0v[GU], nval[GU];  // nval: 8 = vector path, 0 = zero, <0 = -(scalar count)
 #pragma unroll
-    for (int j = 0; j < 8; ++j) v[j] = 0.f;
-    if (row < cnt && k0 < p.k_total) {
-      int s = 0;
-      while (s + 1 < p.d.n_src && k0 >= p.koff[s + 1]) ++s;
-      const nlam_src& src = p.d.src[s];
-      const int col = k0 - p.koff[s];
-      const int ridx = src.idx ? __ldg(src.idx + row0 + row) : row0 + row;
-      const float* rp = src.ptr + (long long)b * src.batch_stride + (long long)ridx * src.ld + col;
-      if (p.vec_ok[s] && col + 8 <= src.width) {
-        const float4 x = __ldg(reinterpret_cast<const float4*>(rp));
-        const float4 y = __ldg(reinterpret_cast<const float4*>(rp) + 1);
-        v[0] = x.x, v[1] = x.y, v[2] = x.z, v[3] = x.w;
-        v[4] = y.x, v[5] = y.y, v[6] = y.z, v[7] = y.w;
+    for (int j = 0; j < GU; ++j) {
+      const int u = base + j * NT;
+      rp[j] = nullptr;
+      nval[j] = 0;
+      rowv[j] = 0, k0v[j] = k_begin;
+      if (u < total) {
+        const int row = u / nch, k0 = k_begin + (u % nch) * 8;
+        rowv[j] = row, k0v[j] = k0;
+        nval[j] = 0;
+        if (row < cnt && k0 < p.k_total) {
+          int s = 0;
+          while (s + 1 < p.d.n_src && k0 >= p.koff[s + 1]) ++s;
+          const nlam_src& src = p.d.src[s];
+          const int col = k0 - p.koff[s];
+          const int ridx = src.idx ? __ldg(src.idx + row0 + row) : row0 + row;
+          rp[j] = src.ptr + (long long)b * src.batch_stride + (long long)ridx * src.ld + col;
+          const int left = src.width - col;
+          nval[j] = (p.vec_ok[s] && left >= 8) ? 8 : -(left < 8 ? left : 8);
+        }
       } else {
-#pragma unroll
-        for (int j = 0; j < 8; ++j)
-          if (col + j < src.width) v[j] = __ldg(rp + j);
+        nval[j] = 1;  // sentinel: no unit
       }
     }
-    uint4 pk = make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]),
-                          pack_bf16(v[6], v[7]));
-    *reinterpret_cast<uint4*>(sA + sw128_off(row, k0 - (k_begin & ~63), a_blk)) = pk;
+    float4 x[GU], y[GU];
+#pragma unroll
+    for (int j = 0; j < GU; ++j) {
+      x[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+      y[j] = x[j];
+      if (nval[j] == 8) {
+        x[j] = __ldg(reinterpret_cast<const float4*>(rp[j]));
+        y[j] = __ldg(reinterpret_cast<const float4*>(rp[j]) + 1);
+      } else if (nval[j] < 0) {
+        float v[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) v[e] = (e < -nval[j]) ? __ldg(rp[j] + e) : 0.f;
+        x[j] = make_float4(v[0], v[1], v[2], v[3]);
+        y[j] = make_float4(v[4], v[5], v[6], v[7]);
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < GU; ++j) {
+      if (nval[j] == 1) continue;
+      uint4 pk = make_uint4(pack_bf16(x[j].x, x[j].y), pack_bf16(x[j].z, x[j].w),
+                            pack_bf16(y[j].x, y[j].y), pack_bf16(y[j].z, y[j].w));
+      *reinterpret_cast<uint4*>(sA + sw128_off(rowv[j], k0v[j] - (k_begin & ~63), a_blk)) = pk;
+    }
   }
 }
 

@@ -98,9 +98,16 @@ __device__ __forceinline__ void copy_tile_out(const uint8_t* s, uint8_t* g, int 
   for (int i = threadIdx.x; i < bytes / 16; i += NT) dst[i] = src[i];
 }
 __device__ __forceinline__ void copy_tile_in(const uint8_t* g, uint8_t* s, int bytes) {
+  // 16 KB blocks: 4 independent 128-bit loads per thread in flight
   const uint4* src = reinterpret_cast<const uint4*>(g);
   uint4* dst = reinterpret_cast<uint4*>(s);
-  for (int i = threadIdx.x; i < bytes / 16; i += NT) dst[i] = __ldg(src + i);
+  for (int i = threadIdx.x; i < bytes / 16; i += 4 * NT) {
+    uint4 v[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) v[j] = __ldg(src + i + j * NT);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) dst[i + j * NT] = v[j];
+  }
 }
 
 constexpr int MAXCH = 4;  // 16-column chunks per thread (n <= 128, two column halves)
@@ -230,41 +237,61 @@ rowmlp_tc_dgrad_kernel(const __grid_constant__ KParams p, const __grid_constant_
     }
 
     // ---------------- dOut rows -> fp32 staging (coalesced), rows >= cnt are zero
+    // batches of 4 units: indices first, then all data loads, then the stores
     {
       const int w4 = g.n2 >> 2;
-      for (int u = tid; u < TM * w4; u += NT) {
-        const int row = u / w4, c4 = u % w4, col = c4 * 4;
-        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (row < cnt && col < dout) {
-          float gs = 1.f;
-          const float* g1p = nullptr;
-          if (p.g1) {
-            const int gi = __ldg(p.g1_idx + row0 + row);
-            if (p.g1_scale) gs = __ldg(p.g1_scale + gi);
-            g1p = p.g1 + (size_t)b * p.g1_batch_stride + (size_t)gi * dout + col;
-          }
-          const float* g0p = p.g0 ? p.g0 + (grow0 + row) * dout + col : nullptr;
-          float tmp[4] = {0.f, 0.f, 0.f, 0.f};
-          if ((dout & 3) == 0) {
-            if (g0p) {
-              const float4 a = __ldg(reinterpret_cast<const float4*>(g0p));
-              tmp[0] = a.x, tmp[1] = a.y, tmp[2] = a.z, tmp[3] = a.w;
-            }
-            if (g1p) {
-              const float4 a = __ldg(reinterpret_cast<const float4*>(g1p));
-              tmp[0] += gs * a.x, tmp[1] += gs * a.y, tmp[2] += gs * a.z, tmp[3] += gs * a.w;
-            }
-          } else {
+      const bool vec = (dout & 3) == 0;
+      for (int base = tid; base < TM * w4; base += NT * 4) {
+        const float* g0p[4];
+        const float* g1p[4];
+        float gs[4];
+        int rowv[4], c4v[4], colv[4];
 #pragma unroll
-            for (int j = 0; j < 4; ++j)
-              if (col + j < dout) {
-                if (g0p) tmp[j] = __ldg(g0p + j);
-                if (g1p) tmp[j] += gs * __ldg(g1p + j);
+        for (int j = 0; j < 4; ++j) {
+          const int u = base + j * NT;
+          g0p[j] = g1p[j] = nullptr;
+          gs[j] = 1.f;
+          rowv[j] = -1;
+          if (u < TM * w4) {
+            const int row = u / w4, c4 = u % w4, col = c4 * 4;
+            rowv[j] = row, c4v[j] = c4, colv[j] = col;
+            if (row < cnt && col < dout) {
+              if (p.g0) g0p[j] = p.g0 + (grow0 + row) * dout + col;
+              if (p.g1) {
+                const int gi = __ldg(p.g1_idx + row0 + row);
+                if (p.g1_scale) gs[j] = __ldg(p.g1_scale + gi);
+                g1p[j] = p.g1 + (size_t)b * p.g1_batch_stride + (size_t)gi * dout + col;
               }
+            }
           }
-          v = make_float4(tmp[0], tmp[1], tmp[2], tmp[3]);
         }
-        *reinterpret_cast<float4*>(stg + stg_idx(row, c4, g.n2)) = v;
+        float4 va[4], vb[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          va[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+          vb[j] = va[j];
+          if (vec) {
+            if (g0p[j]) va[j] = __ldg(reinterpret_cast<const float4*>(g0p[j]));
+            if (g1p[j]) vb[j] = __ldg(reinterpret_cast<const float4*>(g1p[j]));
+          } else {
+            float t0[4] = {0.f, 0.f, 0.f, 0.f}, t1[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+            for (int e = 0; e < 4; ++e)
+              if (rowv[j] >= 0 && colv[j] + e < dout) {
+                if (g0p[j]) t0[e] = __ldg(g0p[j] + e);
+                if (g1p[j]) t1[e] = __ldg(g1p[j] + e);
+              }
+            va[j] = make_float4(t0[0], t0[1], t0[2], t0[3]);
+            vb[j] = make_float4(t1[0], t1[1], t1[2], t1[3]);
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          if (rowv[j] < 0) continue;
+          const float4 v = make_float4(va[j].x + gs[j] * vb[j].x, va[j].y + gs[j] * vb[j].y,
+                                       va[j].z + gs[j] * vb[j].z, va[j].w + gs[j] * vb[j].w);
+          *reinterpret_cast<float4*>(stg + stg_idx(rowv[j], c4v[j], g.n2)) = v;
+        }
       }
     }
 
