@@ -84,7 +84,7 @@ class ClockSampler:
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits",
-                 "-i", str(self.index), "-lms", "100"], stdout=subprocess.PIPE,
+                 "-i", str(self.index), "-lms", "50"], stdout=subprocess.PIPE,
                 stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
