@@ -35,8 +35,11 @@ struct Geo {
   int tiles_per_batch;
 };
 
+template <int FN>
 __global__ void __launch_bounds__(NT, 2)
 rowmlp_tc_fwd_kernel(const __grid_constant__ KParams p, const __grid_constant__ Geo g) {
+  constexpr bool F = FN > 0;  // square fast path: sizes are compile-time constants
+  const int n1 = F ? FN : g.n1, n2 = F ? FN : g.n2, k2 = F ? FN : g.k2;
   extern __shared__ __align__(1024) uint8_t sm[];
   if (smem_u32(sm) & 1023u) __trap();  // SWIZZLE_128B operands need 1024-byte alignment
   // region 0 is time-shared: A operand of GEMM 1 -> A operand of GEMM 2 ->
@@ -52,7 +55,7 @@ rowmlp_tc_fwd_kernel(const __grid_constant__ KParams p, const __grid_constant__ 
   float* stg = reinterpret_cast<float*>(sA);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int dh = p.d.d_hidden, dout = p.d.d_out;
+  const int dh = F ? FN : p.d.d_hidden, dout = F ? FN : p.d.d_out;
 
   if (warp == 0) tmem_alloc(tmem_slot, (uint32_t)g.tmem_cols);
   if (tid == 32) {
@@ -64,19 +67,19 @@ rowmlp_tc_fwd_kernel(const __grid_constant__ KParams p, const __grid_constant__ 
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const uint32_t tH = tmem_base, tY = tmem_base + (uint32_t)g.n1;
+  const uint32_t tH = tmem_base, tY = tmem_base + (uint32_t)n1;
   uint32_t ph0 = 0, ph1 = 0;
   int loaded_chunk = -1;
 
-  const uint32_t idesc1 = make_idesc_bf16(TM, g.n1);
-  const uint32_t idesc2 = make_idesc_bf16(TM, g.n2);
+  const uint32_t idesc1 = make_idesc_bf16(TM, n1);
+  const uint32_t idesc2 = make_idesc_bf16(TM, n2);
   const uint32_t a_blk = TM * 128u;
 
   // epilogue ownership: TMEM lane quarter q, row r, column half hf
   const int q = warp & 3, hf = warp >> 2, r = q * 32 + lane;
-  const int cp1 = g.n1 >= 32 ? g.n1 / 2 : g.n1, cp2 = g.n2 >= 32 ? g.n2 / 2 : g.n2;
-  const bool act1 = g.n1 >= 32 || hf == 0, act2 = g.n2 >= 32 || hf == 0;
-  const bool split2 = g.n2 >= 32;
+  const int cp1 = n1 >= 32 ? n1 / 2 : n1, cp2 = n2 >= 32 ? n2 / 2 : n2;
+  const bool act1 = n1 >= 32 || hf == 0, act2 = n2 >= 32 || hf == 0;
+  const bool split2 = n2 >= 32;
   const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
 
   for (int t = blockIdx.x; t < g.total_tiles; t += gridDim.x) {
@@ -85,14 +88,17 @@ rowmlp_tc_fwd_kernel(const __grid_constant__ KParams p, const __grid_constant__ 
     tile_range<TM>(p.d, tile, row0, cnt, chunk);
 
     if (chunk != loaded_chunk) {  // (re)load the weight set of this chunk
-      stage_weight(p.d.w.w1 + (size_t)chunk * dh * p.k_total, dh, p.k_total, g.n1, g.k1, sW1);
-      stage_weight(p.d.w.w2 + (size_t)chunk * dout * dh, dout, dh, g.n2, g.k2, sW2);
-      stage_params(p.d, chunk, g.n1, g.n2, sPar);
+      stage_weight(p.d.w.w1 + (size_t)chunk * dh * p.k_total, dh, p.k_total, n1, g.k1, sW1);
+      stage_weight(p.d.w.w2 + (size_t)chunk * dout * dh, dout, dh, n2, k2, sW2);
+      stage_params(p.d, chunk, n1, n2, sPar);
       loaded_chunk = chunk;
     }
 
     // ---------------- gather: fp32 rows -> bf16 A operand
-    gather_rows(p, b, row0, cnt, 0, g.k1, sA);
+    if (F)
+      gather_rows_fast<(F ? FN : 64)>(p, b, row0, cnt, 0, p.d.n_src, sA);
+    else
+      gather_rows(p, b, row0, cnt, 0, g.k1, sA);
     fence_async_smem();
     __syncthreads();
 
@@ -100,7 +106,7 @@ rowmlp_tc_fwd_kernel(const __grid_constant__ KParams p, const __grid_constant__ 
     if (tid == 0) {
       tc_fence_after();
       const uint32_t a0 = smem_u32(sA), w0 = smem_u32(sW1);
-      const uint32_t w_blk = (uint32_t)g.n1 * 128u;
+      const uint32_t w_blk = (uint32_t)n1 * 128u;
       for (int ks = 0; ks < g.k1 / 16; ++ks) {
         const uint32_t kb = ks >> 2, kin = (ks & 3) * 32;
         umma_bf16(tH, make_desc_k_sw128(a0 + kb * a_blk + kin),
@@ -138,8 +144,8 @@ rowmlp_tc_fwd_kernel(const __grid_constant__ KParams p, const __grid_constant__ 
     if (tid == 0) {
       tc_fence_after();
       const uint32_t a0 = smem_u32(sA2), w0 = smem_u32(sW2);
-      const uint32_t w_blk = (uint32_t)g.n2 * 128u;
-      for (int ks = 0; ks < g.k2 / 16; ++ks) {
+      const uint32_t w_blk = (uint32_t)n2 * 128u;
+      for (int ks = 0; ks < k2 / 16; ++ks) {
         const uint32_t kb = ks >> 2, kin = (ks & 3) * 32;
         umma_bf16(tY, make_desc_k_sw128(a0 + kb * a_blk + kin),
                   make_desc_k_sw128(w0 + kb * w_blk + kin), idesc2, ks > 0);
@@ -151,9 +157,9 @@ rowmlp_tc_fwd_kernel(const __grid_constant__ KParams p, const __grid_constant__ 
     tc_fence_after();
 
     // ---------------- epilogue 2: y + b2 -> LayerNorm -> fp32 staging tile
-    const float* sB2 = sPar + g.n1;
-    const float* sG = sB2 + g.n2;
-    const float* sBe = sG + g.n2;
+    const float* sB2 = sPar + n1;
+    const float* sG = sB2 + n2;
+    const float* sBe = sG + n2;
     float mean = 0.f, rstd = 1.f;
     if (p.d.w.ln_g) {
       float s = 0.f;
@@ -164,7 +170,7 @@ rowmlp_tc_fwd_kernel(const __grid_constant__ KParams p, const __grid_constant__ 
           tmem_ld16(tY + lane_addr + (uint32_t)c0, v);
 #pragma unroll
           for (int j = 0; j < 16; ++j)
-            if (c0 + j < dout) s += v[j] + sB2[c0 + j];
+            if (F || c0 + j < dout) s += v[j] + sB2[c0 + j];
         }
       sLnx[(0 * TM + r) * 2 + hf] = s;
       __syncthreads();
@@ -177,7 +183,7 @@ rowmlp_tc_fwd_kernel(const __grid_constant__ KParams p, const __grid_constant__ 
           tmem_ld16(tY + lane_addr + (uint32_t)c0, v);
 #pragma unroll
           for (int j = 0; j < 16; ++j)
-            if (c0 + j < dout) {
+            if (F || c0 + j < dout) {
               const float dl = v[j] + sB2[c0 + j] - mean;
               qq += dl * dl;
             }
@@ -297,17 +303,25 @@ int tc_rowmlp_fwd(const nlam_rowmlp& d, cudaStream_t st) {
   NLAM_CHECK(d.out, "rowmlp: out is NULL");
   tc::Geo g{};
   if (tc::make_geo(p, g)) return 1;
-  static int max_set = 0;
-  if ((int)g.smem_bytes > max_set) {
-    NLAM_CUDA(cudaFuncSetAttribute(tc::rowmlp_tc_fwd_kernel,
-                                   cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem_bytes));
-    max_set = (int)g.smem_bytes;
-  }
   int per_sm = g.smem_bytes <= 113 * 1024 ? 2 : 1;
   if (g.tmem_cols * per_sm > 512) per_sm = 1;
   int grid = 148 * per_sm;
   if (grid > g.total_tiles) grid = g.total_tiles;
-  tc::rowmlp_tc_fwd_kernel<<<grid, tc::NT, g.smem_bytes, st>>>(p, g);
+  const int fn = tc::fast_n(p);
+  auto launch = [&](auto kern, int& max_set) -> int {
+    if ((int)g.smem_bytes > max_set) {
+      NLAM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)g.smem_bytes));
+      max_set = (int)g.smem_bytes;
+    }
+    kern<<<grid, tc::NT, g.smem_bytes, st>>>(p, g);
+    return 0;
+  };
+  static int ms0 = 0, ms64 = 0, ms128 = 0;
+  int rc = fn == 64    ? launch(tc::rowmlp_tc_fwd_kernel<64>, ms64)
+           : fn == 128 ? launch(tc::rowmlp_tc_fwd_kernel<128>, ms128)
+                       : launch(tc::rowmlp_tc_fwd_kernel<0>, ms0);
+  if (rc) return rc;
   NLAM_CUDA(cudaGetLastError());
   count_launch();
   return 0;

@@ -102,6 +102,60 @@ __device__ __forceinline__ void gather_rows(const KParams& p, int b, int row0, i
   }
 }
 
+// Fast gather for the square case: every source is exactly FN floats wide and
+// 16-byte aligned.  Thread (rl, c) handles chunk c of rows rl, rl+RPP, ...: no
+// divisions, all row indices then all 2*NP 128-bit loads issued before use.
+// Source s lands at A-tile columns [(s - s_begin)*FN, ...).
+template <int FN>
+__device__ __forceinline__ void gather_rows_fast(const KParams& p, int b, int row0, int cnt,
+                                                 int s_begin, int s_end, uint8_t* sA) {
+  constexpr int CPR = FN / 8;    // 16-byte bf16 chunks per source row
+  constexpr int RPP = NT / CPR;  // rows per pass
+  constexpr int NP = TM / RPP;   // passes
+  const int c = threadIdx.x % CPR, rl = threadIdx.x / CPR;
+  const uint32_t a_blk = TM * 128u;
+  for (int s = s_begin; s < s_end; ++s) {
+    const nlam_src& src = p.d.src[s];
+    const float* base = src.ptr + (long long)b * src.batch_stride + c * 8;
+    const int32_t* idx = src.idx;
+    const int ld = src.ld;
+    int ridx[NP];
+#pragma unroll
+    for (int i = 0; i < NP; ++i) {
+      const int row = i * RPP + rl;
+      ridx[i] = row < cnt ? (idx ? __ldg(idx + row0 + row) : row0 + row) : -1;
+    }
+    float4 x[NP], y[NP];
+#pragma unroll
+    for (int i = 0; i < NP; ++i) {
+      x[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      y[i] = x[i];
+      if (ridx[i] >= 0) {
+        const float4* q = reinterpret_cast<const float4*>(base + (long long)ridx[i] * ld);
+        x[i] = __ldg(q);
+        y[i] = __ldg(q + 1);
+      }
+    }
+    const int kcol = (s - s_begin) * FN + c * 8;
+#pragma unroll
+    for (int i = 0; i < NP; ++i) {
+      const int row = i * RPP + rl;
+      uint4 pk = make_uint4(pack_bf16(x[i].x, x[i].y), pack_bf16(x[i].z, x[i].w),
+                            pack_bf16(y[i].x, y[i].y), pack_bf16(y[i].z, y[i].w));
+      *reinterpret_cast<uint4*>(sA + sw128_off(row, kcol, a_blk)) = pk;
+    }
+  }
+}
+
+// square fast path: d_hidden == d_out == FN, every source FN wide and vectorisable
+inline int fast_n(const KParams& p) {
+  const nlam_rowmlp& d = p.d;
+  if (d.d_hidden != d.d_out || (d.d_hidden != 64 && d.d_hidden != 128)) return 0;
+  for (int s = 0; s < d.n_src; ++s)
+    if (d.src[s].width != d.d_hidden || !p.vec_ok[s]) return 0;
+  return d.d_hidden;
+}
+
 // b1[n1] | b2[n2] | gamma[n2] | beta[n2], zero / identity padded
 __device__ __forceinline__ void stage_params(const nlam_rowmlp& d, int chunk, int n1, int n2,
                                              float* sPar, int n_vec = 3) {

@@ -112,8 +112,13 @@ __device__ __forceinline__ void copy_tile_in(const uint8_t* g, uint8_t* s, int b
 
 constexpr int MAXCH = 4;  // 16-column chunks per thread (n <= 128, two column halves)
 
+template <int FN>
 __global__ void __launch_bounds__(NT, 2)
 rowmlp_tc_dgrad_kernel(const __grid_constant__ KParams p, const __grid_constant__ BGeo g) {
+  constexpr bool F = FN > 0;  // square fast path: sizes are compile-time constants
+  const int n1 = F ? FN : g.n1, n2 = F ? FN : g.n2;
+  const int k2 = F ? FN : g.k2, ko = F ? FN : g.ko;
+  const int kb2 = F ? FN / 64 : g.kb2, kbo = F ? FN / 64 : g.kbo;
   extern __shared__ __align__(1024) uint8_t sm[];
   if (smem_u32(sm) & 1023u) __trap();
   uint8_t* sA = sm;                     // z blocks of one gather round | fp32 staging
@@ -128,7 +133,7 @@ rowmlp_tc_dgrad_kernel(const __grid_constant__ KParams p, const __grid_constant_
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int dh = p.d.d_hidden, dout = p.d.d_out;
+  const int dh = F ? FN : p.d.d_hidden, dout = F ? FN : p.d.d_out;
   const bool has_ln = p.d.w.ln_g != nullptr;
 
   if (warp == 0) tmem_alloc(tmem_slot, (uint32_t)g.tmem_cols);
@@ -147,18 +152,18 @@ rowmlp_tc_dgrad_kernel(const __grid_constant__ KParams p, const __grid_constant_
   int loaded_chunk = -1;
 
   const uint32_t a_blk = TM * 128u;
-  const uint32_t idesc1 = make_idesc_bf16(TM, g.n1);
-  const uint32_t idesc2 = make_idesc_bf16(TM, g.n2);
-  const uint32_t idesc3 = make_idesc_bf16(TM, g.n1, 0, 1);  // B = W2 viewed MN-major
+  const uint32_t idesc1 = make_idesc_bf16(TM, n1);
+  const uint32_t idesc2 = make_idesc_bf16(TM, n2);
+  const uint32_t idesc3 = make_idesc_bf16(TM, n1, 0, 1);  // B = W2 viewed MN-major
   const uint32_t idesc4 = make_idesc_bf16(TM, 64, 0, 1);    // B = W1 block viewed MN-major
 
   const int q = warp & 3, hf = warp >> 2, r = q * 32 + lane;
-  const int cp1 = g.n1 >= 32 ? g.n1 / 2 : g.n1, cp2 = g.n2 >= 32 ? g.n2 / 2 : g.n2;
-  const bool act1 = g.n1 >= 32 || hf == 0, act2 = g.n2 >= 32 || hf == 0;
-  const bool split2 = g.n2 >= 32;
+  const int cp1 = n1 >= 32 ? n1 / 2 : n1, cp2 = n2 >= 32 ? n2 / 2 : n2;
+  const bool act1 = n1 >= 32 || hf == 0, act2 = n2 >= 32 || hf == 0;
+  const bool split2 = n2 >= 32;
   const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
-  const float* sB2 = sPar + g.n1;
-  const float* sG = sB2 + g.n2;
+  const float* sB2 = sPar + n1;
+  const float* sG = sB2 + n2;
 
   // per-CTA column-sum accumulators (lane l owns column c0 + (l & 15) of each chunk)
   float acc_db1[MAXCH], acc_db2[MAXCH], acc_dg[MAXCH], acc_dbt[MAXCH];
@@ -183,7 +188,7 @@ rowmlp_tc_dgrad_kernel(const __grid_constant__ KParams p, const __grid_constant_
     // which: 0 db1 (n1 cols), 1 db2, 2 dgamma, 3 dbeta (n2 cols)
     for (int e = tid; e < 4 * 128; e += NT) {
       const int which = e >> 7, col = e & 127;
-      const int n = which == 0 ? g.n1 : g.n2, cp = which == 0 ? cp1 : cp2;
+      const int n = which == 0 ? n1 : n2, cp = which == 0 ? cp1 : cp2;
       const int real = which == 0 ? dh : dout;
       if (col >= n || col >= real) continue;
       if (which >= 2 && !has_ln) continue;
@@ -207,9 +212,9 @@ rowmlp_tc_dgrad_kernel(const __grid_constant__ KParams p, const __grid_constant_
 
     if (chunk != loaded_chunk) {
       if (loaded_chunk >= 0) flush_colsums(loaded_chunk);
-      stage_weight(p.d.w.w1 + (size_t)chunk * dh * p.k_total, dh, p.k_total, g.n1, g.k1, sW1);
-      stage_weight(p.d.w.w2 + (size_t)chunk * dout * dh, dout, dh, g.n2, g.k2, sW2);
-      stage_params(p.d, chunk, g.n1, g.n2, sPar, 2);  // beta is not needed backward
+      stage_weight(p.d.w.w1 + (size_t)chunk * dh * p.k_total, dh, p.k_total, n1, g.k1, sW1);
+      stage_weight(p.d.w.w2 + (size_t)chunk * dout * dh, dout, dh, n2, k2, sW2);
+      stage_params(p.d, chunk, n1, n2, sPar, 2);  // beta is not needed backward
       loaded_chunk = chunk;
     }
 
@@ -217,13 +222,17 @@ rowmlp_tc_dgrad_kernel(const __grid_constant__ KParams p, const __grid_constant_
     for (int kb0 = 0; kb0 < g.kb1; kb0 += g.rb) {
       const int kbe = min(g.kb1, kb0 + g.rb);
       const int k_begin = kb0 * 64, k_end = min(g.k1, kbe * 64);
-      gather_rows(p, b, row0, cnt, k_begin, k_end, sA);
+      if (F)
+        gather_rows_fast<(F ? FN : 64)>(p, b, row0, cnt, k_begin / (F ? FN : 64),
+                                        k_end / (F ? FN : 64), sA);
+      else
+        gather_rows(p, b, row0, cnt, k_begin, k_end, sA);
       fence_async_smem();
       __syncthreads();
       if (tid == 0) {
         tc_fence_after();
         const uint32_t a0 = smem_u32(sA), w0 = smem_u32(sW1);
-        const uint32_t w_blk = (uint32_t)g.n1 * 128u;
+        const uint32_t w_blk = (uint32_t)n1 * 128u;
         for (int ks = k_begin / 16; ks < k_end / 16; ++ks) {
           const uint32_t kb = ks >> 2, kin = (ks & 3) * 32;
           umma_bf16(tH, make_desc_k_sw128(a0 + (kb - kb0) * a_blk + kin),
@@ -239,7 +248,7 @@ rowmlp_tc_dgrad_kernel(const __grid_constant__ KParams p, const __grid_constant_
     // ---------------- dOut rows -> fp32 staging (coalesced), rows >= cnt are zero
     // batches of 4 units: indices first, then all data loads, then the stores
     {
-      const int w4 = g.n2 >> 2;
+      const int w4 = n2 >> 2;
       const bool vec = (dout & 3) == 0;
       for (int base = tid; base < TM * w4; base += NT * 4) {
         const float* g0p[4];
@@ -290,7 +299,7 @@ rowmlp_tc_dgrad_kernel(const __grid_constant__ KParams p, const __grid_constant_
           if (rowv[j] < 0) continue;
           const float4 v = make_float4(va[j].x + gs[j] * vb[j].x, va[j].y + gs[j] * vb[j].y,
                                        va[j].z + gs[j] * vb[j].z, va[j].w + gs[j] * vb[j].w);
-          *reinterpret_cast<float4*>(stg + stg_idx(rowv[j], c4v[j], g.n2)) = v;
+          *reinterpret_cast<float4*>(stg + stg_idx(rowv[j], c4v[j], n2)) = v;
         }
       }
     }
@@ -321,15 +330,15 @@ rowmlp_tc_dgrad_kernel(const __grid_constant__ KParams p, const __grid_constant_
     if (tid == 0) {
       tc_fence_after();
       const uint32_t a0 = smem_u32(sT), w0 = smem_u32(sW2);
-      const uint32_t w_blk = (uint32_t)g.n2 * 128u;
-      for (int ks = 0; ks < g.k2 / 16; ++ks) {
+      const uint32_t w_blk = (uint32_t)n2 * 128u;
+      for (int ks = 0; ks < k2 / 16; ++ks) {
         const uint32_t kb = ks >> 2, kin = (ks & 3) * 32;
         umma_bf16(tY, make_desc_k_sw128(a0 + kb * a_blk + kin),
                   make_desc_k_sw128(w0 + kb * w_blk + kin), idesc2, ks > 0);
       }
       umma_commit(&bars[0]);
     }
-    copy_tile_out(sT, g.a_img + (size_t)t * g.kb2 * a_blk, g.kb2 * a_blk);
+    copy_tile_out(sT, g.a_img + (size_t)t * kb2 * a_blk, kb2 * a_blk);
     mbar_wait(&bars[0], ph_main);
     ph_main ^= 1;
     tc_fence_after();
@@ -345,7 +354,7 @@ rowmlp_tc_dgrad_kernel(const __grid_constant__ KParams p, const __grid_constant_
           tmem_ld16(tY + lane_addr + (uint32_t)c0, v);
 #pragma unroll
           for (int j = 0; j < 16; ++j)
-            if (c0 + j < dout) s += v[j] + sB2[c0 + j];
+            if (F || c0 + j < dout) s += v[j] + sB2[c0 + j];
         }
       sLnx[r * 2 + hf] = s;
       __syncthreads();
@@ -359,7 +368,7 @@ rowmlp_tc_dgrad_kernel(const __grid_constant__ KParams p, const __grid_constant_
           tmem_ld16(tY + lane_addr + (uint32_t)c0, v);
 #pragma unroll
           for (int j = 0; j < 16; ++j)
-            if (c0 + j < dout) {
+            if (F || c0 + j < dout) {
               const float dl = v[j] + sB2[c0 + j] - mean;
               qq += dl * dl;
             }
@@ -381,7 +390,7 @@ rowmlp_tc_dgrad_kernel(const __grid_constant__ KParams p, const __grid_constant_
 #pragma unroll
             for (int j4 = 0; j4 < 4; ++j4) {
               const float4 d4 =
-                  *reinterpret_cast<const float4*>(stg + stg_idx(r, (c0 >> 2) + j4, g.n2));
+                  *reinterpret_cast<const float4*>(stg + stg_idx(r, (c0 >> 2) + j4, n2));
               dmv[j4 * 4] = d4.x, dmv[j4 * 4 + 1] = d4.y, dmv[j4 * 4 + 2] = d4.z,
                        dmv[j4 * 4 + 3] = d4.w;
             }
@@ -389,8 +398,8 @@ rowmlp_tc_dgrad_kernel(const __grid_constant__ KParams p, const __grid_constant_
             for (int j = 0; j < 16; ++j) {
               const float yh = (v[j] + sB2[c0 + j] - mean) * rstd;
               const float dyh = dmv[j] * sG[c0 + j];
-              pv[j] = (c0 + j < dout) ? dmv[j] * yh : 0.f;
-              if (c0 + j < dout) {
+              pv[j] = (F || c0 + j < dout) ? dmv[j] * yh : 0.f;
+              if (F || c0 + j < dout) {
                 s1 += dyh;
                 s2 += dyh * yh;
               }
@@ -419,7 +428,7 @@ rowmlp_tc_dgrad_kernel(const __grid_constant__ KParams p, const __grid_constant_
 #pragma unroll
           for (int j4 = 0; j4 < 4; ++j4) {
             const float4 d4 =
-                *reinterpret_cast<const float4*>(stg + stg_idx(r, (c0 >> 2) + j4, g.n2));
+                *reinterpret_cast<const float4*>(stg + stg_idx(r, (c0 >> 2) + j4, n2));
             dmv[j4 * 4] = d4.x, dmv[j4 * 4 + 1] = d4.y, dmv[j4 * 4 + 2] = d4.z,
                      dmv[j4 * 4 + 3] = d4.w;
           }
@@ -429,11 +438,11 @@ rowmlp_tc_dgrad_kernel(const __grid_constant__ KParams p, const __grid_constant_
             for (int j = 0; j < 16; ++j) {
               const float yh = (v[j] + sB2[c0 + j] - mean) * rstd;
               const float dyh = dmv[j] * sG[c0 + j];
-              v[j] = (c0 + j < dout && r < cnt) ? rstd * (dyh - m1 - yh * m2) : 0.f;
+              v[j] = ((F || c0 + j < dout) && r < cnt) ? rstd * (dyh - m1 - yh * m2) : 0.f;
             }
           } else {
 #pragma unroll
-            for (int j = 0; j < 16; ++j) v[j] = (c0 + j < dout) ? dmv[j] : 0.f;
+            for (int j = 0; j < 16; ++j) v[j] = (F || c0 + j < dout) ? dmv[j] : 0.f;
           }
           acc_db2[ci] += warp_colsum16(v, lane);
 #pragma unroll
@@ -455,15 +464,15 @@ rowmlp_tc_dgrad_kernel(const __grid_constant__ KParams p, const __grid_constant_
     if (tid == 0) {
       tc_fence_after();
       const uint32_t a0 = smem_u32(sT), w0 = smem_u32(sW2);
-      const uint32_t lbo = (uint32_t)g.n2 * 128u;  // 64-wide blocks of the hidden dim
-      for (int ks = 0; ks < g.ko / 16; ++ks) {
+      const uint32_t lbo = (uint32_t)n2 * 128u;  // 64-wide blocks of the hidden dim
+      for (int ks = 0; ks < ko / 16; ++ks) {
         const uint32_t kb = ks >> 2, kin = (ks & 3) * 32;
         umma_bf16(tY, make_desc_k_sw128(a0 + kb * a_blk + kin),
                   make_desc_mn_sw128(w0 + (uint32_t)ks * 2048u, lbo), idesc3, ks > 0);
       }
       umma_commit(&bars[0]);
     }
-    copy_tile_out(sT, g.dy_img + (size_t)t * g.kbo * a_blk, g.kbo * a_blk);
+    copy_tile_out(sT, g.dy_img + (size_t)t * kbo * a_blk, kbo * a_blk);
     mbar_wait(&bars[0], ph_main);
     ph_main ^= 1;
     tc_fence_after();
@@ -481,7 +490,7 @@ rowmlp_tc_dgrad_kernel(const __grid_constant__ KParams p, const __grid_constant_
           tmem_ld16(tH + lane_addr + (uint32_t)c0, h);
 #pragma unroll
           for (int j = 0; j < 16; ++j)
-            v[j] = (c0 + j < dh) ? v[j] * silu_grad_fast(h[j] + sPar[c0 + j]) : 0.f;
+            v[j] = (F || c0 + j < dh) ? v[j] * silu_grad_fast(h[j] + sPar[c0 + j]) : 0.f;
           acc_db1[ci] += warp_colsum16(v, lane);
 #pragma unroll
           for (int h8 = 0; h8 < 2; ++h8) {
@@ -497,15 +506,15 @@ rowmlp_tc_dgrad_kernel(const __grid_constant__ KParams p, const __grid_constant_
     fence_async_smem();
     tc_fence_before();
     __syncthreads();
-    copy_tile_out(sT, g.dh_img + (size_t)t * g.kb2 * a_blk, g.kb2 * a_blk);
+    copy_tile_out(sT, g.dh_img + (size_t)t * kb2 * a_blk, kb2 * a_blk);
 
     // ---------------- GEMM 4 + epilogue 4: dZ = dH . W1, 64 input columns at a time
     if (g.need_dz) {
       auto issue_dz = [&](int kb) {
         tc_fence_after();
         const uint32_t a0 = smem_u32(sT);
-        const uint32_t w0 = smem_u32(sW1) + (uint32_t)kb * (uint32_t)g.n1 * 128u;
-        for (int ks = 0; ks < g.k2 / 16; ++ks) {
+        const uint32_t w0 = smem_u32(sW1) + (uint32_t)kb * (uint32_t)n1 * 128u;
+        for (int ks = 0; ks < k2 / 16; ++ks) {
           const uint32_t kbb = ks >> 2, kin = (ks & 3) * 32;
           umma_bf16(tZ + (uint32_t)(kb & 1) * 64u, make_desc_k_sw128(a0 + kbb * a_blk + kin),
                     make_desc_mn_sw128(w0 + (uint32_t)ks * 2048u, 0), idesc4, ks > 0);
@@ -570,8 +579,12 @@ rowmlp_tc_dgrad_kernel(const __grid_constant__ KParams p, const __grid_constant_
 }
 
 // -------------------------------------------------------------------- wgrad
+template <int FN>
 __global__ void __launch_bounds__(NT, 2)
 rowmlp_tc_wgrad_kernel(const __grid_constant__ KParams p, const __grid_constant__ BGeo g) {
+  constexpr bool F = FN > 0;
+  const int n1 = F ? FN : g.n1, n2 = F ? FN : g.n2;
+  const int kb2 = F ? FN / 64 : g.kb2, kbo = F ? FN / 64 : g.kbo;
   extern __shared__ __align__(1024) uint8_t sm[];
   if (smem_u32(sm) & 1023u) __trap();
   uint8_t* sZ = sm;
@@ -582,7 +595,7 @@ rowmlp_tc_wgrad_kernel(const __grid_constant__ KParams p, const __grid_constant_
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 1);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int dh = p.d.d_hidden, dout = p.d.d_out;
+  const int dh = F ? FN : p.d.d_hidden, dout = F ? FN : p.d.d_out;
   if (warp == 0) tmem_alloc(tmem_slot, (uint32_t)g.w_tmem_cols);
   if (tid == 32) {
     mbar_init(&bars[0], 1);
@@ -592,11 +605,11 @@ rowmlp_tc_wgrad_kernel(const __grid_constant__ KParams p, const __grid_constant_
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const uint32_t tW2 = tmem_base + (uint32_t)(g.w_mchunks * g.n1);
+  const uint32_t tW2 = tmem_base + (uint32_t)(g.w_mchunks * n1);
   uint32_t ph = 0;
   const uint32_t a_blk = TM * 128u;
-  const uint32_t idesc_w1 = make_idesc_bf16(TM, g.n1, 1, 1);
-  const uint32_t idesc_w2 = make_idesc_bf16(TM, g.n2, 1, 1);
+  const uint32_t idesc_w1 = make_idesc_bf16(TM, n1, 1, 1);
+  const uint32_t idesc_w2 = make_idesc_bf16(TM, n2, 1, 1);
   const int q = warp & 3, hf = warp >> 2, r = q * 32 + lane;
   const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
   int cur_chunk = -1;
@@ -607,24 +620,24 @@ rowmlp_tc_wgrad_kernel(const __grid_constant__ KParams p, const __grid_constant_
     tc_fence_after();
     const ParamLayout lay = p.lay;
     float* dst = g.partial + ((size_t)blockIdx.x * p.d.n_chunks + chunk) * g.p_total;
-    const int cpa = g.n1 >= 32 ? g.n1 / 2 : g.n1;
-    if (g.n1 >= 32 || hf == 0) {
+    const int cpa = n1 >= 32 ? n1 / 2 : n1;
+    if (n1 >= 32 || hf == 0) {
       for (int mc = 0; mc < g.w_mchunks; ++mc) {
         const int kg = mc * 128 + r;  // input column
         for (int cc = 0; cc < cpa; cc += 16) {
           const int c0 = hf * cpa + cc;
           float v[16];
-          tmem_ld16(tmem_base + (uint32_t)(mc * g.n1) + lane_addr + (uint32_t)c0, v);
+          tmem_ld16(tmem_base + (uint32_t)(mc * n1) + lane_addr + (uint32_t)c0, v);
           if (kg < p.k_total) {
 #pragma unroll
             for (int j = 0; j < 16; ++j)
-              if (c0 + j < dh) dst[lay.off_w1() + (size_t)(c0 + j) * p.k_total + kg] = v[j];
+              if (F || c0 + j < dh) dst[lay.off_w1() + (size_t)(c0 + j) * p.k_total + kg] = v[j];
           }
         }
       }
     }
-    const int cpb = g.n2 >= 32 ? g.n2 / 2 : g.n2;
-    if (g.n2 >= 32 || hf == 0) {
+    const int cpb = n2 >= 32 ? n2 / 2 : n2;
+    if (n2 >= 32 || hf == 0) {
       for (int cc = 0; cc < cpb; cc += 16) {
         const int c0 = hf * cpb + cc;
         float v[16];
@@ -632,7 +645,7 @@ rowmlp_tc_wgrad_kernel(const __grid_constant__ KParams p, const __grid_constant_
         if (r < dh) {
 #pragma unroll
           for (int j = 0; j < 16; ++j)
-            if (c0 + j < dout) dst[lay.off_w2() + (size_t)(c0 + j) * dh + r] = v[j];
+            if (F || c0 + j < dout) dst[lay.off_w2() + (size_t)(c0 + j) * dh + r] = v[j];
         }
       }
     }
@@ -649,10 +662,13 @@ rowmlp_tc_wgrad_kernel(const __grid_constant__ KParams p, const __grid_constant_
       cur_chunk = chunk;
       first = true;
     }
-    gather_rows(p, b, row0, cnt, 0, g.k1, sZ);
-    copy_tile_in(g.a_img + (size_t)t * g.kb2 * a_blk, sAi, g.kb2 * a_blk);
-    copy_tile_in(g.dy_img + (size_t)t * g.kbo * a_blk, sDY, g.kbo * a_blk);
-    copy_tile_in(g.dh_img + (size_t)t * g.kb2 * a_blk, sDH, g.kb2 * a_blk);
+    if (F)
+      gather_rows_fast<(F ? FN : 64)>(p, b, row0, cnt, 0, p.d.n_src, sZ);
+    else
+      gather_rows(p, b, row0, cnt, 0, g.k1, sZ);
+    copy_tile_in(g.a_img + (size_t)t * kb2 * a_blk, sAi, kb2 * a_blk);
+    copy_tile_in(g.dy_img + (size_t)t * kbo * a_blk, sDY, kbo * a_blk);
+    copy_tile_in(g.dh_img + (size_t)t * kb2 * a_blk, sDH, kb2 * a_blk);
     fence_async_smem();
     __syncthreads();
     if (tid == 0) {
@@ -660,7 +676,7 @@ rowmlp_tc_wgrad_kernel(const __grid_constant__ KParams p, const __grid_constant_
       const uint32_t z0 = smem_u32(sZ), a0 = smem_u32(sAi), y0 = smem_u32(sDY), h0 = smem_u32(sDH);
       for (int mc = 0; mc < g.w_mchunks; ++mc)
         for (int ks = 0; ks < TM / 16; ++ks)
-          umma_bf16(tmem_base + (uint32_t)(mc * g.n1),
+          umma_bf16(tmem_base + (uint32_t)(mc * n1),
                     make_desc_mn_sw128(z0 + (uint32_t)mc * 2u * a_blk + (uint32_t)ks * 2048u, a_blk),
                     make_desc_mn_sw128(h0 + (uint32_t)ks * 2048u, a_blk), idesc_w1,
                     (!first || ks > 0) ? 1u : 0u);
@@ -696,7 +712,7 @@ static int make_bgeo(const KParams& p, BGeo& g) {
   g.k2 = (d.d_hidden + 15) / 16 * 16;
   g.ko = (d.d_out + 15) / 16 * 16;
   g.kb1 = (g.k1 + 63) / 64, g.kb2 = (g.n1 + 63) / 64, g.kbo = (g.n2 + 63) / 64;
-  g.rb = 3;
+  g.rb = (fast_n(p) == 128) ? 2 : 3;  // fast gather works on whole sources
   g.cY = g.n1, g.cZ = g.n1 + g.nmax;
   g.tmem_cols = pow2_cols(g.cZ + 128);
   const uint32_t blk = TM * 128u;
@@ -801,25 +817,32 @@ int tc_rowmlp_bwd(const nlam_rowmlp_bwd& bd, cudaStream_t st) {
   g.partial = bd.workspace + ws.partial;
   NLAM_CUDA(cudaMemsetAsync(g.partial, 0,
                             sizeof(float) * (size_t)ws.slots * d.n_chunks * g.p_total, st));
-  static int max_d = 0, max_w = 0;
-  if ((int)g.smem_bytes > max_d) {
-    NLAM_CUDA(cudaFuncSetAttribute(tc::rowmlp_tc_dgrad_kernel,
-                                   cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem_bytes));
-    max_d = (int)g.smem_bytes;
-  }
-  if ((int)g.w_smem_bytes > max_w) {
-    NLAM_CUDA(cudaFuncSetAttribute(tc::rowmlp_tc_wgrad_kernel,
-                                   cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.w_smem_bytes));
-    max_w = (int)g.w_smem_bytes;
-  }
+  const int fn = tc::fast_n(p);
   const int gd = tc::grid_for(g.smem_bytes, g.tmem_cols, g.total_tiles);
-  tc::rowmlp_tc_dgrad_kernel<<<gd, tc::NT, g.smem_bytes, st>>>(p, g);
-  NLAM_CUDA(cudaGetLastError());
-  count_launch();
   const int gw = tc::grid_for(g.w_smem_bytes, g.w_tmem_cols, g.total_tiles);
-  tc::rowmlp_tc_wgrad_kernel<<<gw, tc::NT, g.w_smem_bytes, st>>>(p, g);
-  NLAM_CUDA(cudaGetLastError());
-  count_launch();
+  auto launch = [&](auto kern, int& max_set, int grid, uint32_t smem) -> int {
+    if ((int)smem > max_set) {
+      NLAM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      max_set = (int)smem;
+    }
+    kern<<<grid, tc::NT, smem, st>>>(p, g);
+    NLAM_CUDA(cudaGetLastError());
+    count_launch();
+    return 0;
+  };
+  static int md[3] = {0, 0, 0}, mw[3] = {0, 0, 0};
+  int rc;
+  if (fn == 64) {
+    rc = launch(tc::rowmlp_tc_dgrad_kernel<64>, md[1], gd, g.smem_bytes);
+    if (!rc) rc = launch(tc::rowmlp_tc_wgrad_kernel<64>, mw[1], gw, g.w_smem_bytes);
+  } else if (fn == 128) {
+    rc = launch(tc::rowmlp_tc_dgrad_kernel<128>, md[2], gd, g.smem_bytes);
+    if (!rc) rc = launch(tc::rowmlp_tc_wgrad_kernel<128>, mw[2], gw, g.w_smem_bytes);
+  } else {
+    rc = launch(tc::rowmlp_tc_dgrad_kernel<0>, md[0], gd, g.smem_bytes);
+    if (!rc) rc = launch(tc::rowmlp_tc_wgrad_kernel<0>, mw[0], gw, g.w_smem_bytes);
+  }
+  if (rc) return rc;
   return launch_reduce_params(g.partial, ws.slots, d.n_chunks, g.p_total, bd.d_params, st);
 }
 
