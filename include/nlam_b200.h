@@ -75,6 +75,10 @@ typedef struct nlam_rowmlp {
   int32_t n_tiles;
   int32_t residual_src;       /* -1, or s: out += src_s row (needs width==d_out) */
   float* out;                 /* [batch, rows, d_out] contiguous */
+  float* out_res;             /* optional second output: src_0 row + (the value
+                                 written to out); InteractionNet needs both the
+                                 message m_k and e_k + m_k (interaction_net.py:
+                                 112,131).  NULL = not wanted */
   int32_t precision;          /* NLAM_FP32 | NLAM_BF16 */
 } nlam_rowmlp;
 

@@ -68,7 +68,10 @@ inline int fill_params(const nlam_rowmlp& d, KParams& p) {
   NLAM_CHECK(d.residual_src == -1 || d.residual_src == 0, "rowmlp: residual_src must be -1 or 0");
   NLAM_CHECK(d.residual_src < 0 || d.src[0].width == d.d_out,
              "rowmlp: residual source width %d != d_out %d", d.src[0].width, d.d_out);
-  p.out_vec_ok = (d.d_out % 4 == 0) && (((uintptr_t)d.out) % 16 == 0);
+  NLAM_CHECK(!d.out_res || (d.residual_src < 0 && d.src[0].width == d.d_out),
+             "rowmlp: out_res needs residual_src == -1 and src[0].width == d_out");
+  p.out_vec_ok = (d.d_out % 4 == 0) && (((uintptr_t)d.out) % 16 == 0) &&
+                 (((uintptr_t)d.out_res) % 16 == 0);
   p.lay = ParamLayout{k, d.d_hidden, d.d_out, d.w.ln_g != nullptr};
   return 0;
 }

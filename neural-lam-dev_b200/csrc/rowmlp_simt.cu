@@ -254,24 +254,34 @@ __global__ void __launch_bounds__(NT) rowmlp_fwd_kernel(const __grid_constant__ 
     }
   }
   float* out = p.d.out + ((size_t)b * p.d.rows + row0) * dout;
+  float* out2 = p.d.out_res ? p.d.out_res + ((size_t)b * p.d.rows + row0) * dout : nullptr;
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
     const int r = ty * 4 + i;
     if (r >= cnt) continue;
     float* orow = out + (size_t)r * dout;
+    const float* e0 = As + r * C::AS + p.koff[0];  // src_0 row (out_res = src_0 + out)
     if (C::VEC == 4 && p.out_vec_ok) {
 #pragma unroll
       for (int v = 0; v < C::NV; ++v) {
         const int col = (tx + 16 * v) * 4;
-        if (col < dout)
-          *reinterpret_cast<float4*>(orow + col) =
+        if (col < dout) {
+          const float4 o =
               make_float4(acc[i][v * 4], acc[i][v * 4 + 1], acc[i][v * 4 + 2], acc[i][v * 4 + 3]);
+          *reinterpret_cast<float4*>(orow + col) = o;
+          if (out2)
+            *reinterpret_cast<float4*>(out2 + (size_t)r * dout + col) =
+                make_float4(o.x + e0[col], o.y + e0[col + 1], o.z + e0[col + 2], o.w + e0[col + 3]);
+        }
       }
     } else {
 #pragma unroll
       for (int c = 0; c < C::CPT; ++c) {
         const int col = col_of<DP>(tx, c);
-        if (col < dout) orow[col] = acc[i][c];
+        if (col < dout) {
+          orow[col] = acc[i][c];
+          if (out2) out2[(size_t)r * dout + col] = acc[i][c] + e0[col];
+        }
       }
     }
   }
@@ -588,31 +598,37 @@ struct RParams {
   const int32_t* tile_chunk;
   float* out;
 };
-__global__ void reduce_params_kernel(const __grid_constant__ RParams p) {
-  // 8 consecutive lanes share one output element: each sums a fixed subset of the
-  // partials, then the 8 sub-sums are combined in a fixed shuffle order.
-  const int j = (blockIdx.x * blockDim.x + threadIdx.x) >> 3;
-  const int sub = threadIdx.x & 7;
+__global__ void __launch_bounds__(256) reduce_params_kernel(const __grid_constant__ RParams p) {
+  // Block = 32 consecutive output elements (coalesced 128-byte rows of the partial
+  // matrix) x 8 warps; warp w sums partials w, w+8, ...; the 8 sub-sums are then
+  // combined in a fixed order (deterministic).
+  __shared__ float red[8][33];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int j = blockIdx.x * 32 + lane;
   const int chunk = blockIdx.y;
   float s = 0.f;
   if (j < p.p_total) {
     if (j < p.p_main) {
-      for (int sp = sub; sp < p.splits; sp += 8)
+      for (int sp = w; sp < p.splits; sp += 8)
         s += p.partial[((size_t)sp * p.n_chunks + chunk) * p.p_total + j];
     } else {
       const int q = j - p.p_main;  // [2][d_out]
       const int n = p.batch * p.n_tiles;
-      for (int i = sub; i < n; i += 8) {
+      for (int i = w; i < n; i += 8) {
         const int t = i % p.n_tiles;
         if (p.tile_chunk && p.tile_chunk[t] != chunk) continue;
         s += p.ln_partial[(size_t)i * 2 * p.d_out + q];
       }
     }
   }
-  s += __shfl_xor_sync(0xffffffffu, s, 1);
-  s += __shfl_xor_sync(0xffffffffu, s, 2);
-  s += __shfl_xor_sync(0xffffffffu, s, 4);
-  if (j < p.p_total && sub == 0) p.out[(size_t)chunk * p.p_total + j] = s;
+  red[w][lane] = s;
+  __syncthreads();
+  if (w == 0 && j < p.p_total) {
+    float t = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) t += red[i][lane];
+    p.out[(size_t)chunk * p.p_total + j] = t;
+  }
 }
 
 int launch_reduce_params(const float* partial, int splits, int n_chunks, int p_total, float* out,
@@ -621,7 +637,7 @@ int launch_reduce_params(const float* partial, int splits, int n_chunks, int p_t
   rp.partial = partial, rp.splits = splits, rp.n_chunks = n_chunks;
   rp.p_total = p_total, rp.p_main = p_total;
   rp.out = out;
-  dim3 rgrid((p_total * 8 + 255) / 256, n_chunks);
+  dim3 rgrid((p_total + 31) / 32, n_chunks);
   reduce_params_kernel<<<rgrid, 256, 0, st>>>(rp);
   NLAM_CUDA(cudaGetLastError());
   count_launch();
@@ -715,7 +731,7 @@ static int launch_bwd(const KParams& p, const WParams& wp, const RParams& rp, cu
   wgrad_kernel<DP><<<wgrid, NT, 0, st>>>(wp);
   NLAM_CUDA(cudaGetLastError());
   count_launch();
-  dim3 rgrid((rp.p_total * 8 + 255) / 256, rp.n_chunks);
+  dim3 rgrid((rp.p_total + 31) / 32, rp.n_chunks);
   reduce_params_kernel<<<rgrid, 256, 0, st>>>(rp);
   NLAM_CUDA(cudaGetLastError());
   count_launch();

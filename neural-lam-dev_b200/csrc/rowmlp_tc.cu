@@ -213,34 +213,42 @@ rowmlp_tc_fwd_kernel(const __grid_constant__ KParams p, const __grid_constant__ 
     tc_fence_before();
     __syncthreads();
 
-    // ---------------- coalesced store (+ fp32 residual)
+    // ---------------- coalesced store (+ fp32 residual / second output src_0 + out)
     {
       float* out = p.d.out + ((size_t)b * p.d.rows + row0) * dout;
+      float* out2 = p.d.out_res ? p.d.out_res + ((size_t)b * p.d.rows + row0) * dout : nullptr;
       const nlam_src& s0 = p.d.src[0];
       const bool res = p.d.residual_src == 0;
-      if (p.out_vec_ok && (!res || p.vec_ok[0])) {
+      const bool need0 = res || out2;
+      if (p.out_vec_ok && (!need0 || p.vec_ok[0])) {
         const int w4 = dout >> 2;
         for (int u = tid; u < cnt * w4; u += NT) {
           const int row = u / w4, c4 = u % w4;
           float4 v = *reinterpret_cast<const float4*>(stg + (size_t)row * g.stg_ld + c4 * 4);
-          if (res) {
+          float4 e = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (need0) {
             const int ridx = s0.idx ? __ldg(s0.idx + row0 + row) : row0 + row;
-            const float4 e = __ldg(reinterpret_cast<const float4*>(
-                                       s0.ptr + (long long)b * s0.batch_stride +
-                                       (long long)ridx * s0.ld) + c4);
-            v.x += e.x, v.y += e.y, v.z += e.z, v.w += e.w;
+            e = __ldg(reinterpret_cast<const float4*>(s0.ptr + (long long)b * s0.batch_stride +
+                                                      (long long)ridx * s0.ld) + c4);
           }
+          if (res) v.x += e.x, v.y += e.y, v.z += e.z, v.w += e.w;
           *reinterpret_cast<float4*>(out + (size_t)row * dout + c4 * 4) = v;
+          if (out2)
+            *reinterpret_cast<float4*>(out2 + (size_t)row * dout + c4 * 4) =
+                make_float4(v.x + e.x, v.y + e.y, v.z + e.z, v.w + e.w);
         }
       } else {
         for (int u = tid; u < cnt * dout; u += NT) {
           const int row = u / dout, c = u % dout;
           float v = stg[(size_t)row * g.stg_ld + c];
-          if (res) {
+          float e = 0.f;
+          if (need0) {
             const int ridx = s0.idx ? __ldg(s0.idx + row0 + row) : row0 + row;
-            v += __ldg(s0.ptr + (long long)b * s0.batch_stride + (long long)ridx * s0.ld + c);
+            e = __ldg(s0.ptr + (long long)b * s0.batch_stride + (long long)ridx * s0.ld + c);
           }
+          if (res) v += e;
           out[(size_t)row * dout + c] = v;
+          if (out2) out2[(size_t)row * dout + c] = v + e;
         }
       }
     }

@@ -47,6 +47,7 @@ class RowMlp(ctypes.Structure):
         ("n_tiles", ctypes.c_int32),
         ("residual_src", ctypes.c_int32),
         ("out", c_float_p),
+        ("out_res", c_float_p),
         ("precision", ctypes.c_int32),
     ]
 

@@ -54,8 +54,9 @@ class ARModel(nn.Module):
 
     def configure_optimizers(self):
         """AdamW(lr, betas=(0.9, 0.95)), default weight decay (ar_model.py:191-195)."""
+        on_gpu = next(self.parameters()).is_cuda
         return torch.optim.AdamW(self.parameters(), lr=self.args.lr, betas=(0.9, 0.95),
-                                 fused=next(self.parameters()).is_cuda)
+                                 fused=on_gpu, capturable=on_gpu)
 
     @property
     def interior_mask_bool(self):

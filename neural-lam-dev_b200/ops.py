@@ -228,22 +228,28 @@ def _fill_desc(desc, srcs, W, batch, rows, residual, tiles, out, precision):
     desc.precision = _PREC[precision]
 
 
-def rowmlp_fwd_raw(srcs, W, batch, rows, residual, tiles, precision):
-    """srcs: list of (3-D tensor, int32 row index or None)."""
+def rowmlp_fwd_raw(srcs, W, batch, rows, residual, tiles, precision, want_res=False):
+    """srcs: list of (3-D tensor, int32 row index or None).  want_res: also
+    return src_0 + out (second output of the same launch)."""
     lib = L.load()
     dev = srcs[0][0].device
     out = torch.empty((batch, rows, W.d_out), device=dev, dtype=torch.float32)
     desc = L.RowMlp()
     _fill_desc(desc, srcs, W, batch, rows, residual, tiles, out, precision)
+    out_res = None
+    if want_res:
+        out_res = torch.empty_like(out)
+        desc.out_res = out_res.data_ptr()
     end = None
     if _timer["t"] is not None:
-        tag, nbytes, flops = _rowmlp_cost(f"rowmlp_fwd_{precision}", srcs, W, batch, rows, W.d_out)
+        tag, nbytes, flops = _rowmlp_cost(f"rowmlp_fwd_{precision}", srcs, W, batch, rows,
+                                          W.d_out * (2 if want_res else 1))
         if _timer["t"].want(tag):
             end = _timer["t"].start(tag, nbytes, flops)
     L.check(lib.nlam_rowmlp_fwd(ctypes.byref(desc), _stream()), "nlam_rowmlp_fwd")
     if end is not None:
         end.record()
-    return out
+    return (out, out_res) if want_res else out
 
 
 def rowmlp_bwd_raw(srcs, W, batch, rows, residual, tiles, precision, g0, need_src,
@@ -413,16 +419,19 @@ class _InteractionNetFn(torch.autograd.Function):
         # message + edge residual
         edge_out = rowmlp_fwd_raw(
             [(edge3, None), (send3, plan.send32), (rec3, plan.recv32)], We, B, M,
-            False, plan.edge_tiles, prec)
+            False, plan.edge_tiles, prec, want_res=meta["update_edges"])
+        new_edge = None
+        if meta["update_edges"]:
+            edge_out, new_edge = edge_out  # messages m_k and E' = E + m (:112)
         # edge_out holds the messages m_k; aggregate (sum / mean over receivers)
         aggr = segsum_raw(edge_out, plan.rowptr, plan.perm, n_rec,
                           scale=plan.inv_deg if meta["aggr"] == "mean" else None)
         rec_out = rowmlp_fwd_raw([(rec3, None), (aggr, None)], Wa, B, n_rec, True,
                                  plan.aggr_tiles, prec)
         ctx.meta = meta
+        ctx.set_materialize_grads(False)  # unused outputs arrive as None, not zeros
         ctx.save_for_backward(*ew, *aw, send3, rec3, edge3, aggr)
         if meta["update_edges"]:
-            new_edge = edge3 + edge_out  # E' = E + m  (:112)
             return rec_out, new_edge
         return rec_out
 
@@ -450,13 +459,12 @@ class _InteractionNetFn(torch.autograd.Function):
         # edge stage: dm_k = dA[r(k)] (/deg) ; E' = E + m handled after
         need_send, need_rec, need_edge = ctx.needs_input_grad[13:16]
         (dzE, dzS, dzR), dPe = rowmlp_bwd_raw(
-            [(edge3, None), (send3, plan.send32), (rec3, plan.recv32)], We, B, M, False,
+            [(edge3, None), (send3, plan.send32), (rec3, plan.recv32)], We, B, M,
+            d_edge_out is not None,  # E' = E + m: the kernel adds dE' to the edge gradient
             plan.edge_tiles, prec, d_edge_out, [need_edge, need_send, need_rec],
             g1=dA, g1_idx=plan.recv32,
             g1_scale=plan.inv_deg if meta["aggr"] == "mean" else None)
-        d_edge = None
-        if need_edge:
-            d_edge = dzE if d_edge_out is None else dzE + d_edge_out
+        d_edge = dzE if need_edge else None
         d_send = None
         if need_send:
             n_send = send3.shape[1]

@@ -113,8 +113,16 @@ class DataParallelTrainer:
     ranks, AdamW.  `step_from_host(batch)`: same, starting from pinned host
     tensors and ending with the loss on the host (the end-to-end call)."""
 
-    def __init__(self, model, rank=0, world_size=1, overlap=True):
+    def __init__(self, model, rank=0, world_size=1, overlap=True, use_cuda_graph=False):
+        """use_cuda_graph: capture forward + backward + gradient mean + AdamW of one
+        step into a CUDA graph at the first call and replay it afterwards (static
+        shapes; removes the per-launch host cost of the ~470 kernels of a step --
+        GraphLAM -- or of HiLAM's 64 dependent layers)."""
         self.model = model
+        self.use_cuda_graph = use_cuda_graph
+        self._graph = None
+        self._static_batch = None
+        self._static_loss = None
         self.rank, self.world = rank, world_size
         self.device = next(model.parameters()).device
         if world_size > 1:
@@ -125,7 +133,7 @@ class DataParallelTrainer:
                                        EARLY_PREFIXES, overlap)
         self.optimizer = model.configure_optimizers()
 
-    def step(self, batch):
+    def _eager_step(self, batch):
         self.buckets.zero()
         loss = self.model.training_step(batch)
         loss.backward()
@@ -133,7 +141,38 @@ class DataParallelTrainer:
         self.optimizer.step()
         return loss.detach()
 
+    def _capture(self, batch):
+        self._static_batch = tuple(torch.empty_like(t) for t in batch)
+        for dst, src in zip(self._static_batch, batch):
+            dst.copy_(src)
+        # warm-up on a side stream (allocator pools, CSR plans, kernel attributes)
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(2):
+                self._eager_step(self._static_batch)
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        self._graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self._graph):
+            self._static_loss = self._eager_step(self._static_batch)
+
+    def step(self, batch):
+        if not self.use_cuda_graph:
+            return self._eager_step(batch)
+        if self._graph is None:
+            self._capture(batch)
+        for dst, src in zip(self._static_batch, batch):
+            dst.copy_(src, non_blocking=True)
+        self._graph.replay()
+        return self._static_loss
+
     def step_from_host(self, host_batch):
+        if self.use_cuda_graph and self._graph is not None:
+            for dst, src in zip(self._static_batch, host_batch):
+                dst.copy_(src, non_blocking=True)  # pinned host -> static device batch
+            self._graph.replay()
+            return float(self._static_loss.item())
         batch = tuple(t.to(self.device, non_blocking=True) for t in host_batch)
         loss = self.step(batch)
         return float(loss.item())  # device -> host read of the step's result
