@@ -99,6 +99,14 @@ rowmlp_tc_fwd_kernel(const __grid_constant__ KParams p, const __grid_constant__ 
       gather_rows_fast<(F ? FN : 64)>(p, b, row0, cnt, 0, p.d.n_src, sA);
     else
       gather_rows(p, b, row0, cnt, 0, g.k1, sA);
+    {  // L2 prefetch of the next tile's input rows
+      const int tn = t + gridDim.x;
+      if (tn < g.total_tiles) {
+        int r0n, cn, chn;
+        tile_range<TM>(p.d, tn % g.tiles_per_batch, r0n, cn, chn);
+        prefetch_sources(p, tn / g.tiles_per_batch, r0n, cn);
+      }
+    }
     fence_async_smem();
     __syncthreads();
 

@@ -95,7 +95,13 @@ __device__ __forceinline__ uint64_t make_desc_mn_sw128(uint32_t smem_addr, uint3
 __device__ __forceinline__ void copy_tile_out(const uint8_t* s, uint8_t* g, int bytes) {
   const uint4* src = reinterpret_cast<const uint4*>(s);
   uint4* dst = reinterpret_cast<uint4*>(g);
-  for (int i = threadIdx.x; i < bytes / 16; i += NT) dst[i] = src[i];
+  for (int i = threadIdx.x; i < bytes / 16; i += 4 * NT) {  // 16 KB blocks
+    uint4 v[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) v[j] = src[i + j * NT];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) dst[i + j * NT] = v[j];
+  }
 }
 __device__ __forceinline__ void copy_tile_in(const uint8_t* g, uint8_t* s, int bytes) {
   // 16 KB blocks: 4 independent 128-bit loads per thread in flight
@@ -301,6 +307,20 @@ rowmlp_tc_dgrad_kernel(const __grid_constant__ KParams p, const __grid_constant_
                                        va[j].z + gs[j] * vb[j].z, va[j].w + gs[j] * vb[j].w);
           *reinterpret_cast<float4*>(stg + stg_idx(rowv[j], c4v[j], n2)) = v;
         }
+      }
+    }
+
+    {  // L2 prefetch of the next tile's input and dOut rows
+      const int tn = t + gridDim.x;
+      if (tn < g.total_tiles) {
+        int r0n, cn, chn;
+        const int bn = tn / g.tiles_per_batch;
+        tile_range<TM>(p.d, tn % g.tiles_per_batch, r0n, cn, chn);
+        prefetch_sources(p, bn, r0n, cn);
+        if (p.g0)
+          prefetch_tile_rows(p.g0 + (size_t)bn * p.d.rows * dout, nullptr, dout, dout, r0n, cn);
+        if (p.g1)
+          prefetch_tile_rows(p.g1 + (size_t)bn * p.g1_batch_stride, p.g1_idx, dout, dout, r0n, cn);
       }
     }
 
@@ -524,6 +544,22 @@ rowmlp_tc_dgrad_kernel(const __grid_constant__ KParams p, const __grid_constant_
       if (tid == 0) issue_dz(0);
       for (int kb = 0; kb < g.kb1; ++kb) {
         if (tid == 0 && kb + 1 < g.kb1) issue_dz(kb + 1);
+        // fast path: block kb = 64 columns [col0, col0+64) of source fs
+        constexpr int FNN = F ? FN : 64;
+        const int fs = (kb * 64) / FNN, col0 = (kb * 64) % FNN;
+        float* fdst = F ? p.d_src[fs] : nullptr;
+        const bool fres = F && fdst && (fs == p.d.residual_src) && p.g0;
+        float4 e[8];
+        if (fres) {  // residual rows requested early: they arrive while the MMA runs
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int row = (tid >> 4) + 16 * i;
+            e[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (row < cnt)
+              e[i] = __ldg(reinterpret_cast<const float4*>(p.g0 + (grow0 + row) * FNN + col0) +
+                           (tid & 15));
+          }
+        }
         mbar_wait(&bars[1 + (kb & 1)], (ph_z >> (kb & 1)) & 1u);
         ph_z ^= 1u << (kb & 1);
         tc_fence_after();
@@ -539,30 +575,46 @@ rowmlp_tc_dgrad_kernel(const __grid_constant__ KParams p, const __grid_constant_
         }
         tc_fence_before();
         __syncthreads();
-        // coalesced per-source row stores
-        for (int u = tid; u < cnt * 16; u += NT) {
-          const int row = u >> 4, c4 = u & 15, kg = kb * 64 + c4 * 4;
-          if (kg >= p.k_total) continue;
-          int s = 0;
-          while (s + 1 < p.d.n_src && kg >= p.koff[s + 1]) ++s;
-          float* dst = p.d_src[s];
-          if (!dst) continue;
-          const int w = p.d.src[s].width, col = kg - p.koff[s];
-          const float4 v = *reinterpret_cast<const float4*>(stg + stg_idx(row, c4, 64));
-          float tmp[4] = {v.x, v.y, v.z, v.w};
-          const bool res = (s == p.d.residual_src) && p.g0;
-          float* o = dst + (grow0 + row) * w + col;
-          if ((w & 3) == 0) {
-            if (res) {
-              const float4 e = __ldg(reinterpret_cast<const float4*>(p.g0 + (grow0 + row) * dout + col));
-              tmp[0] += e.x, tmp[1] += e.y, tmp[2] += e.z, tmp[3] += e.w;
-            }
-            *reinterpret_cast<float4*>(o) = make_float4(tmp[0], tmp[1], tmp[2], tmp[3]);
-          } else {
+        if (F) {
+          if (fdst) {
+            float* o = fdst + grow0 * FNN + col0 + (tid & 15) * 4;
 #pragma unroll
-            for (int j = 0; j < 4; ++j)
-              if (col + j < w)
-                o[j] = tmp[j] + (res ? __ldg(p.g0 + (grow0 + row) * dout + col + j) : 0.f);
+            for (int i = 0; i < 8; ++i) {
+              const int row = (tid >> 4) + 16 * i;
+              if (row < cnt) {
+                float4 v = *reinterpret_cast<const float4*>(stg + stg_idx(row, tid & 15, 64));
+                if (fres) v.x += e[i].x, v.y += e[i].y, v.z += e[i].z, v.w += e[i].w;
+                *reinterpret_cast<float4*>(o + (size_t)row * FNN) = v;
+              }
+            }
+          }
+        } else {
+          // generic: coalesced per-source row stores
+          for (int u = tid; u < cnt * 16; u += NT) {
+            const int row = u >> 4, c4 = u & 15, kg = kb * 64 + c4 * 4;
+            if (kg >= p.k_total) continue;
+            int s = 0;
+            while (s + 1 < p.d.n_src && kg >= p.koff[s + 1]) ++s;
+            float* dst = p.d_src[s];
+            if (!dst) continue;
+            const int w = p.d.src[s].width, col = kg - p.koff[s];
+            const float4 v = *reinterpret_cast<const float4*>(stg + stg_idx(row, c4, 64));
+            float tmp[4] = {v.x, v.y, v.z, v.w};
+            const bool res = (s == p.d.residual_src) && p.g0;
+            float* o = dst + (grow0 + row) * w + col;
+            if ((w & 3) == 0) {
+              if (res) {
+                const float4 ee =
+                    __ldg(reinterpret_cast<const float4*>(p.g0 + (grow0 + row) * dout + col));
+                tmp[0] += ee.x, tmp[1] += ee.y, tmp[2] += ee.z, tmp[3] += ee.w;
+              }
+              *reinterpret_cast<float4*>(o) = make_float4(tmp[0], tmp[1], tmp[2], tmp[3]);
+            } else {
+#pragma unroll
+              for (int j = 0; j < 4; ++j)
+                if (col + j < w)
+                  o[j] = tmp[j] + (res ? __ldg(p.g0 + (grow0 + row) * dout + col + j) : 0.f);
+            }
           }
         }
         __syncthreads();
@@ -669,6 +721,21 @@ rowmlp_tc_wgrad_kernel(const __grid_constant__ KParams p, const __grid_constant_
     copy_tile_in(g.a_img + (size_t)t * kb2 * a_blk, sAi, kb2 * a_blk);
     copy_tile_in(g.dy_img + (size_t)t * kbo * a_blk, sDY, kbo * a_blk);
     copy_tile_in(g.dh_img + (size_t)t * kb2 * a_blk, sDH, kb2 * a_blk);
+    {  // L2 prefetch of the next tile's rows and bf16 tile images
+      const int tn = t + gridDim.x;
+      if (tn < g.total_tiles) {
+        int r0n, cn, chn;
+        tile_range<TM>(p.d, tn % g.tiles_per_batch, r0n, cn, chn);
+        prefetch_sources(p, tn / g.tiles_per_batch, r0n, cn);
+        const int li = (int)(kb2 * a_blk) >> 7, lo = (int)(kbo * a_blk) >> 7;
+        for (int u = tid; u < li; u += NT) {
+          prefetch_l2(g.a_img + (size_t)tn * kb2 * a_blk + (size_t)u * 128);
+          prefetch_l2(g.dh_img + (size_t)tn * kb2 * a_blk + (size_t)u * 128);
+        }
+        for (int u = tid; u < lo; u += NT)
+          prefetch_l2(g.dy_img + (size_t)tn * kbo * a_blk + (size_t)u * 128);
+      }
+    }
     fence_async_smem();
     __syncthreads();
     if (tid == 0) {
