@@ -35,7 +35,7 @@ struct Geo {
   int tiles_per_batch;
 };
 
-template <int FN>
+template <int FN, bool FG>
 __global__ void __launch_bounds__(NT, 2)
 rowmlp_tc_fwd_kernel(const __grid_constant__ KParams p, const __grid_constant__ Geo g) {
   constexpr bool F = FN > 0;  // square fast path: sizes are compile-time constants
@@ -95,7 +95,7 @@ rowmlp_tc_fwd_kernel(const __grid_constant__ KParams p, const __grid_constant__ 
     }
 
     // ---------------- gather: fp32 rows -> bf16 A operand
-    if (F)
+    if (F && FG)
       gather_rows_fast<(F ? FN : 64)>(p, b, row0, cnt, 0, p.d.n_src, sA);
     else
       gather_rows(p, b, row0, cnt, 0, g.k1, sA);
@@ -333,10 +333,13 @@ int tc_rowmlp_fwd(const nlam_rowmlp& d, cudaStream_t st) {
     kern<<<grid, tc::NT, g.smem_bytes, st>>>(p, g);
     return 0;
   };
-  static int ms0 = 0, ms64 = 0, ms128 = 0;
-  int rc = fn == 64    ? launch(tc::rowmlp_tc_fwd_kernel<64>, ms64)
-           : fn == 128 ? launch(tc::rowmlp_tc_fwd_kernel<128>, ms128)
-                       : launch(tc::rowmlp_tc_fwd_kernel<0>, ms0);
+  const bool fg = tc::fast_gather(p);
+  static int ms[5] = {0, 0, 0, 0, 0};
+  int rc = fn == 64    ? (fg ? launch(tc::rowmlp_tc_fwd_kernel<64, true>, ms[1])
+                             : launch(tc::rowmlp_tc_fwd_kernel<64, false>, ms[2]))
+           : fn == 128 ? (fg ? launch(tc::rowmlp_tc_fwd_kernel<128, true>, ms[3])
+                             : launch(tc::rowmlp_tc_fwd_kernel<128, false>, ms[4]))
+                       : launch(tc::rowmlp_tc_fwd_kernel<0, false>, ms[0]);
   if (rc) return rc;
   NLAM_CUDA(cudaGetLastError());
   count_launch();

@@ -172,13 +172,19 @@ __device__ __forceinline__ void prefetch_sources(const KParams& p, int b, int ro
   }
 }
 
-// square fast path: d_hidden == d_out == FN, every source FN wide and vectorisable
+// square fast path: d_hidden == d_out == FN (compile-time epilogues) ...
 inline int fast_n(const KParams& p) {
   const nlam_rowmlp& d = p.d;
   if (d.d_hidden != d.d_out || (d.d_hidden != 64 && d.d_hidden != 128)) return 0;
-  for (int s = 0; s < d.n_src; ++s)
-    if (d.src[s].width != d.d_hidden || !p.vec_ok[s]) return 0;
   return d.d_hidden;
+}
+// ... and, additionally, every source exactly FN wide and vectorisable (fast gather)
+inline bool fast_gather(const KParams& p) {
+  const nlam_rowmlp& d = p.d;
+  if (!fast_n(p)) return false;
+  for (int s = 0; s < d.n_src; ++s)
+    if (d.src[s].width != d.d_hidden || !p.vec_ok[s]) return false;
+  return true;
 }
 
 // b1[n1] | b2[n2] | gamma[n2] | beta[n2], zero / identity padded

@@ -118,7 +118,7 @@ __device__ __forceinline__ void copy_tile_in(const uint8_t* g, uint8_t* s, int b
 
 constexpr int MAXCH = 4;  // 16-column chunks per thread (n <= 128, two column halves)
 
-template <int FN>
+template <int FN, bool FG>
 __global__ void __launch_bounds__(NT, 2)
 rowmlp_tc_dgrad_kernel(const __grid_constant__ KParams p, const __grid_constant__ BGeo g) {
   constexpr bool F = FN > 0;  // square fast path: sizes are compile-time constants
@@ -228,7 +228,7 @@ rowmlp_tc_dgrad_kernel(const __grid_constant__ KParams p, const __grid_constant_
     for (int kb0 = 0; kb0 < g.kb1; kb0 += g.rb) {
       const int kbe = min(g.kb1, kb0 + g.rb);
       const int k_begin = kb0 * 64, k_end = min(g.k1, kbe * 64);
-      if (F)
+      if (F && FG)
         gather_rows_fast<(F ? FN : 64)>(p, b, row0, cnt, k_begin / (F ? FN : 64),
                                         k_end / (F ? FN : 64), sA);
       else
@@ -547,8 +547,8 @@ rowmlp_tc_dgrad_kernel(const __grid_constant__ KParams p, const __grid_constant_
         // fast path: block kb = 64 columns [col0, col0+64) of source fs
         constexpr int FNN = F ? FN : 64;
         const int fs = (kb * 64) / FNN, col0 = (kb * 64) % FNN;
-        float* fdst = F ? p.d_src[fs] : nullptr;
-        const bool fres = F && fdst && (fs == p.d.residual_src) && p.g0;
+        float* fdst = (F && FG) ? p.d_src[fs] : nullptr;
+        const bool fres = F && FG && fdst && (fs == p.d.residual_src) && p.g0;
         float4 e[8];
         if (fres) {  // residual rows requested early: they arrive while the MMA runs
 #pragma unroll
@@ -575,7 +575,7 @@ rowmlp_tc_dgrad_kernel(const __grid_constant__ KParams p, const __grid_constant_
         }
         tc_fence_before();
         __syncthreads();
-        if (F) {
+        if (F && FG) {
           if (fdst) {
             float* o = fdst + grow0 * FNN + col0 + (tid & 15) * 4;
 #pragma unroll
@@ -631,7 +631,7 @@ rowmlp_tc_dgrad_kernel(const __grid_constant__ KParams p, const __grid_constant_
 }
 
 // -------------------------------------------------------------------- wgrad
-template <int FN>
+template <int FN, bool FG>
 __global__ void __launch_bounds__(NT, 2)
 rowmlp_tc_wgrad_kernel(const __grid_constant__ KParams p, const __grid_constant__ BGeo g) {
   constexpr bool F = FN > 0;
@@ -714,7 +714,7 @@ rowmlp_tc_wgrad_kernel(const __grid_constant__ KParams p, const __grid_constant_
       cur_chunk = chunk;
       first = true;
     }
-    if (F)
+    if (F && FG)
       gather_rows_fast<(F ? FN : 64)>(p, b, row0, cnt, 0, p.d.n_src, sZ);
     else
       gather_rows(p, b, row0, cnt, 0, g.k1, sZ);
@@ -779,7 +779,7 @@ static int make_bgeo(const KParams& p, BGeo& g) {
   g.k2 = (d.d_hidden + 15) / 16 * 16;
   g.ko = (d.d_out + 15) / 16 * 16;
   g.kb1 = (g.k1 + 63) / 64, g.kb2 = (g.n1 + 63) / 64, g.kbo = (g.n2 + 63) / 64;
-  g.rb = (fast_n(p) == 128) ? 2 : 3;  // fast gather works on whole sources
+  g.rb = (fast_n(p) == 128 && fast_gather(p)) ? 2 : 3;  // fast gather works on whole sources
   g.cY = g.n1, g.cZ = g.n1 + g.nmax;
   g.tmem_cols = pow2_cols(g.cZ + 128);
   const uint32_t blk = TM * 128u;
@@ -897,18 +897,24 @@ int tc_rowmlp_bwd(const nlam_rowmlp_bwd& bd, cudaStream_t st) {
     count_launch();
     return 0;
   };
-  static int md[3] = {0, 0, 0}, mw[3] = {0, 0, 0};
+  const bool fg = tc::fast_gather(p);
+  static int md[5] = {0, 0, 0, 0, 0}, mw[5] = {0, 0, 0, 0, 0};
   int rc;
-  if (fn == 64) {
-    rc = launch(tc::rowmlp_tc_dgrad_kernel<64>, md[1], gd, g.smem_bytes);
-    if (!rc) rc = launch(tc::rowmlp_tc_wgrad_kernel<64>, mw[1], gw, g.w_smem_bytes);
+#define NLAM_BWD_PAIR(FNV, FGV, I)                                                          \
+  rc = launch(tc::rowmlp_tc_dgrad_kernel<FNV, FGV>, md[I], gd, g.smem_bytes);                \
+  if (!rc) rc = launch(tc::rowmlp_tc_wgrad_kernel<FNV, FGV>, mw[I], gw, g.w_smem_bytes);
+  if (fn == 64 && fg) {
+    NLAM_BWD_PAIR(64, true, 1)
+  } else if (fn == 64) {
+    NLAM_BWD_PAIR(64, false, 2)
+  } else if (fn == 128 && fg) {
+    NLAM_BWD_PAIR(128, true, 3)
   } else if (fn == 128) {
-    rc = launch(tc::rowmlp_tc_dgrad_kernel<128>, md[2], gd, g.smem_bytes);
-    if (!rc) rc = launch(tc::rowmlp_tc_wgrad_kernel<128>, mw[2], gw, g.w_smem_bytes);
+    NLAM_BWD_PAIR(128, false, 4)
   } else {
-    rc = launch(tc::rowmlp_tc_dgrad_kernel<0>, md[0], gd, g.smem_bytes);
-    if (!rc) rc = launch(tc::rowmlp_tc_wgrad_kernel<0>, mw[0], gw, g.w_smem_bytes);
+    NLAM_BWD_PAIR(0, false, 0)
   }
+#undef NLAM_BWD_PAIR
   if (rc) return rc;
   return launch_reduce_params(g.partial, ws.slots, d.n_chunks, g.p_total, bd.d_params, st);
 }
