@@ -167,6 +167,46 @@ class DataParallelTrainer:
         self._graph.replay()
         return self._static_loss
 
+    def fit_from_host(self, host_batches):
+        """Train on a sequence of pinned host batches (what a DataLoader with
+        pin_memory=True yields): the host->device copy of batch i+1 runs on a copy
+        stream while step i computes; each step's loss is read back to pinned host
+        memory asynchronously and returned as a list of floats at the end.
+        Every copy happens inside this call (weather_dataset.py:603-696 hands
+        batches to Lightning the same way)."""
+        host_batches = list(host_batches)
+        if not host_batches:
+            return []
+        dev = self.device
+        copy_stream = torch.cuda.Stream(device=dev)
+        compute = torch.cuda.current_stream()
+        staging = [tuple(torch.empty_like(t, device=dev) for t in host_batches[0])
+                   for _ in range(2)]
+        ready = [torch.cuda.Event() for _ in range(2)]   # H2D into staging[k] finished
+        consumed = [torch.cuda.Event() for _ in range(2)]  # step reading staging[k] finished
+        losses = torch.empty(len(host_batches), dtype=torch.float32).pin_memory()
+
+        def upload(i):
+            k = i % 2
+            with torch.cuda.stream(copy_stream):
+                if i >= 2:
+                    copy_stream.wait_event(consumed[k])
+                for dst, src in zip(staging[k], host_batches[i]):
+                    dst.copy_(src, non_blocking=True)
+                ready[k].record(copy_stream)
+
+        upload(0)
+        for i in range(len(host_batches)):
+            if i + 1 < len(host_batches):
+                upload(i + 1)
+            k = i % 2
+            compute.wait_event(ready[k])
+            loss = self.step(staging[k])  # graph mode: D2D into the static batch + replay
+            consumed[k].record(compute)
+            losses[i:i + 1].copy_(loss.reshape(1), non_blocking=True)
+        compute.synchronize()
+        return losses.tolist()
+
     def step_from_host(self, host_batch):
         if self.use_cuda_graph and self._graph is not None:
             for dst, src in zip(self._static_batch, host_batch):
