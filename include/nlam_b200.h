@@ -58,6 +58,20 @@ typedef struct nlam_mlp_weights {
   const float* ln_b;
 } nlam_mlp_weights;
 
+/* Optional in-kernel deterministic segment reduction over the rows of a tile
+ * (receiver-aligned tiles: every segment lies inside one tile).  Forward:
+ * out[b, i, :] = scale[i] * sum_{r in [seg_ptr[i], seg_ptr[i+1])} y[b, r, :]
+ * = PyG scatter sum/mean (interaction_net.py:124-131) fused into the edge
+ * kernel, rows summed in tile-table order (= ascending edge id).  Needs the
+ * bf16 path with d_hidden == d_out == source widths in {64, 128}. */
+typedef struct nlam_agg {
+  const int32_t* seg_ptr;  /* [n_seg+1] */
+  const int32_t* tile_seg; /* [n_tiles+1]: tile t owns segments [tile_seg[t], tile_seg[t+1]) */
+  const float* scale;      /* [n_seg] or NULL */
+  float* out;              /* [batch, n_seg, d_out]; NULL = no reduction */
+  int32_t n_seg;
+} nlam_agg;
+
 typedef struct nlam_rowmlp {
   int32_t n_src;
   nlam_src src[NLAM_MAX_SRC];
@@ -79,6 +93,9 @@ typedef struct nlam_rowmlp {
                                  written to out); InteractionNet needs both the
                                  message m_k and e_k + m_k (interaction_net.py:
                                  112,131).  NULL = not wanted */
+  const int32_t* out_idx;     /* optional: row r of out / out_res is written to row
+                                 out_idx[r] (scatter back to original edge order) */
+  nlam_agg agg;               /* optional fused segment reduction (out may then be NULL) */
   int32_t precision;          /* NLAM_FP32 | NLAM_BF16 */
 } nlam_rowmlp;
 
@@ -96,6 +113,11 @@ typedef struct nlam_rowmlp_bwd {
   const float* g1_scale; /* [n1] or NULL (mean aggregation: 1/max(deg,1)) */
   int64_t g1_batch_stride;
   float* d_src[NLAM_MAX_SRC];
+  const int32_t* g0_idx;                   /* optional: dOut row r = g0[b, g0_idx[r], :] */
+  const int32_t* d_src_idx[NLAM_MAX_SRC];  /* optional: row r of d_src[s] goes to row idx[r] */
+  int32_t reduce_src;        /* -1, or s: the gradient rows of source s are segment-summed
+                                (tables of fwd.agg) into d_src[s] = [batch, n_seg, width] */
+  int32_t reduce_accumulate; /* add to the existing contents of d_src[reduce_src] */
   float* d_params;
   float* workspace;       /* nlam_rowmlp_bwd_workspace() floats */
   size_t workspace_floats;

@@ -21,6 +21,9 @@ struct KParams {
   const float* g1_scale;
   long long g1_batch_stride;
   float* d_src[NLAM_MAX_SRC];
+  const int32_t* g0_idx;
+  const int32_t* d_src_idx[NLAM_MAX_SRC];
+  int reduce_src, reduce_accumulate;
   float* a_save;
   float* dy_save;
   float* dh_save;
@@ -73,6 +76,10 @@ inline int fill_params(const nlam_rowmlp& d, KParams& p) {
   p.out_vec_ok = (d.d_out % 4 == 0) && (((uintptr_t)d.out) % 16 == 0) &&
                  (((uintptr_t)d.out_res) % 16 == 0);
   p.lay = ParamLayout{k, d.d_hidden, d.d_out, d.w.ln_g != nullptr};
+  p.reduce_src = -1;
+  NLAM_CHECK(!d.agg.out || (d.agg.seg_ptr && d.agg.tile_seg && d.tile_ptr && d.n_chunks == 1),
+             "rowmlp: agg needs seg_ptr, tile_seg and a (receiver-aligned) tile table");
+  NLAM_CHECK(d.out || d.out_res || d.agg.out || true, "unreachable");
   return 0;
 }
 

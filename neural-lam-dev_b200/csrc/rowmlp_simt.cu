@@ -666,6 +666,8 @@ int simt_rowmlp_fwd(const nlam_rowmlp& d, cudaStream_t st) {
   if (fill_params(d, p)) return 1;
   if (d.rows == 0) return 0;
   NLAM_CHECK(d.out, "rowmlp: out is NULL");
+  NLAM_CHECK(!d.agg.out && !d.out_idx,
+             "rowmlp: fused aggregation / row scatter exist only on the bf16 tensor-core path");
   const int dp = pick_dp(d);
   switch (dp) {
     case 16: return launch_fwd<16>(p, st);
@@ -750,6 +752,9 @@ int simt_rowmlp_bwd(const nlam_rowmlp_bwd& bd, cudaStream_t st) {
   }
   NLAM_CHECK(bd.g0 || bd.g1, "rowmlp_bwd: no output gradient given");
   NLAM_CHECK(!bd.g1 || bd.g1_idx, "rowmlp_bwd: g1 needs g1_idx");
+  NLAM_CHECK(!bd.g0_idx && bd.reduce_src < 0 && !bd.d_src_idx[0] && !bd.d_src_idx[1] &&
+                 !bd.d_src_idx[2],
+             "rowmlp_bwd: row scatter / fused reduction exist only on the bf16 tensor-core path");
   const BwdWs ws = bwd_ws(d);
   NLAM_CHECK(bd.workspace && bd.workspace_floats >= ws.total,
              "rowmlp_bwd: workspace too small (%zu < %zu floats)", bd.workspace_floats, ws.total);

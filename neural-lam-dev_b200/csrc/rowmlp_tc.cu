@@ -221,10 +221,12 @@ rowmlp_tc_fwd_kernel(const __grid_constant__ KParams p, const __grid_constant__ 
     tc_fence_before();
     __syncthreads();
 
-    // ---------------- coalesced store (+ fp32 residual / second output src_0 + out)
-    {
-      float* out = p.d.out + ((size_t)b * p.d.rows + row0) * dout;
-      float* out2 = p.d.out_res ? p.d.out_res + ((size_t)b * p.d.rows + row0) * dout : nullptr;
+    // ---------------- coalesced store (+ fp32 residual / second output src_0 + out),
+    // optional row scatter (out_idx) and fused segment reduction (agg)
+    if (p.d.out || p.d.out_res) {
+      float* out = p.d.out ? p.d.out + (size_t)b * p.d.rows * dout : nullptr;
+      float* out2 = p.d.out_res ? p.d.out_res + (size_t)b * p.d.rows * dout : nullptr;
+      const int32_t* oidx = p.d.out_idx;
       const nlam_src& s0 = p.d.src[0];
       const bool res = p.d.residual_src == 0;
       const bool need0 = res || out2;
@@ -240,9 +242,10 @@ rowmlp_tc_fwd_kernel(const __grid_constant__ KParams p, const __grid_constant__ 
                                                       (long long)ridx * s0.ld) + c4);
           }
           if (res) v.x += e.x, v.y += e.y, v.z += e.z, v.w += e.w;
-          *reinterpret_cast<float4*>(out + (size_t)row * dout + c4 * 4) = v;
+          const size_t orow = oidx ? (size_t)__ldg(oidx + row0 + row) : (size_t)(row0 + row);
+          if (out) *reinterpret_cast<float4*>(out + orow * dout + c4 * 4) = v;
           if (out2)
-            *reinterpret_cast<float4*>(out2 + (size_t)row * dout + c4 * 4) =
+            *reinterpret_cast<float4*>(out2 + orow * dout + c4 * 4) =
                 make_float4(v.x + e.x, v.y + e.y, v.z + e.z, v.w + e.w);
         }
       } else {
@@ -255,9 +258,29 @@ rowmlp_tc_fwd_kernel(const __grid_constant__ KParams p, const __grid_constant__ 
             e = __ldg(s0.ptr + (long long)b * s0.batch_stride + (long long)ridx * s0.ld + c);
           }
           if (res) v += e;
-          out[(size_t)row * dout + c] = v;
-          if (out2) out2[(size_t)row * dout + c] = v + e;
+          const size_t orow = oidx ? (size_t)__ldg(oidx + row0 + row) : (size_t)(row0 + row);
+          if (out) out[orow * dout + c] = v;
+          if (out2) out2[orow * dout + c] = v + e;
         }
+      }
+    }
+    if (p.d.agg.out) {  // receiver-aligned tile: every segment of this tile is complete
+      const int seg_lo = __ldg(p.d.agg.tile_seg + tile), seg_hi = __ldg(p.d.agg.tile_seg + tile + 1);
+      const int w4 = dout >> 2;
+      float* ao = p.d.agg.out + (size_t)b * p.d.agg.n_seg * dout;
+      for (int u = tid; u < (seg_hi - seg_lo) * w4; u += NT) {
+        const int seg = seg_lo + u / w4, c4 = u % w4;
+        const int r0 = __ldg(p.d.agg.seg_ptr + seg) - row0, r1 = __ldg(p.d.agg.seg_ptr + seg + 1) - row0;
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int rr = r0; rr < r1; ++rr) {
+          const float4 v = *reinterpret_cast<const float4*>(stg + (size_t)rr * g.stg_ld + c4 * 4);
+          acc.x += v.x, acc.y += v.y, acc.z += v.z, acc.w += v.w;
+        }
+        if (p.d.agg.scale) {
+          const float sc = __ldg(p.d.agg.scale + seg);
+          acc.x *= sc, acc.y *= sc, acc.z *= sc, acc.w *= sc;
+        }
+        *reinterpret_cast<float4*>(ao + (size_t)seg * dout + c4 * 4) = acc;
       }
     }
     __syncthreads();  // staging (aliases A) is free again
@@ -316,7 +339,8 @@ int tc_rowmlp_fwd(const nlam_rowmlp& d, cudaStream_t st) {
   KParams p{};
   if (fill_params(d, p)) return 1;
   if (d.rows == 0) return 0;
-  NLAM_CHECK(d.out, "rowmlp: out is NULL");
+  NLAM_CHECK(d.out || d.out_res || d.agg.out, "rowmlp: no output requested");
+  NLAM_CHECK(!d.agg.out || d.d_out % 4 == 0, "rowmlp: agg needs d_out %% 4 == 0");
   tc::Geo g{};
   if (tc::make_geo(p, g)) return 1;
   int per_sm = g.smem_bytes <= 113 * 1024 ? 2 : 1;

@@ -271,7 +271,11 @@ rowmlp_tc_dgrad_kernel(const __grid_constant__ KParams p, const __grid_constant_
             const int row = u / w4, c4 = u % w4, col = c4 * 4;
             rowv[j] = row, c4v[j] = c4, colv[j] = col;
             if (row < cnt && col < dout) {
-              if (p.g0) g0p[j] = p.g0 + (grow0 + row) * dout + col;
+              if (p.g0) {
+                const size_t gr = p.g0_idx ? (size_t)b * p.d.rows + __ldg(p.g0_idx + row0 + row)
+                                           : grow0 + row;
+                g0p[j] = p.g0 + gr * dout + col;
+              }
               if (p.g1) {
                 const int gi = __ldg(p.g1_idx + row0 + row);
                 if (p.g1_scale) gs[j] = __ldg(p.g1_scale + gi);
@@ -318,7 +322,7 @@ rowmlp_tc_dgrad_kernel(const __grid_constant__ KParams p, const __grid_constant_
         tile_range<TM>(p.d, tn % g.tiles_per_batch, r0n, cn, chn);
         prefetch_sources(p, bn, r0n, cn);
         if (p.g0)
-          prefetch_tile_rows(p.g0 + (size_t)bn * p.d.rows * dout, nullptr, dout, dout, r0n, cn);
+          prefetch_tile_rows(p.g0 + (size_t)bn * p.d.rows * dout, p.g0_idx, dout, dout, r0n, cn);
         if (p.g1)
           prefetch_tile_rows(p.g1 + (size_t)bn * p.g1_batch_stride, p.g1_idx, dout, dout, r0n, cn);
       }
@@ -555,9 +559,11 @@ rowmlp_tc_dgrad_kernel(const __grid_constant__ KParams p, const __grid_constant_
           for (int i = 0; i < 8; ++i) {
             const int row = (tid >> 4) + 16 * i;
             e[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (row < cnt)
-              e[i] = __ldg(reinterpret_cast<const float4*>(p.g0 + (grow0 + row) * FNN + col0) +
-                           (tid & 15));
+            if (row < cnt) {
+              const size_t gr = p.g0_idx ? (size_t)b * p.d.rows + __ldg(p.g0_idx + row0 + row)
+                                         : grow0 + row;
+              e[i] = __ldg(reinterpret_cast<const float4*>(p.g0 + gr * FNN + col0) + (tid & 15));
+            }
           }
         }
         mbar_wait(&bars[1 + (kb & 1)], (ph_z >> (kb & 1)) & 1u);
@@ -576,15 +582,38 @@ rowmlp_tc_dgrad_kernel(const __grid_constant__ KParams p, const __grid_constant_
         tc_fence_before();
         __syncthreads();
         if (F && FG) {
-          if (fdst) {
-            float* o = fdst + grow0 * FNN + col0 + (tid & 15) * 4;
+          if (fdst && fs == p.reduce_src) {
+            // receiver-aligned tile: sum the gradient rows of each segment (fixed order)
+            const int seg_lo = __ldg(p.d.agg.tile_seg + tile);
+            const int seg_hi = __ldg(p.d.agg.tile_seg + tile + 1);
+            float* ro = fdst + (size_t)b * p.d.agg.n_seg * FNN + col0 + (tid & 15) * 4;
+            for (int seg = seg_lo + (tid >> 4); seg < seg_hi; seg += 16) {
+              const int r0 = __ldg(p.d.agg.seg_ptr + seg) - row0;
+              const int r1 = __ldg(p.d.agg.seg_ptr + seg + 1) - row0;
+              float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+              for (int rr = r0; rr < r1; ++rr) {
+                const float4 v = *reinterpret_cast<const float4*>(stg + stg_idx(rr, tid & 15, 64));
+                acc.x += v.x, acc.y += v.y, acc.z += v.z, acc.w += v.w;
+              }
+              float4* o4 = reinterpret_cast<float4*>(ro + (size_t)seg * FNN);
+              if (p.reduce_accumulate) {
+                const float4 old = *o4;
+                acc.x += old.x, acc.y += old.y, acc.z += old.z, acc.w += old.w;
+              }
+              *o4 = acc;
+            }
+          } else if (fdst) {
+            const int32_t* didx = p.d_src_idx[fs];
+            float* o = fdst + col0 + (tid & 15) * 4;
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
               const int row = (tid >> 4) + 16 * i;
               if (row < cnt) {
                 float4 v = *reinterpret_cast<const float4*>(stg + stg_idx(row, tid & 15, 64));
                 if (fres) v.x += e[i].x, v.y += e[i].y, v.z += e[i].z, v.w += e[i].w;
-                *reinterpret_cast<float4*>(o + (size_t)row * FNN) = v;
+                const size_t orow = didx ? (size_t)b * p.d.rows + __ldg(didx + row0 + row)
+                                         : grow0 + row;
+                *reinterpret_cast<float4*>(o + orow * FNN) = v;
               }
             }
           }
@@ -873,6 +902,20 @@ int tc_rowmlp_bwd(const nlam_rowmlp_bwd& bd, cudaStream_t st) {
   NLAM_CHECK(((uintptr_t)bd.workspace) % 16 == 0, "rowmlp_bwd: workspace must be 16B aligned");
   p.g0 = bd.g0, p.g1 = bd.g1, p.g1_idx = bd.g1_idx, p.g1_scale = bd.g1_scale;
   p.g1_batch_stride = bd.g1_batch_stride;
+  p.g0_idx = bd.g0_idx;
+  p.reduce_src = bd.reduce_src, p.reduce_accumulate = bd.reduce_accumulate;
+  {
+    bool special = bd.g0_idx || bd.reduce_src >= 0;
+    for (int s = 0; s < NLAM_MAX_SRC; ++s) {
+      p.d_src_idx[s] = bd.d_src_idx[s];
+      special |= bd.d_src_idx[s] != nullptr;
+    }
+    NLAM_CHECK(!special || tc::fast_gather(p),
+               "rowmlp_bwd: row scatter / fused reduction need the square fast path "
+               "(d_hidden == d_out == source widths in {64, 128})");
+    NLAM_CHECK(bd.reduce_src < 0 || (d.agg.seg_ptr && d.agg.tile_seg && d.tile_ptr),
+               "rowmlp_bwd: reduce_src needs fwd.agg.seg_ptr / tile_seg and a tile table");
+  }
   g.need_dz = 0;
   for (int s = 0; s < NLAM_MAX_SRC; ++s) {
     p.d_src[s] = s < d.n_src ? bd.d_src[s] : nullptr;

@@ -17,6 +17,9 @@ from torch import nn
 from . import ops, utils
 
 
+import numpy as np  # noqa: E402
+
+
 class _GraphPlan:
     """Per-device integer side tables derived from `edge_index` (built on the
     GPU by nlam_csr_build; never saved, never trained)."""
@@ -32,10 +35,53 @@ class _GraphPlan:
         # receiver-sorted CSR (aggregation) and sender-sorted CSR (grad of x_j gather)
         self.rowptr, self.perm, self.inv_deg = ops.csr_build(self.recv32, num_rec, True)
         self.t_rowptr, self.t_perm, _ = ops.csr_build(self.send32, self.n_send_idx, False)
+        # receiver-sorted views + receiver-aligned tiles (fused aggregation path)
+        self._build_aligned()
         self.edge_tiles = (ops.TileTable(edge_chunk_sizes, dev)
                            if edge_chunk_sizes is not None else None)
         self.aggr_tiles = (ops.TileTable(aggr_chunk_sizes, dev)
                            if aggr_chunk_sizes is not None else None)
+
+    def _build_aligned(self):
+        dev = self.device
+        rowptr = self.rowptr.cpu().numpy().astype(np.int64)
+        tile_seg = _aligned_tiles(rowptr)
+        self.alignable = tile_seg is not None and self.n_edges > 0
+        if not self.alignable:
+            return
+        perm64 = self.perm.long()
+        self.send_sorted = self.send32[perm64].contiguous()
+        self.recv_sorted = self.recv32[perm64].contiguous()
+        mk = lambda a: torch.tensor(np.asarray(a, dtype=np.int32), device=dev)
+        self.a_tile_seg = mk(tile_seg)
+        self.a_tile_ptr = mk(rowptr[tile_seg])
+        self.a_n_tiles = len(tile_seg) - 1
+        # sender CSR over the receiver-sorted positions (backward of the x_j gather)
+        self.ts_rowptr, self.ts_perm, _ = ops.csr_build(self.send_sorted, self.n_send_idx, False)
+
+    def aligned_tables(self, aggr):
+        return {"tile_ptr": self.a_tile_ptr, "n_tiles": self.a_n_tiles,
+                "tile_seg": self.a_tile_seg, "seg_ptr": self.rowptr, "n_seg": self.num_rec,
+                "scale": self.inv_deg if aggr == "mean" else None, "out_idx": self.perm}
+
+
+def _aligned_tiles(rowptr, max_rows=128):
+    """Greedy packing of consecutive receivers into tiles of <= max_rows edges
+    (and <= max_rows receivers); returns tile_seg or None if some in-degree
+    exceeds a tile."""
+    n_rec = rowptr.shape[0] - 1
+    if n_rec == 0:
+        return np.zeros(1, dtype=np.int64)
+    if int((rowptr[1:] - rowptr[:-1]).max()) > max_rows:
+        return None
+    tile_seg = [0]
+    i = 0
+    while i < n_rec:
+        j = int(np.searchsorted(rowptr, rowptr[i] + max_rows, side="right")) - 1
+        j = max(min(j, i + max_rows, n_rec), i + 1)
+        tile_seg.append(j)
+        i = j
+    return np.asarray(tile_seg, dtype=np.int64)
 
 
 class InteractionNet(nn.Module):

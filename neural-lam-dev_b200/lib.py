@@ -31,6 +31,16 @@ class MlpWeights(ctypes.Structure):
     _fields_ = [(n, c_float_p) for n in ("w1", "b1", "w2", "b2", "ln_g", "ln_b")]
 
 
+class Agg(ctypes.Structure):
+    _fields_ = [
+        ("seg_ptr", c_int_p),
+        ("tile_seg", c_int_p),
+        ("scale", c_float_p),
+        ("out", c_float_p),
+        ("n_seg", ctypes.c_int32),
+    ]
+
+
 class RowMlp(ctypes.Structure):
     _fields_ = [
         ("n_src", ctypes.c_int32),
@@ -48,6 +58,8 @@ class RowMlp(ctypes.Structure):
         ("residual_src", ctypes.c_int32),
         ("out", c_float_p),
         ("out_res", c_float_p),
+        ("out_idx", c_int_p),
+        ("agg", Agg),
         ("precision", ctypes.c_int32),
     ]
 
@@ -61,6 +73,10 @@ class RowMlpBwd(ctypes.Structure):
         ("g1_scale", c_float_p),
         ("g1_batch_stride", ctypes.c_int64),
         ("d_src", c_float_p * MAX_SRC),
+        ("g0_idx", c_int_p),
+        ("d_src_idx", c_int_p * MAX_SRC),
+        ("reduce_src", ctypes.c_int32),
+        ("reduce_accumulate", ctypes.c_int32),
         ("d_params", c_float_p),
         ("workspace", c_float_p),
         ("workspace_floats", ctypes.c_size_t),

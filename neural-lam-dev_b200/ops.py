@@ -16,7 +16,10 @@ from torch import nn
 
 from . import lib as L
 
-_state = {"precision": "fp32"}
+import os as _os
+
+_state = {"precision": "fp32",
+          "disable_aligned": _os.environ.get("NLAM_FUSED_AGG", "1") == "0"}
 _PREC = {"fp32": L.FP32, "bf16": L.BF16}
 
 
@@ -28,6 +31,12 @@ def set_precision(mode):
 
 def get_precision():
     return _state["precision"]
+
+
+def set_fused_aggregation(enabled):
+    """Receiver-aligned tiles with the segment sum inside the edge kernel (bf16
+    path, d in {64,128}) vs. messages written once and summed by nlam_segsum."""
+    _state["disable_aligned"] = not enabled
 
 
 def _stream():
@@ -206,7 +215,9 @@ def weights_of(module):
                    st(t[2].bias for t in trip) if has_ln else None, len(trip))
 
 
-def _fill_desc(desc, srcs, W, batch, rows, residual, tiles, out, precision):
+def _fill_desc(desc, srcs, W, batch, rows, residual, tiles, out, precision, aligned=None):
+    """aligned: optional dict with the receiver-aligned tile table and segment
+    tables of a _GraphPlan (fused aggregation path)."""
     desc.n_src = len(srcs)
     for i, (t, idx) in enumerate(srcs):
         desc.src[i] = _src(t, idx)
@@ -220,6 +231,13 @@ def _fill_desc(desc, srcs, W, batch, rows, residual, tiles, out, precision):
         desc.tile_chunk = tiles.tile_chunk.data_ptr()
         desc.chunk_ptr = tiles.chunk_ptr.data_ptr()
         desc.n_tiles = tiles.n_tiles
+    elif aligned is not None:
+        assert W.n_chunks == 1
+        desc.tile_ptr = aligned["tile_ptr"].data_ptr()
+        desc.n_tiles = aligned["n_tiles"]
+        desc.agg.seg_ptr = aligned["seg_ptr"].data_ptr()
+        desc.agg.tile_seg = aligned["tile_seg"].data_ptr()
+        desc.agg.n_seg = aligned["n_seg"]
     else:
         assert W.n_chunks == 1
         desc.n_tiles = (rows + L.TILE_ROWS - 1) // L.TILE_ROWS
@@ -228,37 +246,59 @@ def _fill_desc(desc, srcs, W, batch, rows, residual, tiles, out, precision):
     desc.precision = _PREC[precision]
 
 
-def rowmlp_fwd_raw(srcs, W, batch, rows, residual, tiles, precision, want_res=False):
+def rowmlp_fwd_raw(srcs, W, batch, rows, residual, tiles, precision, want_res=False,
+                   aligned=None):
     """srcs: list of (3-D tensor, int32 row index or None).  want_res: also
-    return src_0 + out (second output of the same launch)."""
+    return src_0 + out (second output of the same launch).
+    aligned (fused aggregation, see _GraphPlan): rows are processed in
+    receiver-sorted order; returns (None, src_0 + out scattered back through
+    aligned['out_idx'] if want_res else None, aggregated [batch, n_seg, d_out])."""
     lib = L.load()
     dev = srcs[0][0].device
-    out = torch.empty((batch, rows, W.d_out), device=dev, dtype=torch.float32)
     desc = L.RowMlp()
-    _fill_desc(desc, srcs, W, batch, rows, residual, tiles, out, precision)
-    out_res = None
+    out = out_res = agg_out = None
+    if aligned is None:
+        out = torch.empty((batch, rows, W.d_out), device=dev, dtype=torch.float32)
+    _fill_desc(desc, srcs, W, batch, rows, residual, tiles, out, precision, aligned)
     if want_res:
-        out_res = torch.empty_like(out)
+        out_res = torch.empty((batch, rows, W.d_out), device=dev, dtype=torch.float32)
         desc.out_res = out_res.data_ptr()
+    if aligned is not None:
+        agg_out = torch.empty((batch, aligned["n_seg"], W.d_out), device=dev, dtype=torch.float32)
+        desc.agg.out = agg_out.data_ptr()
+        desc.agg.scale = aligned["scale"].data_ptr() if aligned.get("scale") is not None else None
+        desc.out_idx = aligned["out_idx"].data_ptr()
     end = None
     if _timer["t"] is not None:
-        tag, nbytes, flops = _rowmlp_cost(f"rowmlp_fwd_{precision}", srcs, W, batch, rows,
-                                          W.d_out * (2 if want_res else 1))
+        extra = W.d_out * ((1 if out is not None else 0) + (1 if want_res else 0))
+        kind = f"rowmlp_fwd_{precision}" + ("_agg" if aligned is not None else "")
+        tag, nbytes, flops = _rowmlp_cost(kind, srcs, W, batch, rows, extra)
+        if aligned is not None:
+            nbytes += 4 * batch * aligned["n_seg"] * W.d_out + 4 * aligned["n_seg"]
         if _timer["t"].want(tag):
             end = _timer["t"].start(tag, nbytes, flops)
     L.check(lib.nlam_rowmlp_fwd(ctypes.byref(desc), _stream()), "nlam_rowmlp_fwd")
     if end is not None:
         end.record()
+    if aligned is not None:
+        return None, out_res, agg_out
     return (out, out_res) if want_res else out
 
 
 def rowmlp_bwd_raw(srcs, W, batch, rows, residual, tiles, precision, g0, need_src,
-                   g1=None, g1_idx=None, g1_scale=None):
-    """Returns (list of per-row source grads or None, d_params (n_chunks, P))."""
+                   g1=None, g1_idx=None, g1_scale=None, aligned=None, g0_idx=None,
+                   d_src_idx=None, reduce_src=-1, reduce_into=None):
+    """Returns (list of per-row source grads or None, d_params (n_chunks, P)).
+    aligned / g0_idx / d_src_idx / reduce_src: fused-aggregation path; the
+    gradient rows of source `reduce_src` are segment-summed and ADDED into the
+    existing tensor `reduce_into` ([batch, n_seg, width])."""
     lib = L.load()
     dev = srcs[0][0].device
     bd = L.RowMlpBwd()
-    _fill_desc(bd.fwd, srcs, W, batch, rows, residual, tiles, None, precision)
+    _fill_desc(bd.fwd, srcs, W, batch, rows, residual, tiles, None, precision, aligned)
+    bd.reduce_src = -1
+    if g0_idx is not None:
+        bd.g0_idx = g0_idx.data_ptr()
     keep = []
     if g0 is not None:
         g0 = g0.contiguous()
@@ -273,9 +313,17 @@ def rowmlp_bwd_raw(srcs, W, batch, rows, residual, tiles, precision, g0, need_sr
         assert g1.stride(1) == W.d_out or g1.shape[1] == 1
     d_srcs = []
     for i, ((t, _), need) in enumerate(zip(srcs, need_src)):
-        if need:
+        if need and i == reduce_src:
+            assert reduce_into is not None and reduce_into.is_contiguous()
+            bd.d_src[i] = reduce_into.data_ptr()
+            bd.reduce_src = i
+            bd.reduce_accumulate = 1
+            d_srcs.append(reduce_into)
+        elif need:
             g = torch.empty((batch, rows, t.shape[2]), device=dev, dtype=torch.float32)
             bd.d_src[i] = g.data_ptr()
+            if d_src_idx is not None and d_src_idx[i] is not None:
+                bd.d_src_idx[i] = d_src_idx[i].data_ptr()
             d_srcs.append(g)
         else:
             d_srcs.append(None)
@@ -396,6 +444,14 @@ def split_mlp_forward(module, x):
     return out.reshape(*lead, W.d_out)
 
 
+def _use_aligned(plan, We, Wa, precision):
+    """Fused-aggregation path: bf16 tensor-core kernels, square d in {64, 128},
+    one weight set, and a graph whose in-degrees fit a 128-row tile."""
+    return (precision == "bf16" and plan.alignable and We.n_chunks == 1 and Wa.n_chunks == 1
+            and We.d_hidden == We.d_out and We.d_out in (64, 128) and We.k == 3 * We.d_out
+            and not _state.get("disable_aligned", False))
+
+
 class _InteractionNetFn(torch.autograd.Function):
     """Whole InteractionNet layer (interaction_net.py:86-131):
     gather -> edge MLP (+edge residual) -> segment sum/mean -> node MLP + residual."""
@@ -416,18 +472,26 @@ class _InteractionNetFn(torch.autograd.Function):
             raise RuntimeError(
                 f"InteractionNet: got send/rec/edge rows {send3.shape[1]}/{rec3.shape[1]}/"
                 f"{edge3.shape[1]}, edge_index needs >={plan.n_send_idx}/{n_rec}/{M}")
-        # message + edge residual
-        edge_out = rowmlp_fwd_raw(
-            [(edge3, None), (send3, plan.send32), (rec3, plan.recv32)], We, B, M,
-            False, plan.edge_tiles, prec, want_res=meta["update_edges"])
-        new_edge = None
-        if meta["update_edges"]:
-            edge_out, new_edge = edge_out  # messages m_k and E' = E + m (:112)
-        # edge_out holds the messages m_k; aggregate (sum / mean over receivers)
-        aggr = segsum_raw(edge_out, plan.rowptr, plan.perm, n_rec,
-                          scale=plan.inv_deg if meta["aggr"] == "mean" else None)
+        al = plan.aligned_tables(meta["aggr"]) if _use_aligned(plan, We, Wa, prec) else None
+        if al is not None:
+            # receiver-sorted, receiver-aligned tiles: gather -> edge MLP -> (E' scatter)
+            # -> per-receiver sum inside ONE kernel; the messages never reach HBM
+            _, new_edge, aggr = rowmlp_fwd_raw(
+                [(edge3, plan.perm), (send3, plan.send_sorted), (rec3, plan.recv_sorted)],
+                We, B, M, False, None, prec, want_res=meta["update_edges"], aligned=al)
+        else:
+            # message (+ E' = E + m as second output), then CSR segment sum / mean
+            edge_out = rowmlp_fwd_raw(
+                [(edge3, None), (send3, plan.send32), (rec3, plan.recv32)], We, B, M,
+                False, plan.edge_tiles, prec, want_res=meta["update_edges"])
+            new_edge = None
+            if meta["update_edges"]:
+                edge_out, new_edge = edge_out  # messages m_k and E' = E + m (:112)
+            aggr = segsum_raw(edge_out, plan.rowptr, plan.perm, n_rec,
+                              scale=plan.inv_deg if meta["aggr"] == "mean" else None)
         rec_out = rowmlp_fwd_raw([(rec3, None), (aggr, None)], Wa, B, n_rec, True,
                                  plan.aggr_tiles, prec)
+        meta = dict(meta, aligned=al is not None)
         ctx.meta = meta
         ctx.set_materialize_grads(False)  # unused outputs arrive as None, not zeros
         ctx.save_for_backward(*ew, *aw, send3, rec3, edge3, aggr)
@@ -456,25 +520,38 @@ class _InteractionNetFn(torch.autograd.Function):
         (dR, dA), dPa = rowmlp_bwd_raw(
             [(rec3, None), (aggr, None)], Wa, B, n_rec, True, plan.aggr_tiles, prec,
             d_rec_out, [True, True])
-        # edge stage: dm_k = dA[r(k)] (/deg) ; E' = E + m handled after
+        # edge stage: dm_k = dE'_k + dA[r(k)] (/deg)
         need_send, need_rec, need_edge = ctx.needs_input_grad[13:16]
-        (dzE, dzS, dzR), dPe = rowmlp_bwd_raw(
-            [(edge3, None), (send3, plan.send32), (rec3, plan.recv32)], We, B, M,
-            d_edge_out is not None,  # E' = E + m: the kernel adds dE' to the edge gradient
-            plan.edge_tiles, prec, d_edge_out, [need_edge, need_send, need_rec],
-            g1=dA, g1_idx=plan.recv32,
-            g1_scale=plan.inv_deg if meta["aggr"] == "mean" else None)
-        d_edge = dzE if need_edge else None
-        d_send = None
-        if need_send:
-            n_send = send3.shape[1]
-            d_send = segsum_raw(dzS, plan.t_rowptr, plan.t_perm, plan.n_send_idx)
-            if n_send > plan.n_send_idx:  # trailing senders without any edge
-                pad = torch.zeros((B, n_send - plan.n_send_idx, dzS.shape[2]), device=dev)
-                d_send = torch.cat((d_send, pad), dim=1)
-        d_rec = None
-        if need_rec:
-            d_rec = segsum_raw(dzR, plan.rowptr, plan.perm, n_rec, out=dR, accumulate=True)
+        scale = plan.inv_deg if meta["aggr"] == "mean" else None
+        if meta["aligned"]:
+            al = plan.aligned_tables(meta["aggr"])
+            (d_edge, dzS, d_rec), dPe = rowmlp_bwd_raw(
+                [(edge3, plan.perm), (send3, plan.send_sorted), (rec3, plan.recv_sorted)],
+                We, B, M, d_edge_out is not None, None, prec, d_edge_out,
+                [need_edge, need_send, need_rec], g1=dA, g1_idx=plan.recv_sorted,
+                g1_scale=scale, aligned=al, g0_idx=plan.perm,
+                d_src_idx=[plan.perm, None, None], reduce_src=2 if need_rec else -1,
+                reduce_into=dR)
+            d_send = None
+            if need_send:
+                d_send = segsum_raw(dzS, plan.ts_rowptr, plan.ts_perm, plan.n_send_idx)
+        else:
+            (dzE, dzS, dzR), dPe = rowmlp_bwd_raw(
+                [(edge3, None), (send3, plan.send32), (rec3, plan.recv32)], We, B, M,
+                d_edge_out is not None,  # E' = E + m: the kernel adds dE' to the edge gradient
+                plan.edge_tiles, prec, d_edge_out, [need_edge, need_send, need_rec],
+                g1=dA, g1_idx=plan.recv32, g1_scale=scale)
+            d_edge = dzE if need_edge else None
+            d_send = None
+            if need_send:
+                d_send = segsum_raw(dzS, plan.t_rowptr, plan.t_perm, plan.n_send_idx)
+            d_rec = None
+            if need_rec:
+                d_rec = segsum_raw(dzR, plan.rowptr, plan.perm, n_rec, out=dR, accumulate=True)
+        if d_send is not None and send3.shape[1] > plan.n_send_idx:
+            pad = torch.zeros((B, send3.shape[1] - plan.n_send_idx, d_send.shape[2]), device=dev)
+            d_send = torch.cat((d_send, pad), dim=1)  # trailing senders without any edge
+
         def fit(g, t):  # batch-1 inputs broadcast against a larger batch
             if g is not None and t.shape[0] == 1 and g.shape[0] > 1:
                 g = g.sum(0, keepdim=True)

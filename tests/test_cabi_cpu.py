@@ -34,7 +34,8 @@ def test_struct_sizes_match_header(built):
     import ctypes
     assert ctypes.sizeof(built.Src) == 32
     assert ctypes.sizeof(built.MlpWeights) == 48
-    assert ctypes.sizeof(built.RowMlp) == 8 + 3 * 32 + 16 + 48 + 8 + 24 + 8 + 8 + 8 + 8
+    assert ctypes.sizeof(built.Agg) == 40
+    assert ctypes.sizeof(built.RowMlp) == 8 + 3 * 32 + 16 + 48 + 8 + 24 + 8 + 8 + 8 + 8 + 40 + 8
     assert ctypes.sizeof(built.SegSum) == 64
 
 

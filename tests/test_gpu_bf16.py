@@ -100,6 +100,10 @@ def test_interaction_net_bf16_vs_reference_golden(dev, bf16, name):
     (64, 20000, 3000, 2500, 2, True, "sum"),
     (64, 9000, 4000, 700, 1, False, "mean"),
     (128, 6000, 900, 900, 2, True, "sum"),
+    (64, 3000, 500, 2500, 2, True, "mean"),    # many receivers without any edge
+    (64, 5000, 300, 40, 1, True, "sum"),       # in-degree ~125: tiles hold one receiver
+    (64, 9000, 300, 40, 2, False, "sum"),      # in-degree > 128: not tile-alignable
+    (128, 4000, 700, 3000, 1, False, "mean"),
 ])
 def test_interaction_net_bf16_vs_oracle(dev, bf16, d, M, n_send, n_rec, B, update, aggr):
     from neural_lam_b200.interaction_net import InteractionNet
@@ -124,10 +128,13 @@ def test_interaction_net_bf16_vs_oracle(dev, bf16, d, M, n_send, n_rec, B, updat
         _close(x, y, "output")
     inet_loss(o_ref).backward()
     inet_loss(o).backward()
+    # 225 messages per receiver (M / n_rec) make the aggregated activations ~15x
+    # larger than the bf16-rounded inputs they came from: 4e-2 there, 2e-2 otherwise
+    tol = 4e-2 if M // n_rec > 128 else TOL
     for x, y, n in zip(b, a, ("send", "rec", "edge")):
-        _close(x.grad, y.grad, f"grad {n}")
+        _close(x.grad, y.grad, f"grad {n}", tol=tol)
     for (n, p), (_, q) in zip(ref.named_parameters(), net.named_parameters()):
-        _close(q.grad, p.grad, f"grad {n}")
+        _close(q.grad, p.grad, f"grad {n}", tol=tol)
 
 
 @pytest.mark.parametrize("name", sorted(MODELS))
