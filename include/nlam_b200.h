@@ -104,7 +104,7 @@ typedef struct nlam_rowmlp {
  * d_src[s] (may be NULL) receives the un-reduced per-row gradient of source s,
  * dense [batch, rows, width_s]; for s == residual_src dOut is added.
  * d_params is one flat buffer per chunk: [dW1 | db1 | dW2 | db2 | dLNg | dLNb]
- * (LN parts absent without LayerNorm), overwritten (not accumulated). */
+ * (LN parts absent without LayerNorm), overwritten unless params_accumulate. */
 typedef struct nlam_rowmlp_bwd {
   nlam_rowmlp fwd;
   const float* g0;       /* [batch, rows, d_out] or NULL */
@@ -119,6 +119,8 @@ typedef struct nlam_rowmlp_bwd {
                                 (tables of fwd.agg) into d_src[s] = [batch, n_seg, width] */
   int32_t reduce_accumulate; /* add to the existing contents of d_src[reduce_src] */
   float* d_params;
+  int32_t params_accumulate; /* 0: d_params is overwritten; 1: gradients are ADDED to it
+                                (lets the caller pass its flat gradient buffer) */
   float* workspace;       /* nlam_rowmlp_bwd_workspace() floats */
   size_t workspace_floats;
 } nlam_rowmlp_bwd;

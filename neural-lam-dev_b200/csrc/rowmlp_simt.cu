@@ -597,6 +597,7 @@ struct RParams {
   int batch, n_tiles, d_out;
   const int32_t* tile_chunk;
   float* out;
+  int accumulate;
 };
 __global__ void __launch_bounds__(256) reduce_params_kernel(const __grid_constant__ RParams p) {
   // Block = 32 consecutive output elements (coalesced 128-byte rows of the partial
@@ -627,13 +628,15 @@ __global__ void __launch_bounds__(256) reduce_params_kernel(const __grid_constan
     float t = 0.f;
 #pragma unroll
     for (int i = 0; i < 8; ++i) t += red[i][lane];
-    p.out[(size_t)chunk * p.p_total + j] = t;
+    float* o = p.out + (size_t)chunk * p.p_total + j;
+    *o = p.accumulate ? *o + t : t;
   }
 }
 
 int launch_reduce_params(const float* partial, int splits, int n_chunks, int p_total, float* out,
-                         cudaStream_t st) {
+                         int accumulate, cudaStream_t st) {
   RParams rp{};
+  rp.accumulate = accumulate;
   rp.partial = partial, rp.splits = splits, rp.n_chunks = n_chunks;
   rp.p_total = p_total, rp.p_main = p_total;
   rp.out = out;
@@ -747,7 +750,8 @@ int simt_rowmlp_bwd(const nlam_rowmlp_bwd& bd, cudaStream_t st) {
   NLAM_CHECK(bd.d_params, "rowmlp_bwd: d_params is NULL");
   const ParamLayout lay = p.lay;
   if (d.rows == 0) {
-    NLAM_CUDA(cudaMemsetAsync(bd.d_params, 0, sizeof(float) * (size_t)d.n_chunks * lay.total(), st));
+    if (!bd.params_accumulate)
+      NLAM_CUDA(cudaMemsetAsync(bd.d_params, 0, sizeof(float) * (size_t)d.n_chunks * lay.total(), st));
     return 0;
   }
   NLAM_CHECK(bd.g0 || bd.g1, "rowmlp_bwd: no output gradient given");
@@ -800,6 +804,7 @@ int simt_rowmlp_bwd(const nlam_rowmlp_bwd& bd, cudaStream_t st) {
   rp.p_total = lay.total(), rp.p_main = lay.off_b2() + d.d_out;
   rp.ln_partial = p.ln_partial, rp.batch = d.batch, rp.n_tiles = n_tiles_of(d);
   rp.d_out = d.d_out, rp.tile_chunk = d.tile_chunk, rp.out = bd.d_params;
+  rp.accumulate = bd.params_accumulate;
 
   const int dp = pick_dp(d);
   switch (dp) {

@@ -23,7 +23,7 @@ namespace nlam {
 
 // defined in rowmlp_simt.cu
 int launch_reduce_params(const float* partial, int splits, int n_chunks, int p_total,
-                         float* out, cudaStream_t st);
+                         float* out, int accumulate, cudaStream_t st);
 
 namespace tc {
 
@@ -889,7 +889,8 @@ int tc_rowmlp_bwd(const nlam_rowmlp_bwd& bd, cudaStream_t st) {
   if (fill_params(d, p)) return 1;
   NLAM_CHECK(bd.d_params, "rowmlp_bwd: d_params is NULL");
   if (d.rows == 0) {
-    NLAM_CUDA(cudaMemsetAsync(bd.d_params, 0, sizeof(float) * (size_t)d.n_chunks * p.lay.total(), st));
+    if (!bd.params_accumulate)
+      NLAM_CUDA(cudaMemsetAsync(bd.d_params, 0, sizeof(float) * (size_t)d.n_chunks * p.lay.total(), st));
     return 0;
   }
   NLAM_CHECK(bd.g0 || bd.g1, "rowmlp_bwd: no output gradient given");
@@ -959,7 +960,8 @@ int tc_rowmlp_bwd(const nlam_rowmlp_bwd& bd, cudaStream_t st) {
   }
 #undef NLAM_BWD_PAIR
   if (rc) return rc;
-  return launch_reduce_params(g.partial, ws.slots, d.n_chunks, g.p_total, bd.d_params, st);
+  return launch_reduce_params(g.partial, ws.slots, d.n_chunks, g.p_total, bd.d_params,
+                              bd.params_accumulate, st);
 }
 
 }  // namespace nlam

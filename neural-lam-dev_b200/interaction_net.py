@@ -146,6 +146,8 @@ class InteractionNet(nn.Module):
             "aggr": self.aggr,
             "update_edges": self.update_edges,
             "precision": ops.get_precision(),
+            "edge_params": We.t,
+            "aggr_params": Wa.t,
         }
         out = ops._InteractionNetFn.apply(meta, *We.t, *Wa.t, send_rep, rec_rep, edge_rep)
         if self.update_edges:

@@ -78,6 +78,7 @@ class RowMlpBwd(ctypes.Structure):
         ("reduce_src", ctypes.c_int32),
         ("reduce_accumulate", ctypes.c_int32),
         ("d_params", c_float_p),
+        ("params_accumulate", ctypes.c_int32),
         ("workspace", c_float_p),
         ("workspace_floats", ctypes.c_size_t),
     ]

@@ -33,6 +33,35 @@ def get_precision():
     return _state["precision"]
 
 
+def set_param_grad_sink(enabled):
+    """When the six gradient tensors (.grad) of an MLP already exist and are
+    adjacent views of one flat buffer (train.FlatGradBuckets), let the kernels
+    ADD the weight gradients straight into that buffer instead of returning them
+    to autograd (which would launch one accumulation kernel per parameter)."""
+    _state["grad_sink"] = bool(enabled)
+
+
+def _grad_sink(params):
+    """Flat destination tensor for an MLP's parameter gradients, or None."""
+    if not _state.get("grad_sink", False):
+        return None
+    ps = [q for q in params if q is not None]
+    if any((not isinstance(q, nn.Parameter)) or q.grad is None or not q.grad.is_contiguous()
+           or q.grad.dtype != torch.float32 for q in ps):
+        return None
+    base = ps[0].grad
+    off = base.data_ptr()
+    total = 0
+    for q in ps:
+        if q.grad.data_ptr() != off:
+            return None
+        off += 4 * q.numel()
+        total += q.numel()
+    if base.storage_offset() + total > base.untyped_storage().nbytes() // 4:
+        return None
+    return torch.as_strided(base, (1, total), (total, 1))
+
+
 def set_fused_aggregation(enabled):
     """Receiver-aligned tiles with the segment sum inside the edge kernel (bf16
     path, d in {64,128}) vs. messages written once and summed by nlam_segsum."""
@@ -170,7 +199,10 @@ class Weights:
         return n + (2 * self.d_out if self.has_ln else 0)
 
     def split_grads(self, flat):
-        """flat (n_chunks, P) -> grads shaped like self.t."""
+        """flat (n_chunks, P) -> grads shaped like self.t (all None if the
+        gradients were accumulated in place, see set_param_grad_sink)."""
+        if flat is None:
+            return [None] * 6
         C, dh, k, do = self.n_chunks, self.d_hidden, self.k, self.d_out
         sizes = [dh * k, dh, do * dh, do] + ([do, do] if self.has_ln else [])
         parts = torch.split(flat, sizes, dim=1)
@@ -287,7 +319,7 @@ def rowmlp_fwd_raw(srcs, W, batch, rows, residual, tiles, precision, want_res=Fa
 
 def rowmlp_bwd_raw(srcs, W, batch, rows, residual, tiles, precision, g0, need_src,
                    g1=None, g1_idx=None, g1_scale=None, aligned=None, g0_idx=None,
-                   d_src_idx=None, reduce_src=-1, reduce_into=None):
+                   d_src_idx=None, reduce_src=-1, reduce_into=None, sink_params=None):
     """Returns (list of per-row source grads or None, d_params (n_chunks, P)).
     aligned / g0_idx / d_src_idx / reduce_src: fused-aggregation path; the
     gradient rows of source `reduce_src` are segment-summed and ADDED into the
@@ -327,8 +359,14 @@ def rowmlp_bwd_raw(srcs, W, batch, rows, residual, tiles, precision, g0, need_sr
             d_srcs.append(g)
         else:
             d_srcs.append(None)
-    d_params = torch.empty((W.n_chunks, W.param_floats()), device=dev, dtype=torch.float32)
-    bd.d_params = d_params.data_ptr()
+    sink = _grad_sink(sink_params) if (W.n_chunks == 1 and sink_params is not None) else None
+    if sink is not None:
+        d_params = None  # gradients are accumulated in place; autograd gets None
+        bd.d_params = sink.data_ptr()
+        bd.params_accumulate = 1
+    else:
+        d_params = torch.empty((W.n_chunks, W.param_floats()), device=dev, dtype=torch.float32)
+        bd.d_params = d_params.data_ptr()
     nws = lib.nlam_rowmlp_bwd_workspace(ctypes.byref(bd.fwd))
     ws = torch.empty((max(int(nws), 4),), device=dev, dtype=torch.float32)
     bd.workspace = ws.data_ptr()
@@ -416,7 +454,7 @@ class _RowMLPFn(torch.autograd.Function):
         B, rows, _ = x3.shape
         d_srcs, d_params = rowmlp_bwd_raw(
             [(x3, None)], W, B, rows, meta["residual"], meta["tiles"], meta["precision"],
-            gout, [ctx.needs_input_grad[7]])
+            gout, [ctx.needs_input_grad[7]], sink_params=meta.get("params"))
         gw = W.split_grads(d_params)
         return (None, *gw, d_srcs[0])
 
@@ -427,7 +465,8 @@ def mlp_forward(module, x, residual=False):
     W = weights_of(module)
     lead = x.shape[:-1]
     x3 = x.reshape(1, -1, x.shape[-1]) if x.dim() != 3 else x
-    meta = {"n_chunks": 1, "residual": residual, "tiles": None, "precision": get_precision()}
+    meta = {"n_chunks": 1, "residual": residual, "tiles": None, "precision": get_precision(),
+            "params": W.t}
     out = _RowMLPFn.apply(meta, *W.t, x3)
     return out.reshape(*lead, W.d_out)
 
@@ -519,7 +558,7 @@ class _InteractionNetFn(torch.autograd.Function):
         # node stage: R' = R + aggr_mlp([R | A])
         (dR, dA), dPa = rowmlp_bwd_raw(
             [(rec3, None), (aggr, None)], Wa, B, n_rec, True, plan.aggr_tiles, prec,
-            d_rec_out, [True, True])
+            d_rec_out, [True, True], sink_params=meta.get("aggr_params"))
         # edge stage: dm_k = dE'_k + dA[r(k)] (/deg)
         need_send, need_rec, need_edge = ctx.needs_input_grad[13:16]
         scale = plan.inv_deg if meta["aggr"] == "mean" else None
@@ -531,7 +570,7 @@ class _InteractionNetFn(torch.autograd.Function):
                 [need_edge, need_send, need_rec], g1=dA, g1_idx=plan.recv_sorted,
                 g1_scale=scale, aligned=al, g0_idx=plan.perm,
                 d_src_idx=[plan.perm, None, None], reduce_src=2 if need_rec else -1,
-                reduce_into=dR)
+                reduce_into=dR, sink_params=meta.get("edge_params"))
             d_send = None
             if need_send:
                 d_send = segsum_raw(dzS, plan.ts_rowptr, plan.ts_perm, plan.n_send_idx)
@@ -540,7 +579,7 @@ class _InteractionNetFn(torch.autograd.Function):
                 [(edge3, None), (send3, plan.send32), (rec3, plan.recv32)], We, B, M,
                 d_edge_out is not None,  # E' = E + m: the kernel adds dE' to the edge gradient
                 plan.edge_tiles, prec, d_edge_out, [need_edge, need_send, need_rec],
-                g1=dA, g1_idx=plan.recv32, g1_scale=scale)
+                g1=dA, g1_idx=plan.recv32, g1_scale=scale, sink_params=meta.get("edge_params"))
             d_edge = dzE if need_edge else None
             d_send = None
             if need_send:

@@ -63,6 +63,7 @@ class FlatGradBuckets:
         self.n_early = sum(p.numel() for _, p in early)
         self.overlap = overlap and world_size > 1 and self.n_early > 0 and dev.type == "cuda"
         self._pending = 0
+        self._early_started = False
         self._early_params = [p for _, p in early]
         self._early_work = None
         self.side = torch.cuda.Stream(device=dev) if self.overlap else None
@@ -74,10 +75,23 @@ class FlatGradBuckets:
         self.flat.zero_()
         self._pending = len(self._early_params)
         self._early_work = None
+        self._early_started = False
+
+    def early_ready(self, grad=None):
+        """All gradients of the early bucket are enqueued on the compute stream."""
+        if self.overlap and self._early_work is None and not self._early_started:
+            self._early_started = True
+            self._launch_early()
+        return grad
 
     def _hook(self, _param):
         self._pending -= 1
-        if self._pending == 0:
+        if self._pending == 0 and not self._early_started:
+            self._early_started = True
+            self._launch_early()
+
+    def _launch_early(self):
+        if True:
             # all early gradients are written on the compute stream: reduce them
             # on the side stream while backward continues
             self.side.wait_stream(torch.cuda.current_stream())
@@ -102,10 +116,10 @@ class FlatGradBuckets:
 
 
 # gradients of these sub-modules are final before backward enters the encoder
-EARLY_PREFIXES = ("output_map", "m2g_gnn", "m2g_embedder", "processor", "m2m_embedder",
-                  "mesh_down", "mesh_up", "mesh_same", "mesh_init", "mesh_read",
-                  "mesh_embedders", "mesh_same_embedders", "mesh_up_embedders",
-                  "mesh_down_embedders")
+# (the static-feature embedders are created first in predict_step, so autograd runs
+# their backward last: they belong to the late bucket)
+EARLY_PREFIXES = ("output_map", "m2g_gnn", "processor", "mesh_down_gnns", "mesh_down_same_gnns",
+                  "mesh_up_gnns", "mesh_up_same_gnns", "mesh_init_gnns", "mesh_read_gnns")
 
 
 class DataParallelTrainer:
@@ -132,6 +146,19 @@ class DataParallelTrainer:
         self.buckets = FlatGradBuckets(list(model.named_parameters()), world_size,
                                        EARLY_PREFIXES, overlap)
         self.optimizer = model.configure_optimizers()
+        # weight gradients go straight into the flat buffer (no per-parameter
+        # accumulation kernels); autograd then never "sees" them, so the early
+        # all-reduce is triggered by the backward of the encoder output instead
+        from . import ops
+        ops.set_param_grad_sink(True)
+        if self.buckets.overlap and hasattr(model, "g2m_gnn"):
+            model.g2m_gnn.register_forward_hook(self._encoder_output_hook)
+
+    def _encoder_output_hook(self, _module, _inputs, output):
+        # fires in backward once everything downstream of the g2m encoder (decoder,
+        # processor) has been differentiated, i.e. its kernels are enqueued
+        if torch.is_tensor(output) and output.requires_grad:
+            output.register_hook(self.buckets.early_ready)
 
     def _eager_step(self, batch):
         self.buckets.zero()
@@ -145,7 +172,15 @@ class DataParallelTrainer:
         self._static_batch = tuple(torch.empty_like(t) for t in batch)
         for dst, src in zip(self._static_batch, batch):
             dst.copy_(src)
-        # warm-up on a side stream (allocator pools, CSR plans, kernel attributes)
+        # warm-up on a side stream (allocator pools, CSR plans, kernel attributes,
+        # lazily created optimizer state); weights and optimizer state are put
+        # back IN PLACE afterwards (the graph refers to these very tensors)
+        params = [p for p in self.model.parameters()]
+        saved_params = [p.detach().clone() for p in params]
+        had_state = len(self.optimizer.state) > 0
+        saved_state = {id(p): {k: (v.clone() if torch.is_tensor(v) else v)
+                               for k, v in st.items()}
+                       for p, st in self.optimizer.state.items()} if had_state else None
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):
@@ -153,6 +188,16 @@ class DataParallelTrainer:
                 self._eager_step(self._static_batch)
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
+        with torch.no_grad():
+            for p, q in zip(params, saved_params):
+                p.copy_(q)
+            for p, st in self.optimizer.state.items():
+                for k, v in st.items():
+                    if torch.is_tensor(v):
+                        if had_state:
+                            v.copy_(saved_state[id(p)][k])
+                        else:
+                            v.zero_()
         self._graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self._graph):
             self._static_loss = self._eager_step(self._static_batch)
