@@ -598,6 +598,11 @@ struct RParams {
   const int32_t* tile_chunk;
   float* out;
   int accumulate;
+  // optional second partial buffer holding only the bias / LayerNorm-affine
+  // gradients: [vec_slots][n_chunks][vec_len], laid out [db1 | db2 | dLNg | dLNb]
+  const float* vec_partial;
+  int vec_slots, vec_len;
+  ParamLayout lay;
 };
 __global__ void __launch_bounds__(256) reduce_params_kernel(const __grid_constant__ RParams p) {
   // Block = 32 consecutive output elements (coalesced 128-byte rows of the partial
@@ -609,7 +614,17 @@ __global__ void __launch_bounds__(256) reduce_params_kernel(const __grid_constan
   const int chunk = blockIdx.y;
   float s = 0.f;
   if (j < p.p_total) {
-    if (j < p.p_main) {
+    int v = -1;
+    if (p.vec_partial) {  // is j a bias / LayerNorm-affine entry?
+      const ParamLayout& L = p.lay;
+      if (j >= L.off_b1() && j < L.off_w2()) v = j - L.off_b1();
+      else if (j >= L.off_b2() && j < L.off_b2() + L.d_out) v = L.d_hidden + j - L.off_b2();
+      else if (L.has_ln && j >= L.off_lng()) v = L.d_hidden + L.d_out + j - L.off_lng();
+    }
+    if (v >= 0) {
+      for (int sp = w; sp < p.vec_slots; sp += 8)
+        s += p.vec_partial[((size_t)sp * p.n_chunks + chunk) * p.vec_len + v];
+    } else if (j < p.p_main) {
       for (int sp = w; sp < p.splits; sp += 8)
         s += p.partial[((size_t)sp * p.n_chunks + chunk) * p.p_total + j];
     } else {
@@ -634,9 +649,11 @@ __global__ void __launch_bounds__(256) reduce_params_kernel(const __grid_constan
 }
 
 int launch_reduce_params(const float* partial, int splits, int n_chunks, int p_total, float* out,
-                         int accumulate, cudaStream_t st) {
+                         int accumulate, const float* vec_partial, int vec_slots, int vec_len,
+                         ParamLayout lay, cudaStream_t st) {
   RParams rp{};
   rp.accumulate = accumulate;
+  rp.vec_partial = vec_partial, rp.vec_slots = vec_slots, rp.vec_len = vec_len, rp.lay = lay;
   rp.partial = partial, rp.splits = splits, rp.n_chunks = n_chunks;
   rp.p_total = p_total, rp.p_main = p_total;
   rp.out = out;

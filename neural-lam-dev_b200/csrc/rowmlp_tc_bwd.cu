@@ -23,7 +23,8 @@ namespace nlam {
 
 // defined in rowmlp_simt.cu
 int launch_reduce_params(const float* partial, int splits, int n_chunks, int p_total,
-                         float* out, int accumulate, cudaStream_t st);
+                         float* out, int accumulate, const float* vec_partial, int vec_slots,
+                         int vec_len, ParamLayout lay, cudaStream_t st);
 
 namespace tc {
 
@@ -40,8 +41,9 @@ struct BGeo {
   uint8_t* a_img;
   uint8_t* dy_img;
   uint8_t* dh_img;
-  float* partial;        // [slots][n_chunks][p_total]
-  int p_total;
+  float* partial;        // wgrad: [w_slots][n_chunks][p_total] (matrix entries)
+  float* vec_partial;    // dgrad: [d_slots][n_chunks][vec_len] = [db1 | db2 | dLNg | dLNb]
+  int p_total, vec_len;
   // wgrad
   int w_tmem_cols, w_mchunks;
   uint32_t w_off_a, w_off_dy, w_off_dh, w_off_bar, w_smem_bytes;
@@ -189,8 +191,7 @@ rowmlp_tc_dgrad_kernel(const __grid_constant__ KParams p, const __grid_constant_
       }
     }
     __syncthreads();
-    const ParamLayout lay = p.lay;
-    float* dst = g.partial + ((size_t)blockIdx.x * p.d.n_chunks + chunk) * g.p_total;
+    float* dst = g.vec_partial + ((size_t)blockIdx.x * p.d.n_chunks + chunk) * g.vec_len;
     // which: 0 db1 (n1 cols), 1 db2, 2 dgamma, 3 dbeta (n2 cols)
     for (int e = tid; e < 4 * 128; e += NT) {
       const int which = e >> 7, col = e & 127;
@@ -202,9 +203,9 @@ rowmlp_tc_dgrad_kernel(const __grid_constant__ KParams p, const __grid_constant_
       float s = 0.f;
 #pragma unroll
       for (int qq = 0; qq < 4; ++qq) s += sRed[((h * 4 + qq) * 4 + which) * 64 + cc];
-      const int off = which == 0 ? lay.off_b1() : which == 1 ? lay.off_b2()
-                    : which == 2 ? lay.off_lng() : lay.off_lnb();
-      dst[off + col] = s;
+      const int off = which == 0 ? 0 : which == 1 ? dh : which == 2 ? dh + dout : dh + 2 * dout;
+      // several weight sets: a CTA may come back to a chunk (zero-initialised slots)
+      dst[off + col] = p.d.n_chunks > 1 ? dst[off + col] + s : s;
     }
 #pragma unroll
     for (int i = 0; i < MAXCH; ++i) acc_db1[i] = acc_db2[i] = acc_dg[i] = acc_dbt[i] = 0.f;
@@ -223,6 +224,72 @@ rowmlp_tc_dgrad_kernel(const __grid_constant__ KParams p, const __grid_constant_
       stage_params(p.d, chunk, n1, n2, sPar, 2);  // beta is not needed backward
       loaded_chunk = chunk;
     }
+
+    // dOut = g0 rows (+ scale * gathered g1 rows): batches of 4 units per thread,
+    // row indices first, then all data loads; the combine + store happens later
+    auto dm_load = [&](int base, float4 (&va)[4], float4 (&vb)[4], float (&gs)[4],
+                       int (&rowv)[4], int (&c4v)[4]) {
+      const int w4 = n2 >> 2;
+      const bool vec = (dout & 3) == 0;
+      const float* g0p[4];
+      const float* g1p[4];
+      int colv[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int u = base + j * NT;
+        g0p[j] = g1p[j] = nullptr;
+        gs[j] = 1.f;
+        rowv[j] = -1, c4v[j] = 0, colv[j] = 0;
+        if (u < TM * w4) {
+          const int row = u / w4, c4 = u % w4, col = c4 * 4;
+          rowv[j] = row, c4v[j] = c4, colv[j] = col;
+          if (row < cnt && col < dout) {
+            if (p.g0) {
+              const size_t gr = p.g0_idx ? (size_t)b * p.d.rows + __ldg(p.g0_idx + row0 + row)
+                                         : grow0 + row;
+              g0p[j] = p.g0 + gr * dout + col;
+            }
+            if (p.g1) {
+              const int gi = __ldg(p.g1_idx + row0 + row);
+              if (p.g1_scale) gs[j] = __ldg(p.g1_scale + gi);
+              g1p[j] = p.g1 + (size_t)b * p.g1_batch_stride + (size_t)gi * dout + col;
+            }
+          }
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        va[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+        vb[j] = va[j];
+        if (vec) {
+          if (g0p[j]) va[j] = __ldg(reinterpret_cast<const float4*>(g0p[j]));
+          if (g1p[j]) vb[j] = __ldg(reinterpret_cast<const float4*>(g1p[j]));
+        } else {
+          float t0[4] = {0.f, 0.f, 0.f, 0.f}, t1[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+          for (int e = 0; e < 4; ++e)
+            if (rowv[j] >= 0 && colv[j] + e < dout) {
+              if (g0p[j]) t0[e] = __ldg(g0p[j] + e);
+              if (g1p[j]) t1[e] = __ldg(g1p[j] + e);
+            }
+          va[j] = make_float4(t0[0], t0[1], t0[2], t0[3]);
+          vb[j] = make_float4(t1[0], t1[1], t1[2], t1[3]);
+        }
+      }
+    };
+    auto dm_store = [&](const float4 (&va)[4], const float4 (&vb)[4], const float (&gs)[4],
+                        const int (&rowv)[4], const int (&c4v)[4]) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        if (rowv[j] < 0) continue;
+        const float4 v = make_float4(va[j].x + gs[j] * vb[j].x, va[j].y + gs[j] * vb[j].y,
+                                     va[j].z + gs[j] * vb[j].z, va[j].w + gs[j] * vb[j].w);
+        *reinterpret_cast<float4*>(stg + stg_idx(rowv[j], c4v[j], n2)) = v;
+      }
+    };
+    float4 dm0_a[4], dm0_b[4];
+    float dm0_s[4];
+    int dm0_row[4], dm0_c4[4];
 
     // ---------------- gather rounds + GEMM 1 (H = z . W1^T)
     for (int kb0 = 0; kb0 < g.kb1; kb0 += g.rb) {
@@ -246,72 +313,22 @@ rowmlp_tc_dgrad_kernel(const __grid_constant__ KParams p, const __grid_constant_
         }
         umma_commit(&bars[0]);
       }
+      // first batch of dOut loads flies while the last GEMM-1 round executes
+      if (kbe == g.kb1) dm_load(tid, dm0_a, dm0_b, dm0_s, dm0_row, dm0_c4);
       mbar_wait(&bars[0], ph_main);
       ph_main ^= 1;
       tc_fence_after();
     }
 
-    // ---------------- dOut rows -> fp32 staging (coalesced), rows >= cnt are zero
-    // batches of 4 units: indices first, then all data loads, then the stores
-    {
-      const int w4 = n2 >> 2;
-      const bool vec = (dout & 3) == 0;
-      for (int base = tid; base < TM * w4; base += NT * 4) {
-        const float* g0p[4];
-        const float* g1p[4];
-        float gs[4];
-        int rowv[4], c4v[4], colv[4];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const int u = base + j * NT;
-          g0p[j] = g1p[j] = nullptr;
-          gs[j] = 1.f;
-          rowv[j] = -1;
-          if (u < TM * w4) {
-            const int row = u / w4, c4 = u % w4, col = c4 * 4;
-            rowv[j] = row, c4v[j] = c4, colv[j] = col;
-            if (row < cnt && col < dout) {
-              if (p.g0) {
-                const size_t gr = p.g0_idx ? (size_t)b * p.d.rows + __ldg(p.g0_idx + row0 + row)
-                                           : grow0 + row;
-                g0p[j] = p.g0 + gr * dout + col;
-              }
-              if (p.g1) {
-                const int gi = __ldg(p.g1_idx + row0 + row);
-                if (p.g1_scale) gs[j] = __ldg(p.g1_scale + gi);
-                g1p[j] = p.g1 + (size_t)b * p.g1_batch_stride + (size_t)gi * dout + col;
-              }
-            }
-          }
-        }
-        float4 va[4], vb[4];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          va[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-          vb[j] = va[j];
-          if (vec) {
-            if (g0p[j]) va[j] = __ldg(reinterpret_cast<const float4*>(g0p[j]));
-            if (g1p[j]) vb[j] = __ldg(reinterpret_cast<const float4*>(g1p[j]));
-          } else {
-            float t0[4] = {0.f, 0.f, 0.f, 0.f}, t1[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-            for (int e = 0; e < 4; ++e)
-              if (rowv[j] >= 0 && colv[j] + e < dout) {
-                if (g0p[j]) t0[e] = __ldg(g0p[j] + e);
-                if (g1p[j]) t1[e] = __ldg(g1p[j] + e);
-              }
-            va[j] = make_float4(t0[0], t0[1], t0[2], t0[3]);
-            vb[j] = make_float4(t1[0], t1[1], t1[2], t1[3]);
-          }
-        }
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          if (rowv[j] < 0) continue;
-          const float4 v = make_float4(va[j].x + gs[j] * vb[j].x, va[j].y + gs[j] * vb[j].y,
-                                       va[j].z + gs[j] * vb[j].z, va[j].w + gs[j] * vb[j].w);
-          *reinterpret_cast<float4*>(stg + stg_idx(rowv[j], c4v[j], n2)) = v;
-        }
-      }
+    // ---------------- dOut rows -> fp32 staging (coalesced), rows >= cnt are zero.
+    // The first batch of loads was issued before waiting for GEMM 1 (dm0_*).
+    dm_store(dm0_a, dm0_b, dm0_s, dm0_row, dm0_c4);
+    for (int base = tid + NT * 4; base < TM * (n2 >> 2); base += NT * 4) {
+      float4 va[4], vb[4];
+      float gs[4];
+      int rowv[4], c4v[4];
+      dm_load(base, va, vb, gs, rowv, c4v);
+      dm_store(va, vb, gs, rowv, c4v);
     }
 
     {  // L2 prefetch of the next tile's input and dOut rows
@@ -697,7 +714,9 @@ rowmlp_tc_wgrad_kernel(const __grid_constant__ KParams p, const __grid_constant_
   bool first = true;
 
   auto flush = [&](int chunk) {
-    // accumulators -> per-CTA partial in final [n][k] orientation
+    // accumulators -> per-CTA partial in final [n][k] orientation (added to the
+    // zero-initialised slot when there are several weight sets: a CTA may revisit one)
+    const bool multi = p.d.n_chunks > 1;
     tc_fence_after();
     const ParamLayout lay = p.lay;
     float* dst = g.partial + ((size_t)blockIdx.x * p.d.n_chunks + chunk) * g.p_total;
@@ -712,7 +731,10 @@ rowmlp_tc_wgrad_kernel(const __grid_constant__ KParams p, const __grid_constant_
           if (kg < p.k_total) {
 #pragma unroll
             for (int j = 0; j < 16; ++j)
-              if (F || c0 + j < dh) dst[lay.off_w1() + (size_t)(c0 + j) * p.k_total + kg] = v[j];
+              if (F || c0 + j < dh) {
+                float* o = dst + lay.off_w1() + (size_t)(c0 + j) * p.k_total + kg;
+                *o = multi ? *o + v[j] : v[j];
+              }
           }
         }
       }
@@ -726,7 +748,10 @@ rowmlp_tc_wgrad_kernel(const __grid_constant__ KParams p, const __grid_constant_
         if (r < dh) {
 #pragma unroll
           for (int j = 0; j < 16; ++j)
-            if (F || c0 + j < dout) dst[lay.off_w2() + (size_t)(c0 + j) * dh + r] = v[j];
+            if (F || c0 + j < dout) {
+              float* o = dst + lay.off_w2() + (size_t)(c0 + j) * dh + r;
+              *o = multi ? *o + v[j] : v[j];
+            }
         }
       }
     }
@@ -829,6 +854,7 @@ static int make_bgeo(const KParams& p, BGeo& g) {
   g.tiles_per_batch = n_tiles_of(d, TM);
   g.total_tiles = g.tiles_per_batch * d.batch;
   g.p_total = p.lay.total();
+  g.vec_len = d.d_hidden + d.d_out * (p.lay.has_ln ? 3 : 1);
   // wgrad
   g.w_mchunks = (g.kb1 + 1) / 2;
   g.w_tmem_cols = pow2_cols(g.w_mchunks * g.n1 + g.n2);
@@ -853,9 +879,18 @@ static int grid_for(uint32_t smem, int tmem_cols, int total_tiles) {
   return grid < total_tiles ? grid : total_tiles;
 }
 
+// wgrad CTAs keep their accumulators in TMEM across tiles and flush a full
+// parameter block at the end: few, long-lived CTAs keep the partial traffic small
+static int wgrad_grid(const BGeo& g) {
+  int grid = grid_for(g.w_smem_bytes, g.w_tmem_cols, g.total_tiles);
+  const int want = (g.total_tiles + 3) / 4;
+  if (grid > want) grid = want;
+  return grid < 1 ? 1 : grid;
+}
+
 struct TcBwdWs {
-  size_t a_img, dy_img, dh_img, partial, total;  // float offsets
-  int slots;
+  size_t a_img, dy_img, dh_img, partial, vec_partial, total;  // float offsets
+  int d_slots, w_slots;
 };
 static TcBwdWs tc_bwd_ws(const KParams& p, const BGeo& g) {
   auto al = [](size_t x) { return (x + 255) / 256 * 256; };
@@ -865,10 +900,10 @@ static TcBwdWs tc_bwd_ws(const KParams& p, const BGeo& g) {
   w.a_img = o, o += al((size_t)g.total_tiles * g.kb2 * blk_f);
   w.dy_img = o, o += al((size_t)g.total_tiles * g.kbo * blk_f);
   w.dh_img = o, o += al((size_t)g.total_tiles * g.kb2 * blk_f);
-  const int gd = grid_for(g.smem_bytes, g.tmem_cols, g.total_tiles);
-  const int gw = grid_for(g.w_smem_bytes, g.w_tmem_cols, g.total_tiles);
-  w.slots = gd > gw ? gd : gw;
-  w.partial = o, o += al((size_t)w.slots * p.d.n_chunks * g.p_total);
+  w.d_slots = grid_for(g.smem_bytes, g.tmem_cols, g.total_tiles);
+  w.w_slots = wgrad_grid(g);
+  w.partial = o, o += al((size_t)w.w_slots * p.d.n_chunks * g.p_total);
+  w.vec_partial = o, o += al((size_t)w.d_slots * p.d.n_chunks * g.vec_len);
   w.total = o;
   return w;
 }
@@ -926,11 +961,13 @@ int tc_rowmlp_bwd(const nlam_rowmlp_bwd& bd, cudaStream_t st) {
   g.dy_img = reinterpret_cast<uint8_t*>(bd.workspace + ws.dy_img);
   g.dh_img = reinterpret_cast<uint8_t*>(bd.workspace + ws.dh_img);
   g.partial = bd.workspace + ws.partial;
-  NLAM_CUDA(cudaMemsetAsync(g.partial, 0,
-                            sizeof(float) * (size_t)ws.slots * d.n_chunks * g.p_total, st));
+  g.vec_partial = bd.workspace + ws.vec_partial;
+  if (d.n_chunks > 1)  // a CTA only writes the chunks it visited
+    NLAM_CUDA(cudaMemsetAsync(g.partial, 0,
+                              sizeof(float) * (ws.vec_partial + (size_t)ws.d_slots * d.n_chunks *
+                                                                    g.vec_len - ws.partial), st));
   const int fn = tc::fast_n(p);
-  const int gd = tc::grid_for(g.smem_bytes, g.tmem_cols, g.total_tiles);
-  const int gw = tc::grid_for(g.w_smem_bytes, g.w_tmem_cols, g.total_tiles);
+  const int gd = ws.d_slots, gw = ws.w_slots;
   auto launch = [&](auto kern, int& max_set, int grid, uint32_t smem) -> int {
     if ((int)smem > max_set) {
       NLAM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -960,8 +997,8 @@ int tc_rowmlp_bwd(const nlam_rowmlp_bwd& bd, cudaStream_t st) {
   }
 #undef NLAM_BWD_PAIR
   if (rc) return rc;
-  return launch_reduce_params(g.partial, ws.slots, d.n_chunks, g.p_total, bd.d_params,
-                              bd.params_accumulate, st);
+  return launch_reduce_params(g.partial, ws.w_slots, d.n_chunks, g.p_total, bd.d_params,
+                              bd.params_accumulate, g.vec_partial, ws.d_slots, g.vec_len, p.lay, st);
 }
 
 }  // namespace nlam
