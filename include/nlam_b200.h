@@ -140,6 +140,40 @@ typedef struct nlam_segsum {
   int32_t accumulate; /* 0: overwrite, 1: add to out */
 } nlam_segsum;
 
+/* One auto-regressive state update fused with its loss term:
+ *   pred = prev + net_out*diff_std + diff_mean            (base_graph_model.py:174-177)
+ *   new  = interior ? pred : truth                        (ar_model.py:244-247)
+ *   loss_sum = sum_{rows,f} interior * ((new - truth) * inv_std[f])^2
+ * (metrics.py:21-84 wmse/mse with the interior mask; the caller divides by
+ * batch * steps * #interior, ar_model.py:294-298).  Tensors are [rows, features]
+ * contiguous with rows = batch*nodes; inv_std NULL = unweighted (mse). */
+typedef struct nlam_state_step {
+  const float* net_out;
+  const float* prev;
+  const float* truth;
+  const float* diff_std;  /* [features] */
+  const float* diff_mean; /* [features] */
+  const float* inv_std;   /* [features] = 1/per_var_std, or NULL */
+  const float* interior;  /* [nodes] 1 = interior, 0 = boundary */
+  float* new_state;       /* [rows, features] */
+  float* loss_partial;    /* [nlam_state_step_partials(rows)] scratch */
+  float* loss_sum;        /* [1] */
+  int64_t rows;
+  int32_t nodes;
+  int32_t features;
+} nlam_state_step;
+
+/* Backward: d_pred = interior * (d_new + d_loss * 2 (new - truth) inv_std^2);
+ * d_net_out = d_pred * diff_std; d_prev = d_pred.  d_new / d_loss (device scalar)
+ * may be NULL; fwd.new_state is the saved forward output. */
+typedef struct nlam_state_step_bwd {
+  nlam_state_step fwd;
+  const float* d_new;
+  const float* d_loss;
+  float* d_net_out;
+  float* d_prev;
+} nlam_state_step_bwd;
+
 const char* nlam_last_error(void);
 int nlam_version(void);
 /* Number of kernels this library has launched in this process (monotonic;
@@ -159,6 +193,9 @@ size_t nlam_rowmlp_bwd_workspace(const nlam_rowmlp* desc);
 size_t nlam_rowmlp_param_floats(const nlam_rowmlp* desc); /* per chunk */
 int nlam_rowmlp_bwd_run(const nlam_rowmlp_bwd* desc, void* stream);
 int nlam_segsum_run(const nlam_segsum* desc, void* stream);
+int64_t nlam_state_step_partials(int64_t rows);
+int nlam_state_step_fwd(const nlam_state_step* desc, void* stream);
+int nlam_state_step_bwd_run(const nlam_state_step_bwd* desc, void* stream);
 
 #ifdef __cplusplus
 }

@@ -99,6 +99,18 @@ class SegSum(ctypes.Structure):
     ]
 
 
+class StateStep(ctypes.Structure):
+    _fields_ = [(n, c_float_p) for n in ("net_out", "prev", "truth", "diff_std", "diff_mean",
+                                         "inv_std", "interior", "new_state", "loss_partial",
+                                         "loss_sum")] + [
+        ("rows", ctypes.c_int64), ("nodes", ctypes.c_int32), ("features", ctypes.c_int32)]
+
+
+class StateStepBwd(ctypes.Structure):
+    _fields_ = [("fwd", StateStep), ("d_new", c_float_p), ("d_loss", c_float_p),
+                ("d_net_out", c_float_p), ("d_prev", c_float_p)]
+
+
 # every symbol include/nlam_b200.h declares: name -> (restype, argtypes)
 SYMBOLS = {
     "nlam_last_error": (ctypes.c_char_p, []),
@@ -114,6 +126,9 @@ SYMBOLS = {
     "nlam_rowmlp_param_floats": (ctypes.c_size_t, [ctypes.POINTER(RowMlp)]),
     "nlam_rowmlp_bwd_run": (ctypes.c_int, [ctypes.POINTER(RowMlpBwd), ctypes.c_void_p]),
     "nlam_segsum_run": (ctypes.c_int, [ctypes.POINTER(SegSum), ctypes.c_void_p]),
+    "nlam_state_step_partials": (ctypes.c_int64, [ctypes.c_int64]),
+    "nlam_state_step_fwd": (ctypes.c_int, [ctypes.POINTER(StateStep), ctypes.c_void_p]),
+    "nlam_state_step_bwd_run": (ctypes.c_int, [ctypes.POINTER(StateStepBwd), ctypes.c_void_p]),
 }
 
 _lib = None

@@ -97,10 +97,34 @@ class ARModel(nn.Module):
 
     def training_step(self, batch):
         """Mean over batch and unrolled steps of the masked loss (ar_model.py:287-309)."""
+        if (self.loss in (metrics.wmse, metrics.mse) and not self.output_std
+                and hasattr(self, "net_output") and batch[0].is_cuda):
+            return self._fused_training_step(batch)
         prediction, target, pred_std, _ = self.common_step(batch)
         if self.loss in (metrics.wmse, metrics.mse) and not self.output_std:
             return self._masked_squared_loss(prediction, target, pred_std)
         return torch.mean(self.loss(prediction, target, pred_std, mask=self.interior_mask_bool))
+
+    def _fused_training_step(self, batch):
+        """Same value as the generic path, with the state update, boundary blend and
+        loss term of every AR step done by one kernel (ops.state_step)."""
+        from .. import ops
+        init_states, target_states, forcing_features, _ = batch
+        prev_prev_state, prev_state = init_states[:, 0], init_states[:, 1]
+        if not hasattr(self, "_inv_std_buf") or self._inv_std_buf.device != prev_state.device:
+            self._inv_std_buf = (1.0 / self.per_var_std).contiguous()
+            self._interior_flat = self.interior_mask[:, 0].contiguous()
+        inv_std = self._inv_std_buf if self.loss is metrics.wmse else None
+        n_steps = forcing_features.shape[1]
+        total = None
+        for i in range(n_steps):
+            net_output = self.net_output(prev_state, prev_prev_state, forcing_features[:, i])
+            new_state, loss_sum = ops.state_step(
+                net_output, prev_state, target_states[:, i], self.diff_std, self.diff_mean,
+                inv_std, self._interior_flat)
+            total = loss_sum if total is None else total + loss_sum
+            prev_prev_state, prev_state = prev_state, new_state
+        return total / float(init_states.shape[0] * n_steps * self._num_interior)
 
     def _masked_squared_loss(self, prediction, target, pred_std):
         """mean_{B,T}( mean_{interior nodes}( sum_vars ((pred-target)/std)^2 ) ) -- the

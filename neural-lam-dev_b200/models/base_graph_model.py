@@ -48,6 +48,17 @@ class BaseGraphModel(ARModel):
 
     def predict_step(self, prev_state, prev_prev_state, forcing):
         """X_{t-1}, X_t, forcing -> X_{t+1} (base_graph_model.py:106-177)."""
+        net_output = self.net_output(prev_state, prev_prev_state, forcing)
+        if self.output_std:
+            pred_delta_mean, pred_std_raw = net_output.chunk(2, dim=-1)
+            pred_std = torch.nn.functional.softplus(pred_std_raw)
+        else:
+            pred_delta_mean, pred_std = net_output, None
+        rescaled_delta_mean = pred_delta_mean * self.diff_std + self.diff_mean
+        return prev_state + rescaled_delta_mean, pred_std
+
+    def net_output(self, prev_state, prev_prev_state, forcing):
+        """Encode-process-decode up to the output map (base_graph_model.py:106-159)."""
         batch_size = prev_state.shape[0]
         grid_features = torch.cat(
             (prev_state, prev_prev_state, forcing,
@@ -62,12 +73,4 @@ class BaseGraphModel(ARModel):
         grid_rep = ops.mlp_forward(self.encoding_grid_mlp, grid_emb, residual=True)
         mesh_rep = self.process_step(mesh_rep)
         grid_rep = self.m2g_gnn(mesh_rep, grid_rep, self.expand_to_batch(m2g_emb, batch_size))
-        net_output = self.output_map(grid_rep)
-
-        if self.output_std:
-            pred_delta_mean, pred_std_raw = net_output.chunk(2, dim=-1)
-            pred_std = torch.nn.functional.softplus(pred_std_raw)
-        else:
-            pred_delta_mean, pred_std = net_output, None
-        rescaled_delta_mean = pred_delta_mean * self.diff_std + self.diff_mean
-        return prev_state + rescaled_delta_mean, pred_std
+        return self.output_map(grid_rep)

@@ -598,3 +598,62 @@ class _InteractionNetFn(torch.autograd.Function):
 
         return (None, *We.split_grads(dPe), *Wa.split_grads(dPa), fit(d_send, send3),
                 fit(d_rec, rec3), fit(d_edge, edge3))
+
+
+class _StateStepFn(torch.autograd.Function):
+    """(new_state, loss_sum) = fused AR state update + masked squared-error term
+    (nlam_state_step_fwd / nlam_state_step_bwd_run)."""
+
+    @staticmethod
+    def forward(ctx, net_out, prev, truth, diff_std, diff_mean, inv_std, interior):
+        lib = L.load()
+        net_out, prev, truth = (_rows3d(t, "state").contiguous() for t in (net_out, prev, truth))
+        B, N, F = net_out.shape
+        d = L.StateStep()
+        new_state = torch.empty_like(net_out)
+        n_part = int(lib.nlam_state_step_partials(B * N))
+        partial = torch.empty((n_part,), device=net_out.device, dtype=torch.float32)
+        loss_sum = torch.empty((1,), device=net_out.device, dtype=torch.float32)
+        d.net_out, d.prev, d.truth = net_out.data_ptr(), prev.data_ptr(), truth.data_ptr()
+        d.diff_std, d.diff_mean = diff_std.data_ptr(), diff_mean.data_ptr()
+        d.inv_std = inv_std.data_ptr() if inv_std is not None else None
+        d.interior = interior.data_ptr()
+        d.new_state, d.loss_partial, d.loss_sum = (new_state.data_ptr(), partial.data_ptr(),
+                                                   loss_sum.data_ptr())
+        d.rows, d.nodes, d.features = B * N, N, F
+        L.check(lib.nlam_state_step_fwd(ctypes.byref(d), _stream()), "nlam_state_step_fwd")
+        ctx.set_materialize_grads(False)
+        ctx.save_for_backward(new_state, truth, diff_std, inv_std, interior)
+        ctx.mark_non_differentiable()
+        return new_state, loss_sum.reshape(())
+
+    @staticmethod
+    def backward(ctx, d_new, d_loss):
+        lib = L.load()
+        new_state, truth, diff_std, inv_std, interior = ctx.saved_tensors
+        B, N, F = new_state.shape
+        bd = L.StateStepBwd()
+        bd.fwd.new_state, bd.fwd.truth = new_state.data_ptr(), truth.data_ptr()
+        bd.fwd.diff_std, bd.fwd.interior = diff_std.data_ptr(), interior.data_ptr()
+        bd.fwd.inv_std = inv_std.data_ptr() if inv_std is not None else None
+        bd.fwd.rows, bd.fwd.nodes, bd.fwd.features = B * N, N, F
+        if d_new is not None:
+            d_new = d_new.contiguous()
+            bd.d_new = d_new.data_ptr()
+        if d_loss is not None:
+            d_loss = d_loss.contiguous()
+            bd.d_loss = d_loss.data_ptr()
+        need_net, need_prev = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
+        d_net = torch.empty_like(new_state) if need_net else None
+        d_prev = torch.empty_like(new_state) if need_prev else None
+        if d_net is None and d_prev is None:
+            return (None,) * 7
+        bd.d_net_out = d_net.data_ptr() if d_net is not None else None
+        bd.d_prev = d_prev.data_ptr() if d_prev is not None else None
+        L.check(lib.nlam_state_step_bwd_run(ctypes.byref(bd), _stream()), "nlam_state_step_bwd_run")
+        return d_net, d_prev, None, None, None, None, None
+
+
+def state_step(net_out, prev, truth, diff_std, diff_mean, inv_std, interior):
+    """new_state, loss_sum for one AR step (see _StateStepFn)."""
+    return _StateStepFn.apply(net_out, prev, truth, diff_std, diff_mean, inv_std, interior)
