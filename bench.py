@@ -187,7 +187,20 @@ def run_ours(a):
     from neural_lam_b200 import config as nl_config
     from neural_lam_b200 import lib, models, ops, synthetic, train
 
+    # NCCL prints its version banner on stdout while the communicator is created:
+    # keep stdout to the one JSON line by pointing fd 1 at stderr until then
+    multi = int(os.environ.get("WORLD_SIZE", "1")) > 1
+    if multi:
+        sys.stdout.flush()
+        saved_stdout = os.dup(1)
+        os.dup2(2, 1)
     rank, world, device = train.init_distributed()
+    if multi:
+        dist.barrier()  # creates the communicator
+        torch.cuda.synchronize()
+        sys.stdout.flush()
+        os.dup2(saved_stdout, 1)
+        os.close(saved_stdout)
     assert device.type == "cuda", "bench.py needs a GPU (no CPU fallback for the product path)"
     assert world == a.gpus, f"--gpus {a.gpus} but WORLD_SIZE={world}"
     ops.set_precision(a.precision)
@@ -196,7 +209,7 @@ def run_ours(a):
         torch.manual_seed(42)
         model = models.GraphLAM(args, nl_config.default_config(), ds)
     model = model.to(device)
-    use_graph = bool(a.cuda_graph) and world == 1
+    use_graph = bool(a.cuda_graph)
     trainer = train.DataParallelTrainer(model, rank, world, use_cuda_graph=False)
 
     # rotating set of distinct batches, > 2x L2 in total, so that no step finds its
@@ -329,8 +342,11 @@ def run_ours(a):
         }
         print(json.dumps(line), flush=True)
     if world > 1:
-        dist.barrier()
-        dist.destroy_process_group()
+        # every collective of this run has completed on every rank; skip the NCCL /
+        # CUDA-graph teardown (it can block at interpreter exit) and leave at once
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
 
 
 def main():

@@ -79,6 +79,8 @@ class FlatGradBuckets:
 
     def early_ready(self, grad=None):
         """All gradients of the early bucket are enqueued on the compute stream."""
+        if self.flat.is_cuda and torch.cuda.is_current_stream_capturing():
+            return grad
         if self.overlap and self._early_work is None and not self._early_started:
             self._early_started = True
             self._launch_early()
@@ -103,6 +105,8 @@ class FlatGradBuckets:
         """Finish the gradient mean over ranks (call after backward)."""
         if self.world == 1:
             return
+        if self.flat.is_cuda and torch.cuda.is_current_stream_capturing():
+            raise RuntimeError("the gradient all-reduce must stay outside CUDA-graph capture")
         if self.flat.is_cuda:
             if self._early_work is not None:
                 dist.all_reduce(self.flat[self.n_early:], op=dist.ReduceOp.AVG)
@@ -160,13 +164,17 @@ class DataParallelTrainer:
         if torch.is_tensor(output) and output.requires_grad:
             output.register_hook(self.buckets.early_ready)
 
-    def _eager_step(self, batch):
+    def _forward_backward(self, batch):
         self.buckets.zero()
         loss = self.model.training_step(batch)
         loss.backward()
+        return loss.detach()
+
+    def _eager_step(self, batch):
+        loss = self._forward_backward(batch)
         self.buckets.reduce()
         self.optimizer.step()
-        return loss.detach()
+        return loss
 
     def _capture(self, batch):
         self._static_batch = tuple(torch.empty_like(t) for t in batch)
@@ -198,9 +206,22 @@ class DataParallelTrainer:
                             v.copy_(saved_state[id(p)][k])
                         else:
                             v.zero_()
+        # one process: the whole step is one graph.  Several ranks: forward + backward
+        # are the graph; the (single, latency-bound) NCCL all-reduce and AdamW stay
+        # outside it (NCCL inside a captured graph hung on this stack)
         self._graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self._graph):
-            self._static_loss = self._eager_step(self._static_batch)
+            if self.world == 1:
+                self._static_loss = self._eager_step(self._static_batch)
+            else:
+                self._static_loss = self._forward_backward(self._static_batch)
+
+    def _replay(self):
+        self._graph.replay()
+        if self.world > 1:
+            self.buckets._early_work = None  # no hook fired: whole buffer in one all-reduce
+            self.buckets.reduce()
+            self.optimizer.step()
 
     def step(self, batch):
         if not self.use_cuda_graph:
@@ -209,7 +230,7 @@ class DataParallelTrainer:
             self._capture(batch)
         for dst, src in zip(self._static_batch, batch):
             dst.copy_(src, non_blocking=True)
-        self._graph.replay()
+        self._replay()
         return self._static_loss
 
     def fit_from_host(self, host_batches):
@@ -256,7 +277,7 @@ class DataParallelTrainer:
         if self.use_cuda_graph and self._graph is not None:
             for dst, src in zip(self._static_batch, host_batch):
                 dst.copy_(src, non_blocking=True)  # pinned host -> static device batch
-            self._graph.replay()
+            self._replay()
             return float(self._static_loss.item())
         batch = tuple(t.to(self.device, non_blocking=True) for t in host_batch)
         loss = self.step(batch)
