@@ -287,10 +287,16 @@ def run_ours(a):
                  "src": "measured"}
     except (OSError, KeyError, ValueError):
         pass
+    traffic = None
+    try:
+        with open(os.path.join(ROOT, "profiles", "roofline_traffic.json")) as f:
+            traffic = json.load(f).get(dominant)
+    except (OSError, ValueError):
+        pass
     avg_s = dom_ms / 1e3 / n_l
     gbs = dom_bytes / avg_s / 1e9
     roofline = {"bound": "hbm", "achieved": gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                "frac": gbs / peaks["hbm_gbs"], "traffic": None, "kernel": dominant,
+                "frac": gbs / peaks["hbm_gbs"], "traffic": traffic, "kernel": dominant,
                 "launches_timed": n_l, "avg_us": avg_s * 1e6,
                 "algorithmic_bytes_per_launch": dom_bytes,
                 "tflops": dom_flops / avg_s / 1e12, "peak_src": peaks["src"],

@@ -123,6 +123,10 @@ typedef struct nlam_rowmlp_bwd {
                                 (lets the caller pass its flat gradient buffer) */
   float* workspace;       /* nlam_rowmlp_bwd_workspace() floats */
   size_t workspace_floats;
+  int32_t stage_mask;     /* 0 = everything; else bit 0: input-gradient kernel, bit 1:
+                             weight-gradient kernel, bit 2: partial reduction (lets a
+                             profiler time the three launches separately; the stages
+                             must run in this order on the same workspace) */
 } nlam_rowmlp_bwd;
 
 /* out[b,i,:] (+)= scale[i] * sum_{p in [ptr[i],ptr[i+1])} src[b, idx[p], :]

@@ -735,7 +735,8 @@ static BwdWs bwd_ws(const nlam_rowmlp& d) {
 size_t simt_rowmlp_bwd_workspace(const nlam_rowmlp& d) { return bwd_ws(d).total; }
 
 template <int DP>
-static int launch_bwd(const KParams& p, const WParams& wp, const RParams& rp, cudaStream_t st) {
+static int launch_bwd(const KParams& p, const WParams& wp, const RParams& rp, int mask,
+                      cudaStream_t st) {
   using C = Cfg<DP>;
   static bool attr_set = false;
   if (!attr_set) {
@@ -743,20 +744,26 @@ static int launch_bwd(const KParams& p, const WParams& wp, const RParams& rp, cu
                                    cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM));
     attr_set = true;
   }
-  dim3 grid(n_tiles_of(p.d), p.d.batch);
-  rowmlp_bwd_kernel<DP><<<grid, NT, C::SMEM, st>>>(p);
-  NLAM_CUDA(cudaGetLastError());
-  count_launch();
-  int kb = 0;
-  for (int j = 0; j < wp.n_jobs; ++j) kb += wp.job[j].kblocks;
-  dim3 wgrid(wp.splits, kb, wp.n_chunks);
-  wgrad_kernel<DP><<<wgrid, NT, 0, st>>>(wp);
-  NLAM_CUDA(cudaGetLastError());
-  count_launch();
-  dim3 rgrid((rp.p_total + 31) / 32, rp.n_chunks);
-  reduce_params_kernel<<<rgrid, 256, 0, st>>>(rp);
-  NLAM_CUDA(cudaGetLastError());
-  count_launch();
+  if (mask & 1) {
+    dim3 grid(n_tiles_of(p.d), p.d.batch);
+    rowmlp_bwd_kernel<DP><<<grid, NT, C::SMEM, st>>>(p);
+    NLAM_CUDA(cudaGetLastError());
+    count_launch();
+  }
+  if (mask & 2) {
+    int kb = 0;
+    for (int j = 0; j < wp.n_jobs; ++j) kb += wp.job[j].kblocks;
+    dim3 wgrid(wp.splits, kb, wp.n_chunks);
+    wgrad_kernel<DP><<<wgrid, NT, 0, st>>>(wp);
+    NLAM_CUDA(cudaGetLastError());
+    count_launch();
+  }
+  if (mask & 4) {
+    dim3 rgrid((rp.p_total + 31) / 32, rp.n_chunks);
+    reduce_params_kernel<<<rgrid, 256, 0, st>>>(rp);
+    NLAM_CUDA(cudaGetLastError());
+    count_launch();
+  }
   return 0;
 }
 
@@ -824,11 +831,12 @@ int simt_rowmlp_bwd(const nlam_rowmlp_bwd& bd, cudaStream_t st) {
   rp.accumulate = bd.params_accumulate;
 
   const int dp = pick_dp(d);
+  const int mask = bd.stage_mask ? bd.stage_mask : 7;
   switch (dp) {
-    case 16: return launch_bwd<16>(p, wp, rp, st);
-    case 32: return launch_bwd<32>(p, wp, rp, st);
-    case 64: return launch_bwd<64>(p, wp, rp, st);
-    case 128: return launch_bwd<128>(p, wp, rp, st);
+    case 16: return launch_bwd<16>(p, wp, rp, mask, st);
+    case 32: return launch_bwd<32>(p, wp, rp, mask, st);
+    case 64: return launch_bwd<64>(p, wp, rp, mask, st);
+    case 128: return launch_bwd<128>(p, wp, rp, mask, st);
   }
   set_error("rowmlp_bwd: widths above 128 are not supported");
   return 1;

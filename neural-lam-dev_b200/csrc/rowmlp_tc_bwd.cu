@@ -962,7 +962,7 @@ int tc_rowmlp_bwd(const nlam_rowmlp_bwd& bd, cudaStream_t st) {
   g.dh_img = reinterpret_cast<uint8_t*>(bd.workspace + ws.dh_img);
   g.partial = bd.workspace + ws.partial;
   g.vec_partial = bd.workspace + ws.vec_partial;
-  if (d.n_chunks > 1)  // a CTA only writes the chunks it visited
+  if (d.n_chunks > 1 && (!bd.stage_mask || (bd.stage_mask & 1)))  // CTAs write visited chunks only
     NLAM_CUDA(cudaMemsetAsync(g.partial, 0,
                               sizeof(float) * (ws.vec_partial + (size_t)ws.d_slots * d.n_chunks *
                                                                     g.vec_len - ws.partial), st));
@@ -981,9 +981,12 @@ int tc_rowmlp_bwd(const nlam_rowmlp_bwd& bd, cudaStream_t st) {
   const bool fg = tc::fast_gather(p);
   static int md[5] = {0, 0, 0, 0, 0}, mw[5] = {0, 0, 0, 0, 0};
   int rc;
+  const int mask = bd.stage_mask ? bd.stage_mask : 7;
 #define NLAM_BWD_PAIR(FNV, FGV, I)                                                          \
-  rc = launch(tc::rowmlp_tc_dgrad_kernel<FNV, FGV>, md[I], gd, g.smem_bytes);                \
-  if (!rc) rc = launch(tc::rowmlp_tc_wgrad_kernel<FNV, FGV>, mw[I], gw, g.w_smem_bytes);
+  rc = 0;                                                                                   \
+  if (mask & 1) rc = launch(tc::rowmlp_tc_dgrad_kernel<FNV, FGV>, md[I], gd, g.smem_bytes); \
+  if (!rc && (mask & 2))                                                                    \
+    rc = launch(tc::rowmlp_tc_wgrad_kernel<FNV, FGV>, mw[I], gw, g.w_smem_bytes);
   if (fn == 64 && fg) {
     NLAM_BWD_PAIR(64, true, 1)
   } else if (fn == 64) {
@@ -997,6 +1000,7 @@ int tc_rowmlp_bwd(const nlam_rowmlp_bwd& bd, cudaStream_t st) {
   }
 #undef NLAM_BWD_PAIR
   if (rc) return rc;
+  if (!(mask & 4)) return 0;
   return launch_reduce_params(g.partial, ws.w_slots, d.n_chunks, g.p_total, bd.d_params,
                               bd.params_accumulate, g.vec_partial, ws.d_slots, g.vec_len, p.lay, st);
 }

@@ -81,6 +81,7 @@ class RowMlpBwd(ctypes.Structure):
         ("params_accumulate", ctypes.c_int32),
         ("workspace", c_float_p),
         ("workspace_floats", ctypes.c_size_t),
+        ("stage_mask", ctypes.c_int32),
     ]
 
 

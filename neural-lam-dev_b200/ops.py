@@ -372,18 +372,34 @@ def rowmlp_bwd_raw(srcs, W, batch, rows, residual, tiles, precision, g0, need_sr
     bd.workspace = ws.data_ptr()
     bd.workspace_floats = ws.numel()
     keep.extend([g0, g1, ws])
-    end = None
-    if _timer["t"] is not None:
-        # rows moved besides the inputs: dOut read, per-source grads written,
-        # a/dy/dh saved and re-read by the weight-gradient kernel
-        extra = W.d_out + sum(t.shape[2] for (t, _), n in zip(srcs, need_src) if n)
-        extra += 2 * (2 * W.d_hidden + W.d_out)
-        tag, nbytes, flops = _rowmlp_cost(f"rowmlp_bwd_{precision}", srcs, W, batch, rows, extra)
-        if _timer["t"].want(tag):
-            end = _timer["t"].start(tag, nbytes, 3 * flops)
-    L.check(lib.nlam_rowmlp_bwd_run(ctypes.byref(bd), _stream()), "nlam_rowmlp_bwd_run")
-    if end is not None:
-        end.record()
+    timer = _timer["t"]
+    if timer is None:
+        L.check(lib.nlam_rowmlp_bwd_run(ctypes.byref(bd), _stream()), "nlam_rowmlp_bwd_run")
+    else:
+        # time the three launches separately (stage_mask) with CUDA events.
+        # Algorithmic bytes: dgrad = distinct input rows + dOut rows + per-source
+        # gradient rows + the bf16 a/dY/dH tile images; wgrad = input rows + images
+        k = sum(t.shape[2] for t, _ in srcs)
+        src_bytes = sum(_src_bytes(t, i, batch) for t, i in srcs)
+        w_bytes = 4 * W.n_chunks * W.param_floats()
+        dsrc = sum(t.shape[2] for (t, _), n in zip(srcs, need_src) if n)
+        img = 2 * (2 * W.d_hidden + W.d_out) if precision == "bf16" else 4 * (2 * W.d_hidden + W.d_out)
+        rows_all = batch * rows
+        fl = 2 * rows_all * (k * W.d_hidden + W.d_hidden * W.d_out)
+        shape = f"rows={rows}|K={k}|dh={W.d_hidden}|dout={W.d_out}|B={batch}"
+        agg = "_agg" if aligned is not None else ""
+        stages = (
+            (1, f"rowmlp_dgrad_{precision}{agg}|{shape}",
+             src_bytes + w_bytes + rows_all * (4 * W.d_out + 4 * dsrc + img), 2 * fl if dsrc else fl + fl // 2),
+            (2, f"rowmlp_wgrad_{precision}{agg}|{shape}", src_bytes + rows_all * img, fl),
+            (4, f"reduce_params_{precision}|{shape}", 2 * w_bytes, 0),
+        )
+        for mask, tag, nbytes, flops in stages:
+            bd.stage_mask = mask
+            end = timer.start(tag, nbytes, flops) if timer.want(tag) else None
+            L.check(lib.nlam_rowmlp_bwd_run(ctypes.byref(bd), _stream()), "nlam_rowmlp_bwd_run")
+            if end is not None:
+                end.record()
     return d_srcs, d_params
 
 
