@@ -177,6 +177,47 @@ def run_reference(a):
     print(json.dumps(line), flush=True)
 
 
+def layer_edges_per_s(model, batch_size, device, iters=5):
+    """BASELINE metric (i): InteractionNet fwd+bwd edges/s per layer type, on the
+    model's own layers (MEPS g2m / m2m / m2g edge sets), CUDA-event timed."""
+    import torch
+
+    d = model.args.hidden_dim
+    out = {}
+    layers = {"g2m": (model.g2m_gnn, model.num_grid_nodes, model.num_mesh_nodes),
+              "m2m": (model.processor[0], model.num_mesh_nodes, model.num_mesh_nodes),
+              "m2g": (model.m2g_gnn, model.num_mesh_nodes, model.num_grid_nodes)}
+    for name, (net, n_send, n_rec) in layers.items():
+        M = net.edge_index.shape[1]
+        send = torch.randn(batch_size, n_send, d, device=device, requires_grad=True)
+        rec = send if name == "m2m" else torch.randn(batch_size, n_rec, d, device=device,
+                                                      requires_grad=True)
+        if net.update_edges:
+            edge = torch.randn(batch_size, M, d, device=device, requires_grad=True)
+        else:  # static edge embedding shared by the batch (stride-0 expand)
+            edge = torch.randn(M, d, device=device, requires_grad=True).unsqueeze(0).expand(
+                batch_size, -1, -1)
+
+        def run():
+            o = net(send, rec, edge)
+            o = o if isinstance(o, tuple) else (o,)
+            sum(x.sum() for x in o).backward()
+
+        for _ in range(2):
+            run()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(iters):
+            run()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / iters
+        out[name] = {"edges": M, "ms_fwd_bwd": ms, "edges_per_s": batch_size * M / (ms / 1e3)}
+    model.zero_grad(set_to_none=False)
+    return out
+
+
 # ------------------------------------------------------------------ GPU arm
 def run_ours(a):
     import torch
@@ -325,6 +366,11 @@ def run_ours(a):
            "last_loss": host_losses[-1],
            "api": "DataParallelTrainer.fit_from_host(pinned batches)"}
 
+    layers = None
+    if rank == 0 and world == 1:
+        ops.set_param_grad_sink(False)
+        layers = layer_edges_per_s(model, a.batch, device)
+
     cpu = None
     if rank == 0 and world == 1 and not a.no_cpu_baseline:
         cpu = time_cpu_oracle(a, 3, 1)
@@ -345,6 +391,7 @@ def run_ours(a):
                       "no explicit flush"}),
             "clocks": clk, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
             "cpu_baseline": cpu, "impl": "ours", "loss": float(loss.item()),
+            "interaction_net_fwd_bwd": layers,
         }
         print(json.dumps(line), flush=True)
     if world > 1:
