@@ -156,11 +156,14 @@ __device__ __forceinline__ void prefetch_l2(const void* ptr) {
 // sources need the row index first.
 __device__ __forceinline__ void prefetch_tile_rows(const float* base, const int32_t* idx, int ld,
                                                    int width, int row0, int cnt) {
+  // one thread per row (TM <= NT): the row index is loaded first, then all lines of
+  // the row are prefetched back to back (no dependent-load stall per line)
   const int lines = (width * 4 + 127) >> 7;  // 128-byte lines per row
-  for (int u = threadIdx.x; u < cnt * lines; u += NT) {
-    const int row = u / lines, l = u % lines;
+  const int row = threadIdx.x;
+  if (row < cnt) {
     const int ridx = idx ? __ldg(idx + row0 + row) : row0 + row;
-    prefetch_l2(reinterpret_cast<const char*>(base + (long long)ridx * ld) + l * 128);
+    const char* p = reinterpret_cast<const char*>(base + (long long)ridx * ld);
+    for (int l = 0; l < lines; ++l) prefetch_l2(p + l * 128);
   }
 }
 

@@ -570,6 +570,15 @@ rowmlp_tc_dgrad_kernel(const __grid_constant__ KParams p, const __grid_constant_
         const int fs = (kb * 64) / FNN, col0 = (kb * 64) % FNN;
         float* fdst = (F && FG) ? p.d_src[fs] : nullptr;
         const bool fres = F && FG && fdst && (fs == p.d.residual_src) && p.g0;
+        const int32_t* didx = fdst ? p.d_src_idx[fs] : nullptr;
+        int orow_i[8];
+        if (didx && fs != p.reduce_src) {  // scatter targets, fetched while the MMA runs
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int row = (tid >> 4) + 16 * i;
+            orow_i[i] = row < cnt ? __ldg(didx + row0 + row) : 0;
+          }
+        }
         float4 e[8];
         if (fres) {  // residual rows requested early: they arrive while the MMA runs
 #pragma unroll
@@ -607,20 +616,18 @@ rowmlp_tc_dgrad_kernel(const __grid_constant__ KParams p, const __grid_constant_
             for (int seg = seg_lo + (tid >> 4); seg < seg_hi; seg += 16) {
               const int r0 = __ldg(p.d.agg.seg_ptr + seg) - row0;
               const int r1 = __ldg(p.d.agg.seg_ptr + seg + 1) - row0;
+              float4* o4 = reinterpret_cast<float4*>(ro + (size_t)seg * FNN);
+              float4 old = make_float4(0.f, 0.f, 0.f, 0.f);
+              if (p.reduce_accumulate) old = *o4;  // in flight during the shared-memory sum
               float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
               for (int rr = r0; rr < r1; ++rr) {
                 const float4 v = *reinterpret_cast<const float4*>(stg + stg_idx(rr, tid & 15, 64));
                 acc.x += v.x, acc.y += v.y, acc.z += v.z, acc.w += v.w;
               }
-              float4* o4 = reinterpret_cast<float4*>(ro + (size_t)seg * FNN);
-              if (p.reduce_accumulate) {
-                const float4 old = *o4;
-                acc.x += old.x, acc.y += old.y, acc.z += old.z, acc.w += old.w;
-              }
+              acc.x += old.x, acc.y += old.y, acc.z += old.z, acc.w += old.w;
               *o4 = acc;
             }
           } else if (fdst) {
-            const int32_t* didx = p.d_src_idx[fs];
             float* o = fdst + col0 + (tid & 15) * 4;
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
@@ -628,8 +635,7 @@ rowmlp_tc_dgrad_kernel(const __grid_constant__ KParams p, const __grid_constant_
               if (row < cnt) {
                 float4 v = *reinterpret_cast<const float4*>(stg + stg_idx(row, tid & 15, 64));
                 if (fres) v.x += e[i].x, v.y += e[i].y, v.z += e[i].z, v.w += e[i].w;
-                const size_t orow = didx ? (size_t)b * p.d.rows + __ldg(didx + row0 + row)
-                                         : grow0 + row;
+                const size_t orow = didx ? (size_t)b * p.d.rows + orow_i[i] : grow0 + row;
                 *reinterpret_cast<float4*>(o + orow * FNN) = v;
               }
             }
