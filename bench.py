@@ -39,7 +39,7 @@ def parse():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--precision", default=os.environ.get("NLAM_PRECISION", "fp32"),
+    ap.add_argument("--precision", default=os.environ.get("NLAM_PRECISION", "bf16"),
                     choices=["fp32", "bf16"])
     ap.add_argument("--batch", type=int, default=4, help="samples per GPU per step")
     ap.add_argument("--hidden-dim", type=int, default=64)

@@ -135,6 +135,14 @@ def mse(pred, target, pred_std, mask=None):
     return wmse(pred, target, torch.ones_like(pred_std), mask)
 
 
+def nll(pred, target, pred_std, mask=None):
+    """metrics.py:176-201: Gaussian negative log-likelihood."""
+    v = -torch.distributions.Normal(pred, pred_std).log_prob(target)
+    if mask is not None:
+        v = v[..., mask, :]
+    return v.mean(dim=-2).sum(dim=-1)
+
+
 class _BufList(nn.Module):
     def __init__(self, tensors):
         super().__init__()
@@ -210,7 +218,7 @@ class ARModel(nn.Module):
         self.num_grid_nodes, d_static = self.grid_static_features.shape
         self.grid_dim = (2 * self.grid_output_dim + d_static + d_forc * (
             args.num_past_forcing_steps + args.num_future_forcing_steps + 1))
-        self.loss = {"wmse": wmse, "mse": mse}[args.loss.lower()]
+        self.loss = {"wmse": wmse, "mse": mse, "nll": nll}[args.loss.lower()]
         bm = torch.tensor(datastore.boundary_mask.values, dtype=f32).unsqueeze(1)
         self.register_buffer("boundary_mask", bm, persistent=False)
         self.register_buffer("interior_mask", 1.0 - bm, persistent=False)
@@ -221,13 +229,16 @@ class ARModel(nn.Module):
 
     def unroll_prediction(self, init_states, forcing_features, true_states):
         prev_prev, prev = init_states[:, 0], init_states[:, 1]
-        preds = []
+        preds, stds = [], []
         for i in range(forcing_features.shape[1]):
-            pred, _ = self.predict_step(prev, prev_prev, forcing_features[:, i])
+            pred, std = self.predict_step(prev, prev_prev, forcing_features[:, i])
             new = self.boundary_mask * true_states[:, i] + self.interior_mask * pred
             preds.append(new)
+            if self.output_std:
+                stds.append(std)
             prev_prev, prev = prev, new
-        return torch.stack(preds, dim=1), self.per_var_std
+        pred_std = torch.stack(stds, dim=1) if self.output_std else self.per_var_std
+        return torch.stack(preds, dim=1), pred_std
 
     def training_step(self, batch):
         init_states, target, forcing, _ = batch
