@@ -17,23 +17,13 @@
 //
 // Reference semantics: utils.make_mlp (utils.py:191-214), InteractionNet.message /
 // aggr_mlp (interaction_net.py:106,117-121), SplitMLPs (:134-163).
+#include <stdlib.h>
+
 #include "rowmlp_tc.cuh"
 
 namespace nlam {
 namespace tc {
 
-struct Geo {
-  int n1, n2;          // padded d_hidden / d_out (16, 32, 64 or 128)
-  int k1;              // K of GEMM 1 padded to 16
-  int k2;              // K of GEMM 2 (= d_hidden padded to 16)
-  int kb1, kb2;        // 64-wide K blocks
-  int tmem_cols;       // power of two >= 32
-  int stg_ld;          // floats per staging row (n2 + 4)
-  uint32_t off_w1, off_w2, off_par, off_lnx, off_bar;  // byte offsets
-  uint32_t smem_bytes;
-  int total_tiles;     // batch * tiles
-  int tiles_per_batch;
-};
 
 template <int FN, bool FG>
 __global__ void __launch_bounds__(NT, 2)
@@ -343,6 +333,13 @@ int tc_rowmlp_fwd(const nlam_rowmlp& d, cudaStream_t st) {
   NLAM_CHECK(!d.agg.out || d.d_out % 4 == 0, "rowmlp: agg needs d_out %% 4 == 0");
   tc::Geo g{};
   if (tc::make_geo(p, g)) return 1;
+  {  // four tiles in flight per SM with shared weights, when there is enough work
+    static const int mc_env = getenv("NLAM_FWD_MC") ? atoi(getenv("NLAM_FWD_MC")) : -1;
+    // measured on MEPS shapes: +16 % on the 3-source edge MLPs (gather-latency bound),
+    // -12 % on the 2-source node MLP, so only the former take this path by default
+    const bool want = mc_env < 0 ? (g.total_tiles > 296 && d.n_src == 3) : mc_env != 0;
+    if (want && tc_fwd_mc_supported(p)) return tc_rowmlp_fwd_mc(p, g, st);
+  }
   int per_sm = g.smem_bytes <= 113 * 1024 ? 2 : 1;
   if (g.tmem_cols * per_sm > 512) per_sm = 1;
   int grid = 148 * per_sm;

@@ -10,6 +10,19 @@ constexpr int TM = 128;  // rows per tile == UMMA M
 constexpr int NT = 256;
 
 
+struct Geo {
+  int n1, n2;          // padded d_hidden / d_out (16, 32, 64 or 128)
+  int k1;              // K of GEMM 1 padded to 16
+  int k2;              // K of GEMM 2 (= d_hidden padded to 16)
+  int kb1, kb2;        // 64-wide K blocks
+  int tmem_cols;       // power of two >= 32
+  int stg_ld;          // floats per staging row (n2 + 4)
+  uint32_t off_w1, off_w2, off_par, off_lnx, off_bar;  // byte offsets
+  uint32_t smem_bytes;
+  int total_tiles;     // batch * tiles
+  int tiles_per_batch;
+};
+
 inline int pad_n(int n) { return n <= 16 ? 16 : n <= 32 ? 32 : n <= 64 ? 64 : n <= 128 ? 128 : -1; }
 
 __device__ __forceinline__ float silu_fast(float x) { return __fdividef(x, 1.0f + __expf(-x)); }
@@ -211,4 +224,9 @@ __device__ __forceinline__ void stage_params(const nlam_rowmlp& d, int chunk, in
 }
 
 }  // namespace tc
+
+// multi-context forward (rowmlp_tc_mc.cu)
+bool tc_fwd_mc_supported(const KParams& p);
+int tc_rowmlp_fwd_mc(const KParams& p, const tc::Geo& g, cudaStream_t st);
+
 }  // namespace nlam
