@@ -73,7 +73,7 @@ rowmlp_tc_fwd_kernel(const __grid_constant__ KParams p, const __grid_constant__ 
   const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
 
   for (int t = blockIdx.x; t < g.total_tiles; t += gridDim.x) {
-    const int b = t / g.tiles_per_batch, tile = t % g.tiles_per_batch;
+    const int b = t % p.d.batch, tile = t / p.d.batch;  // batch innermost: shared rows hit L2
     int row0, cnt, chunk;
     tile_range<TM>(p.d, tile, row0, cnt, chunk);
 
@@ -93,8 +93,8 @@ rowmlp_tc_fwd_kernel(const __grid_constant__ KParams p, const __grid_constant__ 
       const int tn = t + gridDim.x;
       if (tn < g.total_tiles) {
         int r0n, cn, chn;
-        tile_range<TM>(p.d, tn % g.tiles_per_batch, r0n, cn, chn);
-        prefetch_sources(p, tn / g.tiles_per_batch, r0n, cn);
+        tile_range<TM>(p.d, tn / p.d.batch, r0n, cn, chn);
+        prefetch_sources(p, tn % p.d.batch, r0n, cn);
       }
     }
     fence_async_smem();

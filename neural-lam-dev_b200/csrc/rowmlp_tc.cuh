@@ -188,6 +188,79 @@ __device__ __forceinline__ void prefetch_sources(const KParams& p, int b, int ro
   }
 }
 
+// ---- pipelined fast gather (all sources FN wide) -------------------------------
+// Each warp of the NTH-thread group owns RPW = TM / (NTH/32) consecutive tile rows.
+// Lane l holds the source-row indices of row (l % RPW) of its warp -- loaded one
+// tile ahead by load_row_idx, so the index latency is off the critical path --
+// and hands them to the lanes that gather that row with a shuffle.  The 2 * n_src
+// half-source units are software-pipelined: the 128-bit loads of unit u+1 are in
+// flight while unit u is converted to bf16 and stored in the UMMA A layout.
+template <int NTH>
+__device__ __forceinline__ void load_row_idx(const KParams& p, int row0, int cnt, int gtid,
+                                             int (&ridx)[NLAM_MAX_SRC]) {
+  constexpr int RPW = TM / (NTH / 32);
+  const int row = (gtid >> 5) * RPW + ((gtid & 31) % RPW);
+#pragma unroll
+  for (int s = 0; s < NLAM_MAX_SRC; ++s) {
+    ridx[s] = -1;
+    if (s < p.d.n_src && row < cnt) {
+      const int32_t* idx = p.d.src[s].idx;
+      ridx[s] = idx ? __ldg(idx + row0 + row) : row0 + row;
+    }
+  }
+}
+
+template <int FN, int NTH>
+__device__ __forceinline__ void gather_rows_pipe(const KParams& p, int b,
+                                                 const int (&ridx)[NLAM_MAX_SRC], uint8_t* sA,
+                                                 int gtid) {
+  constexpr int LPR = FN / 8;                // lanes per row (16-byte bf16 chunks)
+  constexpr int RPPW = 32 / LPR;             // rows per warp pass
+  constexpr int RPW = TM / (NTH / 32);       // rows per warp
+  constexpr int NH = RPW / RPPW / 2;         // rows per half-source unit and thread
+  static_assert(NH >= 1, "bad gather geometry");
+  const int lane = gtid & 31, c = lane % LPR, rl = lane / LPR;
+  const int rbase = (gtid >> 5) * RPW;
+  const uint32_t a_blk = TM * 128u;
+  float4 x[2][NH], y[2][NH];
+  const int n_units = 2 * p.d.n_src;
+
+  auto issue = [&](int s, int hsel, int buf) {
+    const nlam_src& src = p.d.src[s];
+    const float* base = src.ptr + (long long)b * src.batch_stride + c * 8;
+    const int my = s == 0 ? ridx[0] : s == 1 ? ridx[1] : ridx[2];
+#pragma unroll
+    for (int j = 0; j < NH; ++j) {
+      const int rw = rl + RPPW * (hsel * NH + j);  // row inside this warp's block
+      const int ri = __shfl_sync(0xffffffffu, my, rw);
+      x[buf][j] = make_float4(0.f, 0.f, 0.f, 0.f);
+      y[buf][j] = x[buf][j];
+      if (ri >= 0) {
+        const float4* q = reinterpret_cast<const float4*>(base + (long long)ri * src.ld);
+        x[buf][j] = __ldg(q);
+        y[buf][j] = __ldg(q + 1);
+      }
+    }
+  };
+  auto drain = [&](int s, int hsel, int buf) {
+#pragma unroll
+    for (int j = 0; j < NH; ++j) {
+      const int row = rbase + rl + RPPW * (hsel * NH + j);
+      uint4 pk = make_uint4(pack_bf16(x[buf][j].x, x[buf][j].y), pack_bf16(x[buf][j].z, x[buf][j].w),
+                            pack_bf16(y[buf][j].x, y[buf][j].y), pack_bf16(y[buf][j].z, y[buf][j].w));
+      *reinterpret_cast<uint4*>(sA + sw128_off(row, s * FN + c * 8, a_blk)) = pk;
+    }
+  };
+  issue(0, 0, 0);
+#pragma unroll
+  for (int u = 0; u < 2 * NLAM_MAX_SRC; ++u) {
+    if (u < n_units) {
+      if (u + 1 < n_units) issue((u + 1) >> 1, (u + 1) & 1, (u + 1) & 1);
+      drain(u >> 1, u & 1, u & 1);
+    }
+  }
+}
+
 // square fast path: d_hidden == d_out == FN (compile-time epilogues) ...
 inline int fast_n(const KParams& p) {
   const nlam_rowmlp& d = p.d;

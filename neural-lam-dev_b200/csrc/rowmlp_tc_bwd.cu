@@ -212,7 +212,7 @@ rowmlp_tc_dgrad_kernel(const __grid_constant__ KParams p, const __grid_constant_
   };
 
   for (int t = blockIdx.x; t < g.total_tiles; t += gridDim.x) {
-    const int b = t / g.tiles_per_batch, tile = t % g.tiles_per_batch;
+    const int b = t % p.d.batch, tile = t / p.d.batch;  // batch innermost: shared rows hit L2
     int row0, cnt, chunk;
     tile_range<TM>(p.d, tile, row0, cnt, chunk);
     const size_t grow0 = (size_t)b * p.d.rows + row0;
@@ -335,8 +335,8 @@ rowmlp_tc_dgrad_kernel(const __grid_constant__ KParams p, const __grid_constant_
       const int tn = t + gridDim.x;
       if (tn < g.total_tiles) {
         int r0n, cn, chn;
-        const int bn = tn / g.tiles_per_batch;
-        tile_range<TM>(p.d, tn % g.tiles_per_batch, r0n, cn, chn);
+        const int bn = tn % p.d.batch;
+        tile_range<TM>(p.d, tn / p.d.batch, r0n, cn, chn);
         prefetch_sources(p, bn, r0n, cn);
         if (p.g0)
           prefetch_tile_rows(p.g0 + (size_t)bn * p.d.rows * dout, p.g0_idx, dout, dout, r0n, cn);
@@ -766,7 +766,7 @@ rowmlp_tc_wgrad_kernel(const __grid_constant__ KParams p, const __grid_constant_
   };
 
   for (int t = blockIdx.x; t < g.total_tiles; t += gridDim.x) {
-    const int b = t / g.tiles_per_batch, tile = t % g.tiles_per_batch;
+    const int b = t % p.d.batch, tile = t / p.d.batch;  // batch innermost: shared rows hit L2
     int row0, cnt, chunk;
     tile_range<TM>(p.d, tile, row0, cnt, chunk);
     if (chunk != cur_chunk) {
@@ -785,8 +785,8 @@ rowmlp_tc_wgrad_kernel(const __grid_constant__ KParams p, const __grid_constant_
       const int tn = t + gridDim.x;
       if (tn < g.total_tiles) {
         int r0n, cn, chn;
-        tile_range<TM>(p.d, tn % g.tiles_per_batch, r0n, cn, chn);
-        prefetch_sources(p, tn / g.tiles_per_batch, r0n, cn);
+        tile_range<TM>(p.d, tn / p.d.batch, r0n, cn, chn);
+        prefetch_sources(p, tn % p.d.batch, r0n, cn);
         const int li = (int)(kb2 * a_blk) >> 7, lo = (int)(kbo * a_blk) >> 7;
         for (int u = tid; u < li; u += NT) {
           prefetch_l2(g.a_img + (size_t)tn * kb2 * a_blk + (size_t)u * 128);

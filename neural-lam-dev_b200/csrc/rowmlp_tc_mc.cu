@@ -140,25 +140,38 @@ rowmlp_tc_fwd_mc_kernel(const __grid_constant__ KParams p, const __grid_constant
   const int k1steps = p.d.n_src * FN / 16;
   const int stride = gridDim.x * MC_WG;
 
+  // source-row indices of this thread's row, loaded one tile ahead
+  int nidx[NLAM_MAX_SRC] = {-1, -1, -1};
+  {
+    const int t0 = blockIdx.x * MC_WG + wg;
+    if (t0 < g.total_tiles) {
+      int r0, c0, ch0;
+      tile_range<TM>(p.d, t0 / p.d.batch, r0, c0, ch0);
+      load_row_idx<128>(p, r0, c0, wtid, nidx);
+    }
+  }
   for (int t = blockIdx.x * MC_WG + wg; t < g.total_tiles; t += stride) {
-    const int b = t / g.tiles_per_batch, tile = t % g.tiles_per_batch;
+    const int b = t % p.d.batch, tile = t / p.d.batch;  // batch innermost: shared rows hit L2
     int row0, cnt, chunk;
     tile_range<TM>(p.d, tile, row0, cnt, chunk);
 
-    // ---------------- gather (bf16 A operand) + L2 prefetch of this pipeline's next tile
-    gather_rows_wg(p, b, row0, cnt, sR, wtid);
+    // ---------------- gather (bf16 A operand); indices of the next tile + L2 prefetch
+    int cidx[NLAM_MAX_SRC] = {nidx[0], nidx[1], nidx[2]};
+    gather_rows_pipe<FN, 128>(p, b, cidx, sR, wtid);
     {
       const int tn = t + stride;
       if (tn < g.total_tiles) {
         int r0n, cn, chn;
-        tile_range<TM>(p.d, tn % g.tiles_per_batch, r0n, cn, chn);
-        const int bn = tn / g.tiles_per_batch;
-        if (wtid < cn) {
-          for (int s = 0; s < p.d.n_src; ++s) {
+        tile_range<TM>(p.d, tn / p.d.batch, r0n, cn, chn);
+        const int bn = tn % p.d.batch;
+        load_row_idx<128>(p, r0n, cn, wtid, nidx);
+#pragma unroll
+        for (int s = 0; s < NLAM_MAX_SRC; ++s) {
+          const int ri = s == 0 ? nidx[0] : s == 1 ? nidx[1] : nidx[2];
+          if (s < p.d.n_src && ri >= 0) {
             const nlam_src& src = p.d.src[s];
-            const int ridx = src.idx ? __ldg(src.idx + r0n + wtid) : r0n + wtid;
             const char* q = reinterpret_cast<const char*>(
-                src.ptr + (long long)bn * src.batch_stride + (long long)ridx * src.ld);
+                src.ptr + (long long)bn * src.batch_stride + (long long)ri * src.ld);
             prefetch_l2(q);
             prefetch_l2(q + 128);
           }
