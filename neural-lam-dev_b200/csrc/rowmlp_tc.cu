@@ -72,6 +72,15 @@ rowmlp_tc_fwd_kernel(const __grid_constant__ KParams p, const __grid_constant__ 
   const bool split2 = n2 >= 32;
   const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
 
+  // pipelined gather (64-wide sources): row indices are fetched one tile ahead
+  constexpr bool PIPE = false;  // no gain measured in the two-CTA forward kernel
+  int nidx[NLAM_MAX_SRC] = {-1, -1, -1};
+  if (PIPE && (int)blockIdx.x < g.total_tiles) {
+    int r0, c0, ch0;
+    tile_range<TM>(p.d, blockIdx.x / p.d.batch, r0, c0, ch0);
+    load_row_idx<NT>(p, r0, c0, tid, nidx);
+  }
+
   for (int t = blockIdx.x; t < g.total_tiles; t += gridDim.x) {
     const int b = t % p.d.batch, tile = t / p.d.batch;  // batch innermost: shared rows hit L2
     int row0, cnt, chunk;
@@ -85,16 +94,25 @@ rowmlp_tc_fwd_kernel(const __grid_constant__ KParams p, const __grid_constant__ 
     }
 
     // ---------------- gather: fp32 rows -> bf16 A operand
-    if (F && FG)
+    if (PIPE) {
+      const int cidx[NLAM_MAX_SRC] = {nidx[0], nidx[1], nidx[2]};
+      gather_rows_pipe<64, NT>(p, b, cidx, sA, tid);
+    } else if (F && FG) {
       gather_rows_fast<(F ? FN : 64)>(p, b, row0, cnt, 0, p.d.n_src, sA);
-    else
+    } else {
       gather_rows(p, b, row0, cnt, 0, g.k1, sA);
-    {  // L2 prefetch of the next tile's input rows
+    }
+    {  // next tile: row indices (pipelined gather) and L2 prefetch of its input rows
       const int tn = t + gridDim.x;
       if (tn < g.total_tiles) {
         int r0n, cn, chn;
         tile_range<TM>(p.d, tn / p.d.batch, r0n, cn, chn);
-        prefetch_sources(p, tn % p.d.batch, r0n, cn);
+        if (PIPE) {
+          load_row_idx<NT>(p, r0n, cn, tid, nidx);
+          prefetch_rows_of(p, tn % p.d.batch, nidx, (tid & 31) < 16);
+        } else {
+          prefetch_sources(p, tn % p.d.batch, r0n, cn);
+        }
       }
     }
     fence_async_smem();

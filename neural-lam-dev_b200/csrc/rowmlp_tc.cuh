@@ -261,6 +261,22 @@ __device__ __forceinline__ void gather_rows_pipe(const KParams& p, int b,
   }
 }
 
+// L2 prefetch of the (64-float) source rows whose indices this thread holds
+__device__ __forceinline__ void prefetch_rows_of(const KParams& p, int b,
+                                                 const int (&ridx)[NLAM_MAX_SRC], bool active) {
+#pragma unroll
+  for (int s = 0; s < NLAM_MAX_SRC; ++s) {
+    const int ri = s == 0 ? ridx[0] : s == 1 ? ridx[1] : ridx[2];
+    if (active && s < p.d.n_src && ri >= 0) {
+      const nlam_src& src = p.d.src[s];
+      const char* q = reinterpret_cast<const char*>(src.ptr + (long long)b * src.batch_stride +
+                                                    (long long)ri * src.ld);
+      prefetch_l2(q);
+      prefetch_l2(q + 128);
+    }
+  }
+}
+
 // square fast path: d_hidden == d_out == FN (compile-time epilogues) ...
 inline int fast_n(const KParams& p) {
   const nlam_rowmlp& d = p.d;

@@ -211,6 +211,16 @@ rowmlp_tc_dgrad_kernel(const __grid_constant__ KParams p, const __grid_constant_
     for (int i = 0; i < MAXCH; ++i) acc_db1[i] = acc_db2[i] = acc_dg[i] = acc_dbt[i] = 0.f;
   };
 
+  // pipelined gather (64-wide sources): row indices are fetched one tile ahead
+  // (off in this kernel: the extra live registers spill and cost more than the gather gains)
+  constexpr bool PIPE = false;
+  int nidx[NLAM_MAX_SRC] = {-1, -1, -1};
+  if (PIPE && (int)blockIdx.x < g.total_tiles) {
+    int r0, c0, ch0;
+    tile_range<TM>(p.d, blockIdx.x / p.d.batch, r0, c0, ch0);
+    load_row_idx<NT>(p, r0, c0, tid, nidx);
+  }
+
   for (int t = blockIdx.x; t < g.total_tiles; t += gridDim.x) {
     const int b = t % p.d.batch, tile = t / p.d.batch;  // batch innermost: shared rows hit L2
     int row0, cnt, chunk;
@@ -295,11 +305,15 @@ rowmlp_tc_dgrad_kernel(const __grid_constant__ KParams p, const __grid_constant_
     for (int kb0 = 0; kb0 < g.kb1; kb0 += g.rb) {
       const int kbe = min(g.kb1, kb0 + g.rb);
       const int k_begin = kb0 * 64, k_end = min(g.k1, kbe * 64);
-      if (F && FG)
+      if (PIPE) {  // one round covers all (<= 3) sources
+        const int cidx[NLAM_MAX_SRC] = {nidx[0], nidx[1], nidx[2]};
+        gather_rows_pipe<64, NT>(p, b, cidx, sA, tid);
+      } else if (F && FG) {
         gather_rows_fast<(F ? FN : 64)>(p, b, row0, cnt, k_begin / (F ? FN : 64),
                                         k_end / (F ? FN : 64), sA);
-      else
+      } else {
         gather_rows(p, b, row0, cnt, k_begin, k_end, sA);
+      }
       fence_async_smem();
       __syncthreads();
       if (tid == 0) {
@@ -337,7 +351,12 @@ rowmlp_tc_dgrad_kernel(const __grid_constant__ KParams p, const __grid_constant_
         int r0n, cn, chn;
         const int bn = tn % p.d.batch;
         tile_range<TM>(p.d, tn / p.d.batch, r0n, cn, chn);
-        prefetch_sources(p, bn, r0n, cn);
+        if (PIPE) {
+          load_row_idx<NT>(p, r0n, cn, tid, nidx);
+          prefetch_rows_of(p, bn, nidx, (tid & 31) < 16);
+        } else {
+          prefetch_sources(p, bn, r0n, cn);
+        }
         if (p.g0)
           prefetch_tile_rows(p.g0 + (size_t)bn * p.d.rows * dout, p.g0_idx, dout, dout, r0n, cn);
         if (p.g1)
@@ -765,6 +784,14 @@ rowmlp_tc_wgrad_kernel(const __grid_constant__ KParams p, const __grid_constant_
     __syncthreads();
   };
 
+  constexpr bool PIPE = F && FG && FN == 64;
+  int nidx[NLAM_MAX_SRC] = {-1, -1, -1};
+  if (PIPE && (int)blockIdx.x < g.total_tiles) {
+    int r0, c0, ch0;
+    tile_range<TM>(p.d, blockIdx.x / p.d.batch, r0, c0, ch0);
+    load_row_idx<NT>(p, r0, c0, tid, nidx);
+  }
+
   for (int t = blockIdx.x; t < g.total_tiles; t += gridDim.x) {
     const int b = t % p.d.batch, tile = t / p.d.batch;  // batch innermost: shared rows hit L2
     int row0, cnt, chunk;
@@ -774,10 +801,14 @@ rowmlp_tc_wgrad_kernel(const __grid_constant__ KParams p, const __grid_constant_
       cur_chunk = chunk;
       first = true;
     }
-    if (F && FG)
+    if (PIPE) {
+      const int cidx[NLAM_MAX_SRC] = {nidx[0], nidx[1], nidx[2]};
+      gather_rows_pipe<64, NT>(p, b, cidx, sZ, tid);
+    } else if (F && FG) {
       gather_rows_fast<(F ? FN : 64)>(p, b, row0, cnt, 0, p.d.n_src, sZ);
-    else
+    } else {
       gather_rows(p, b, row0, cnt, 0, g.k1, sZ);
+    }
     copy_tile_in(g.a_img + (size_t)t * kb2 * a_blk, sAi, kb2 * a_blk);
     copy_tile_in(g.dy_img + (size_t)t * kbo * a_blk, sDY, kbo * a_blk);
     copy_tile_in(g.dh_img + (size_t)t * kb2 * a_blk, sDH, kb2 * a_blk);
@@ -786,7 +817,12 @@ rowmlp_tc_wgrad_kernel(const __grid_constant__ KParams p, const __grid_constant_
       if (tn < g.total_tiles) {
         int r0n, cn, chn;
         tile_range<TM>(p.d, tn / p.d.batch, r0n, cn, chn);
-        prefetch_sources(p, tn % p.d.batch, r0n, cn);
+        if (PIPE) {
+          load_row_idx<NT>(p, r0n, cn, tid, nidx);
+          prefetch_rows_of(p, tn % p.d.batch, nidx, (tid & 31) < 16);
+        } else {
+          prefetch_sources(p, tn % p.d.batch, r0n, cn);
+        }
         const int li = (int)(kb2 * a_blk) >> 7, lo = (int)(kbo * a_blk) >> 7;
         for (int u = tid; u < li; u += NT) {
           prefetch_l2(g.a_img + (size_t)tn * kb2 * a_blk + (size_t)u * 128);
