@@ -31,44 +31,6 @@ __device__ __forceinline__ void wg_sync(int wg) {
   asm volatile("bar.sync %0, 128;" ::"r"(wg + 1) : "memory");
 }
 
-// all sources 64 floats wide; 128 threads: thread (rl, c) = chunk c of rows rl + 16 i
-__device__ __forceinline__ void gather_rows_wg(const KParams& p, int b, int row0, int cnt,
-                                               uint8_t* sA, int wtid) {
-  constexpr int NP = 8;
-  const int c = wtid & 7, rl = wtid >> 3;
-  const uint32_t a_blk = TM * 128u;
-  for (int s = 0; s < p.d.n_src; ++s) {
-    const nlam_src& src = p.d.src[s];
-    const float* base = src.ptr + (long long)b * src.batch_stride + c * 8;
-    const int32_t* idx = src.idx;
-    const int ld = src.ld;
-    int ridx[NP];
-#pragma unroll
-    for (int i = 0; i < NP; ++i) {
-      const int row = i * 16 + rl;
-      ridx[i] = row < cnt ? (idx ? __ldg(idx + row0 + row) : row0 + row) : -1;
-    }
-    float4 x[NP], y[NP];
-#pragma unroll
-    for (int i = 0; i < NP; ++i) {
-      x[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-      y[i] = x[i];
-      if (ridx[i] >= 0) {
-        const float4* q = reinterpret_cast<const float4*>(base + (long long)ridx[i] * ld);
-        x[i] = __ldg(q);
-        y[i] = __ldg(q + 1);
-      }
-    }
-#pragma unroll
-    for (int i = 0; i < NP; ++i) {
-      const int row = i * 16 + rl;
-      uint4 pk = make_uint4(pack_bf16(x[i].x, x[i].y), pack_bf16(x[i].z, x[i].w),
-                            pack_bf16(y[i].x, y[i].y), pack_bf16(y[i].z, y[i].w));
-      *reinterpret_cast<uint4*>(sA + sw128_off(row, s * MC_FN + c * 8, a_blk)) = pk;
-    }
-  }
-}
-
 __global__ void __launch_bounds__(MC_NT, 1)
 rowmlp_tc_fwd_mc_kernel(const __grid_constant__ KParams p, const __grid_constant__ Geo g) {
   extern __shared__ __align__(1024) uint8_t sm[];
