@@ -180,6 +180,11 @@ typedef struct nlam_state_step_bwd {
 
 const char* nlam_last_error(void);
 int nlam_version(void);
+/* Kernel-selection knobs (process-wide; -1 = automatic, 0 = off, 1 = force when
+ * eligible): "fwd_mc" = 4-pipeline shared-weight forward kernel, "dgrad_mc" =
+ * 3-pipeline shared-weight input-gradient kernel.  Returns 0, or 1 for an
+ * unknown name.  Environment NLAM_FWD_MC / NLAM_DGRAD_MC give the initial values. */
+int nlam_set_option(const char* name, int value);
 /* Number of kernels this library has launched in this process (monotonic;
  * bench.py reports the delta over its timed region as "gpu_launches"). */
 int64_t nlam_launch_count(void);

@@ -1,5 +1,6 @@
 // C ABI entry points (include/nlam_b200.h) -> kernel launchers.
 #include <stdarg.h>
+#include <stdlib.h>
 
 #include <atomic>
 #include <string.h>
@@ -15,10 +16,25 @@ void set_error(const char* fmt, ...) {
   va_end(ap);
 }
 static std::atomic<long long> g_launches{0};
+static int env_or(const char* name, int dflt) {
+  const char* v = getenv(name);
+  return v ? atoi(v) : dflt;
+}
+static std::atomic<int> g_fwd_mc{env_or("NLAM_FWD_MC", -1)};
+static std::atomic<int> g_dgrad_mc{env_or("NLAM_DGRAD_MC", 0)};
+int option_fwd_mc() { return g_fwd_mc.load(); }
+int option_dgrad_mc() { return g_dgrad_mc.load(); }
 void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 }  // namespace nlam
 
 using namespace nlam;
+
+extern "C" int nlam_set_option(const char* name, int value) {
+  if (name && !strcmp(name, "fwd_mc")) return nlam::g_fwd_mc.store(value), 0;
+  if (name && !strcmp(name, "dgrad_mc")) return nlam::g_dgrad_mc.store(value), 0;
+  nlam::set_error("nlam_set_option: unknown option");
+  return 1;
+}
 
 extern "C" int64_t nlam_launch_count(void) { return (int64_t)nlam::g_launches.load(); }
 

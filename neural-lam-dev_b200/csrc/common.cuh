@@ -10,6 +10,8 @@ namespace nlam {
 
 void set_error(const char* fmt, ...);
 void count_launch(int n = 1);
+int option_fwd_mc();    // -1 auto, 0 off, 1 force
+int option_dgrad_mc();
 
 #define NLAM_CHECK(cond, ...)        \
   do {                               \

@@ -352,7 +352,7 @@ int tc_rowmlp_fwd(const nlam_rowmlp& d, cudaStream_t st) {
   tc::Geo g{};
   if (tc::make_geo(p, g)) return 1;
   {  // four tiles in flight per SM with shared weights, when there is enough work
-    static const int mc_env = getenv("NLAM_FWD_MC") ? atoi(getenv("NLAM_FWD_MC")) : -1;
+    const int mc_env = option_fwd_mc();
     // measured on MEPS shapes: +16 % on the 3-source edge MLPs (gather-latency bound),
     // -12 % on the 2-source node MLP, so only the former take this path by default
     const bool want = mc_env < 0 ? (g.total_tiles > 296 && d.n_src == 3) : mc_env != 0;

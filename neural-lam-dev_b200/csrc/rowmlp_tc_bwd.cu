@@ -17,7 +17,9 @@
 //
 // Reference: autograd of utils.make_mlp / InteractionNet.message / aggr_mlp
 // (utils.py:191-214, interaction_net.py:106,117-121).
-#include "rowmlp_tc.cuh"
+#include <stdlib.h>
+
+#include "rowmlp_tc_bwd.cuh"
 
 namespace nlam {
 
@@ -27,96 +29,6 @@ int launch_reduce_params(const float* partial, int splits, int n_chunks, int p_t
                          int vec_len, ParamLayout lay, cudaStream_t st);
 
 namespace tc {
-
-struct BGeo {
-  int n1, n2, nmax;
-  int k1, k2, ko;        // K of GEMM1 (pad 16), GEMM2 (= pad16(dh)), GEMM3 (= pad16(dout))
-  int kb1, kb2, kbo;     // 64-wide blocks of z, of the hidden tile, of the dY tile
-  int rb;                // z blocks gathered per round
-  int tmem_cols, cY, cZ;
-  uint32_t off_t, off_w1, off_w2, off_par, off_lnx, off_bar, smem_bytes;
-  int total_tiles, tiles_per_batch;
-  int need_dz;           // any source gradient requested
-  // scratch
-  uint8_t* a_img;
-  uint8_t* dy_img;
-  uint8_t* dh_img;
-  float* partial;        // wgrad: [w_slots][n_chunks][p_total] (matrix entries)
-  float* vec_partial;    // dgrad: [d_slots][n_chunks][vec_len] = [db1 | db2 | dLNg | dLNb]
-  int p_total, vec_len;
-  // wgrad
-  int w_tmem_cols, w_mchunks;
-  uint32_t w_off_a, w_off_dy, w_off_dh, w_off_bar, w_smem_bytes;
-};
-
-// swizzled fp32 staging tile [128][n] (n multiple of 16): 16-byte chunk c4 of row r
-__device__ __forceinline__ int stg_idx(int r, int c4, int n) {
-  const int nc = n >> 2;
-  const int m = (nc < 8 ? nc : 8) - 1;
-  return r * n + ((c4 ^ (r & m)) << 2);
-}
-
-// Column sums over the 32 lanes of a warp of a 16-column chunk held one row per
-// lane; lane l ends up with the total of column (l & 15).  16 shuffles.
-__device__ __forceinline__ float warp_colsum16(const float (&v)[16], int lane) {
-  float w8[8], w4[4], w2[2];
-  const bool b3 = lane & 8, b2 = lane & 4, b1 = lane & 2, b0 = lane & 1;
-#pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    const float send = b3 ? v[i] : v[i + 8];
-    const float recv = __shfl_xor_sync(0xffffffffu, send, 8);
-    w8[i] = (b3 ? v[i + 8] : v[i]) + recv;
-  }
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const float send = b2 ? w8[i] : w8[i + 4];
-    const float recv = __shfl_xor_sync(0xffffffffu, send, 4);
-    w4[i] = (b2 ? w8[i + 4] : w8[i]) + recv;
-  }
-#pragma unroll
-  for (int i = 0; i < 2; ++i) {
-    const float send = b1 ? w4[i] : w4[i + 2];
-    const float recv = __shfl_xor_sync(0xffffffffu, send, 2);
-    w2[i] = (b1 ? w4[i + 2] : w4[i]) + recv;
-  }
-  const float send = b0 ? w2[0] : w2[1];
-  const float recv = __shfl_xor_sync(0xffffffffu, send, 1);
-  float w1 = (b0 ? w2[1] : w2[0]) + recv;
-  w1 += __shfl_xor_sync(0xffffffffu, w1, 16);
-  return w1;
-}
-
-// MN-major SW128 descriptor: tile stored [K rows][64 MN elements] (128-byte
-// rows, same physical layout as the K-major tiles), 8-row K groups 1024 B apart
-// (SBO), 64-element MN blocks `lbo_bytes` apart (LBO).
-__device__ __forceinline__ uint64_t make_desc_mn_sw128(uint32_t smem_addr, uint32_t lbo_bytes) {
-  return (uint64_t)((smem_addr >> 4) & 0x3FFF) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16) |
-         (64ull << 32) | (1ull << 46) | (2ull << 61);
-}
-
-__device__ __forceinline__ void copy_tile_out(const uint8_t* s, uint8_t* g, int bytes) {
-  const uint4* src = reinterpret_cast<const uint4*>(s);
-  uint4* dst = reinterpret_cast<uint4*>(g);
-  for (int i = threadIdx.x; i < bytes / 16; i += 4 * NT) {  // 16 KB blocks
-    uint4 v[4];
-#pragma unroll
-    for (int j = 0; j < 4; ++j) v[j] = src[i + j * NT];
-#pragma unroll
-    for (int j = 0; j < 4; ++j) dst[i + j * NT] = v[j];
-  }
-}
-__device__ __forceinline__ void copy_tile_in(const uint8_t* g, uint8_t* s, int bytes) {
-  // 16 KB blocks: 4 independent 128-bit loads per thread in flight
-  const uint4* src = reinterpret_cast<const uint4*>(g);
-  uint4* dst = reinterpret_cast<uint4*>(s);
-  for (int i = threadIdx.x; i < bytes / 16; i += 4 * NT) {
-    uint4 v[4];
-#pragma unroll
-    for (int j = 0; j < 4; ++j) v[j] = __ldg(src + i + j * NT);
-#pragma unroll
-    for (int j = 0; j < 4; ++j) dst[i + j * NT] = v[j];
-  }
-}
 
 constexpr int MAXCH = 4;  // 16-column chunks per thread (n <= 128, two column halves)
 
@@ -930,6 +842,17 @@ static int wgrad_grid(const BGeo& g) {
   return grid < 1 ? 1 : grid;
 }
 
+// three tiles in flight per SM with shared weights (rowmlp_tc_bwd_mc.cu), when there
+// is enough work to fill the machine that way
+static bool use_dgrad_mc(const KParams& p, const BGeo& g) {
+  // default off: in the full train step the two-CTA kernel is ~1 % faster (B200, MEPS)
+  const int env = option_dgrad_mc();
+  if (env == 0) return false;
+  if (!tc_dgrad_mc_supported(p, g)) return false;
+  // measured: +4 % on the 3-source edge MLPs, -6 % on the 2-source node MLP
+  return env > 0 || (g.total_tiles > 296 && p.d.n_src == 3);
+}
+
 struct TcBwdWs {
   size_t a_img, dy_img, dh_img, partial, vec_partial, total;  // float offsets
   int d_slots, w_slots;
@@ -942,7 +865,8 @@ static TcBwdWs tc_bwd_ws(const KParams& p, const BGeo& g) {
   w.a_img = o, o += al((size_t)g.total_tiles * g.kb2 * blk_f);
   w.dy_img = o, o += al((size_t)g.total_tiles * g.kbo * blk_f);
   w.dh_img = o, o += al((size_t)g.total_tiles * g.kb2 * blk_f);
-  w.d_slots = grid_for(g.smem_bytes, g.tmem_cols, g.total_tiles);
+  w.d_slots = use_dgrad_mc(p, g) ? tc_dgrad_mc_grid(g)
+                                 : grid_for(g.smem_bytes, g.tmem_cols, g.total_tiles);
   w.w_slots = wgrad_grid(g);
   w.partial = o, o += al((size_t)w.w_slots * p.d.n_chunks * g.p_total);
   w.vec_partial = o, o += al((size_t)w.d_slots * p.d.n_chunks * g.vec_len);
@@ -1024,9 +948,12 @@ int tc_rowmlp_bwd(const nlam_rowmlp_bwd& bd, cudaStream_t st) {
   static int md[5] = {0, 0, 0, 0, 0}, mw[5] = {0, 0, 0, 0, 0};
   int rc;
   const int mask = bd.stage_mask ? bd.stage_mask : 7;
+  const bool dmc = tc::use_dgrad_mc(p, g);
 #define NLAM_BWD_PAIR(FNV, FGV, I)                                                          \
   rc = 0;                                                                                   \
-  if (mask & 1) rc = launch(tc::rowmlp_tc_dgrad_kernel<FNV, FGV>, md[I], gd, g.smem_bytes); \
+  if (mask & 1)                                                                             \
+    rc = dmc ? tc_rowmlp_dgrad_mc(p, g, st)                                                 \
+             : launch(tc::rowmlp_tc_dgrad_kernel<FNV, FGV>, md[I], gd, g.smem_bytes);       \
   if (!rc && (mask & 2))                                                                    \
     rc = launch(tc::rowmlp_tc_wgrad_kernel<FNV, FGV>, mw[I], gw, g.w_smem_bytes);
   if (fn == 64 && fg) {

@@ -117,6 +117,7 @@ SYMBOLS = {
     "nlam_last_error": (ctypes.c_char_p, []),
     "nlam_version": (ctypes.c_int, []),
     "nlam_launch_count": (ctypes.c_int64, []),
+    "nlam_set_option": (ctypes.c_int, [ctypes.c_char_p, ctypes.c_int]),
     "nlam_csr_build": (
         ctypes.c_int,
         [c_int_p, ctypes.c_int64, ctypes.c_int32, c_int_p, c_int_p, c_float_p, c_int_p,

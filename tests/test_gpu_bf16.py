@@ -96,6 +96,19 @@ def test_interaction_net_bf16_vs_reference_golden(dev, bf16, name):
         _close(p.grad, ref["param_grads"][n], f"grad {n}")
 
 
+@pytest.fixture(params=["default", "multi_context", "two_cta"])
+def kernel_choice(request):
+    """Exercise both kernel families of the d=64 path (nlam_set_option)."""
+    from neural_lam_b200 import lib
+    val = {"default": (-1, 0), "multi_context": (1, 1), "two_cta": (0, 0)}[request.param]
+    l = lib.load()
+    l.nlam_set_option(b"fwd_mc", val[0])
+    l.nlam_set_option(b"dgrad_mc", val[1])
+    yield request.param
+    l.nlam_set_option(b"fwd_mc", -1)
+    l.nlam_set_option(b"dgrad_mc", 0)
+
+
 @pytest.mark.parametrize("d,M,n_send,n_rec,B,update,aggr", [
     (64, 20000, 3000, 2500, 2, True, "sum"),
     (64, 9000, 4000, 700, 1, False, "mean"),
@@ -105,7 +118,8 @@ def test_interaction_net_bf16_vs_reference_golden(dev, bf16, name):
     (64, 9000, 300, 40, 2, False, "sum"),      # in-degree > 128: not tile-alignable
     (128, 4000, 700, 3000, 1, False, "mean"),
 ])
-def test_interaction_net_bf16_vs_oracle(dev, bf16, d, M, n_send, n_rec, B, update, aggr):
+def test_interaction_net_bf16_vs_oracle(dev, bf16, kernel_choice, d, M, n_send, n_rec, B, update,
+                                        aggr):
     from neural_lam_b200.interaction_net import InteractionNet
     from oracle import port
     g = torch.Generator().manual_seed(d + M)
