@@ -44,6 +44,8 @@ def parse():
     ap.add_argument("--batch", type=int, default=4, help="samples per GPU per step")
     ap.add_argument("--hidden-dim", type=int, default=64)
     ap.add_argument("--processor-layers", type=int, default=4)
+    ap.add_argument("--graph", default="1level", choices=["1level", "multiscale"],
+                    help="mesh graph (BASELINE configs[1] = 1level; configs[2] = multiscale)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cuda-graph", type=int, default=1,
                     help="replay the train step as one CUDA graph (single-GPU runs)")
@@ -55,15 +57,20 @@ def make_case(root, a):
 
     ds = synthetic.meps_datastore(root, seed=0)
     args = synthetic.ModelArgs(hidden_dim=a.hidden_dim, processor_layers=a.processor_layers,
-                               graph="1level", loss="wmse")
-    create_graph.create_graph(os.path.join(root, "graph", "1level"),
-                              ds.get_xy("state", stacked=False), n_max_levels=1,
+                               graph=a.graph, loss="wmse")
+    create_graph.create_graph(os.path.join(root, "graph", a.graph),
+                              ds.get_xy("state", stacked=False),
+                              n_max_levels=1 if a.graph == "1level" else None,
                               hierarchical=False)
     return ds, args
 
 
 def config_dict(a, extra=None):
-    cfg = {"workload": WORKLOAD, "global_batch": a.batch * a.gpus, "batch_per_gpu": a.batch,
+    workload = WORKLOAD
+    if (a.hidden_dim, a.processor_layers, a.graph) != (64, 4, "1level"):
+        workload = (f"GraphLAM {a.graph} mesh, hidden_dim={a.hidden_dim}, {a.processor_layers} "
+                    "processor layers, synthetic MEPS 268x238 grid, 17 state vars, ar_steps=1")
+    cfg = {"workload": workload, "global_batch": a.batch * a.gpus, "batch_per_gpu": a.batch,
            "ar_steps": 1, "hidden_dim": a.hidden_dim, "processor_layers": a.processor_layers,
            "parallelism": f"dp{a.gpus}" if a.gpus > 1 else "single"}
     if extra:
