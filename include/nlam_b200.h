@@ -183,7 +183,9 @@ int nlam_version(void);
 /* Kernel-selection knobs (process-wide; -1 = automatic, 0 = off, 1 = force when
  * eligible): "fwd_mc" = 4-pipeline shared-weight forward kernel, "dgrad_mc" =
  * 3-pipeline shared-weight input-gradient kernel.  Returns 0, or 1 for an
- * unknown name.  Environment NLAM_FWD_MC / NLAM_DGRAD_MC give the initial values. */
+ * unknown name.  "bwd_fused" (default on) = single input + weight gradient kernel
+ * for square 64-wide MLPs.  Environment NLAM_FWD_MC / NLAM_DGRAD_MC /
+ * NLAM_BWD_FUSED give the initial values. */
 int nlam_set_option(const char* name, int value);
 /* Number of kernels this library has launched in this process (monotonic;
  * bench.py reports the delta over its timed region as "gpu_launches"). */
@@ -200,6 +202,10 @@ int nlam_csr_build(const int32_t* key, int64_t n_edges, int32_t n_keys, int32_t*
 int nlam_rowmlp_fwd(const nlam_rowmlp* desc, void* stream);
 size_t nlam_rowmlp_bwd_workspace(const nlam_rowmlp* desc);
 size_t nlam_rowmlp_param_floats(const nlam_rowmlp* desc); /* per chunk */
+/* Kernels nlam_rowmlp_bwd_run launches for this descriptor: 3 = input gradients,
+ * weight gradients, partial reduction (stage_mask bits 1, 2, 4); 2 = one fused
+ * input + weight gradient kernel (bit 1; bit 2 is a no-op) and the reduction. */
+int nlam_rowmlp_bwd_stages(const nlam_rowmlp* desc);
 int nlam_rowmlp_bwd_run(const nlam_rowmlp_bwd* desc, void* stream);
 int nlam_segsum_run(const nlam_segsum* desc, void* stream);
 int64_t nlam_state_step_partials(int64_t rows);

@@ -22,8 +22,10 @@ static int env_or(const char* name, int dflt) {
 }
 static std::atomic<int> g_fwd_mc{env_or("NLAM_FWD_MC", -1)};
 static std::atomic<int> g_dgrad_mc{env_or("NLAM_DGRAD_MC", 0)};
+static std::atomic<int> g_bwd_fused{env_or("NLAM_BWD_FUSED", -1)};
 int option_fwd_mc() { return g_fwd_mc.load(); }
 int option_dgrad_mc() { return g_dgrad_mc.load(); }
+int option_bwd_fused() { return g_bwd_fused.load(); }
 void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 }  // namespace nlam
 
@@ -32,6 +34,7 @@ using namespace nlam;
 extern "C" int nlam_set_option(const char* name, int value) {
   if (name && !strcmp(name, "fwd_mc")) return nlam::g_fwd_mc.store(value), 0;
   if (name && !strcmp(name, "dgrad_mc")) return nlam::g_dgrad_mc.store(value), 0;
+  if (name && !strcmp(name, "bwd_fused")) return nlam::g_bwd_fused.store(value), 0;
   nlam::set_error("nlam_set_option: unknown option");
   return 1;
 }
@@ -56,6 +59,12 @@ extern "C" size_t nlam_rowmlp_bwd_workspace(const nlam_rowmlp* d) {
   if (!d) return 0;
   if (d->precision == NLAM_BF16 && tc::tc_supported(*d)) return tc_rowmlp_bwd_workspace(*d);
   return simt_rowmlp_bwd_workspace(*d);
+}
+
+extern "C" int nlam_rowmlp_bwd_stages(const nlam_rowmlp* d) {
+  if (!d) return 0;
+  if (d->precision == NLAM_BF16 && tc::tc_supported(*d) && tc_rowmlp_bwd_is_fused(*d)) return 2;
+  return 3;
 }
 
 extern "C" size_t nlam_rowmlp_param_floats(const nlam_rowmlp* d) {

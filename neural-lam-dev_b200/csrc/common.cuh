@@ -12,6 +12,7 @@ void set_error(const char* fmt, ...);
 void count_launch(int n = 1);
 int option_fwd_mc();    // -1 auto, 0 off, 1 force
 int option_dgrad_mc();
+int option_bwd_fused();  // -1 / 1: fused dgrad + wgrad kernel where eligible, 0: two kernels
 
 #define NLAM_CHECK(cond, ...)        \
   do {                               \
@@ -74,5 +75,6 @@ bool tc_supported(const nlam_rowmlp& d);
 int tc_rowmlp_fwd(const nlam_rowmlp& d, cudaStream_t st);
 int tc_rowmlp_bwd(const nlam_rowmlp_bwd& d, cudaStream_t st);
 size_t tc_rowmlp_bwd_workspace(const nlam_rowmlp& d);
+bool tc_rowmlp_bwd_is_fused(const nlam_rowmlp& d);
 
 }  // namespace nlam

@@ -853,6 +853,11 @@ static bool use_dgrad_mc(const KParams& p, const BGeo& g) {
   return env > 0 || (g.total_tiles > 296 && p.d.n_src == 3);
 }
 
+// one kernel for input and weight gradients (rowmlp_tc_bwd_fused.cu): square 64-wide MLPs
+static bool use_bwd_fused(const KParams& p) {
+  return option_bwd_fused() != 0 && tc_bwd_fused_supported(p);
+}
+
 struct TcBwdWs {
   size_t a_img, dy_img, dh_img, partial, vec_partial, total;  // float offsets
   int d_slots, w_slots;
@@ -862,12 +867,14 @@ static TcBwdWs tc_bwd_ws(const KParams& p, const BGeo& g) {
   TcBwdWs w;
   const size_t blk_f = TM * 128 / 4;  // floats per 16 KB block
   size_t o = 0;
-  w.a_img = o, o += al((size_t)g.total_tiles * g.kb2 * blk_f);
-  w.dy_img = o, o += al((size_t)g.total_tiles * g.kbo * blk_f);
-  w.dh_img = o, o += al((size_t)g.total_tiles * g.kb2 * blk_f);
-  w.d_slots = use_dgrad_mc(p, g) ? tc_dgrad_mc_grid(g)
-                                 : grid_for(g.smem_bytes, g.tmem_cols, g.total_tiles);
-  w.w_slots = wgrad_grid(g);
+  const bool fused = use_bwd_fused(p);  // no bf16 tile images, one partial slot per CTA
+  w.a_img = o, o += fused ? 0 : al((size_t)g.total_tiles * g.kb2 * blk_f);
+  w.dy_img = o, o += fused ? 0 : al((size_t)g.total_tiles * g.kbo * blk_f);
+  w.dh_img = o, o += fused ? 0 : al((size_t)g.total_tiles * g.kb2 * blk_f);
+  w.d_slots = fused ? tc_bwd_fused_grid(g)
+              : use_dgrad_mc(p, g) ? tc_dgrad_mc_grid(g)
+                                   : grid_for(g.smem_bytes, g.tmem_cols, g.total_tiles);
+  w.w_slots = fused ? w.d_slots : wgrad_grid(g);
   w.partial = o, o += al((size_t)w.w_slots * p.d.n_chunks * g.p_total);
   w.vec_partial = o, o += al((size_t)w.d_slots * p.d.n_chunks * g.vec_len);
   w.total = o;
@@ -875,6 +882,12 @@ static TcBwdWs tc_bwd_ws(const KParams& p, const BGeo& g) {
 }
 
 }  // namespace tc
+
+bool tc_rowmlp_bwd_is_fused(const nlam_rowmlp& d) {
+  KParams p{};
+  if (fill_params(d, p)) return false;
+  return tc::use_bwd_fused(p);
+}
 
 size_t tc_rowmlp_bwd_workspace(const nlam_rowmlp& d) {
   KParams p{};
@@ -949,6 +962,13 @@ int tc_rowmlp_bwd(const nlam_rowmlp_bwd& bd, cudaStream_t st) {
   int rc;
   const int mask = bd.stage_mask ? bd.stage_mask : 7;
   const bool dmc = tc::use_dgrad_mc(p, g);
+  if (tc::use_bwd_fused(p)) {  // stage bit 1 covers input AND weight gradients
+    if ((mask & 1) && tc_rowmlp_bwd_fused(p, g, st)) return 1;
+    if (!(mask & 4)) return 0;
+    return launch_reduce_params(g.partial, ws.w_slots, d.n_chunks, g.p_total, bd.d_params,
+                                bd.params_accumulate, g.vec_partial, ws.d_slots, g.vec_len, p.lay,
+                                st);
+  }
 #define NLAM_BWD_PAIR(FNV, FGV, I)                                                          \
   rc = 0;                                                                                   \
   if (mask & 1)                                                                             \

@@ -1,0 +1,645 @@
+// Fused bf16 tcgen05 row-MLP BACKWARD (input gradients + weight gradients in one
+// kernel) for the square 64-wide case (d_hidden = d_out = source widths = 64, one
+// weight set): every InteractionNet edge / node MLP of the d=64 models.
+//
+// One persistent CTA per SM, 544 threads:
+//   * two CONTEXTS of 256 threads, each an independent pipeline over 128-row tiles
+//     (gather z -> GEMM1 -> SiLU -> GEMM2 -> LayerNorm' -> GEMM3 -> SiLU' -> GEMM4 ->
+//     per-source gradient rows), same math as rowmlp_tc_dgrad_kernel;
+//   * one ISSUE warp that feeds the weight-gradient UMMAs
+//        dW2^T += a^T . dY      (when a context has a and dY in shared memory)
+//        dW1^T += z^T . dH      (when it has z and dH)
+//     into ONE set of fp32 TMEM accumulators that lives for the whole kernel.  The
+//     issue thread serves the contexts in a fixed round-robin order (context 0 tile
+//     k, context 1 tile k, context 0 tile k+1, ...): accumulation order -- and so
+//     the result -- is deterministic, and no bf16 tile image ever goes to HBM.
+//
+// Shared memory (195 KB): W1 / W2 bf16 operands staged once per SM (32 KB) + per
+// context 80 KB = z tile (48 KB, later the fp32 staging of the dZ rows) | a -> dH
+// tile (16 KB) | dOut (bf16, staged coalesced) -> dY tile (16 KB).
+// TMEM (448 of 512 columns): per context H (64) | Y (64), recycled as dA and the
+// double-buffered dZ; shared dW1^T (2 x 64) and dW2^T (64).
+//
+// Reference: autograd of utils.make_mlp / InteractionNet.message / aggr_mlp
+// (utils.py:191-214, interaction_net.py:106,117-121).
+#include "rowmlp_tc_bwd.cuh"
+
+namespace nlam {
+namespace tc {
+
+constexpr int FU_CTX = 2;
+constexpr int FU_CT = 256;                     // threads per context
+constexpr int FU_NT = FU_CTX * FU_CT + 32;     // + the weight-gradient issue warp
+constexpr int FU_FN = 64;
+constexpr uint32_t FU_BLK = TM * 128u;         // one 64-column bf16 tile block: 16 KB
+constexpr uint32_t FU_CTXB = 5u * FU_BLK;      // z (3) | a/dH | dOut/dY
+constexpr uint32_t FU_OFF_W1 = FU_CTX * FU_CTXB;
+constexpr uint32_t FU_OFF_W2 = FU_OFF_W1 + 3u * FU_FN * 128u;
+constexpr uint32_t FU_OFF_PAR = FU_OFF_W2 + FU_FN * 128u;
+constexpr uint32_t FU_OFF_LNX = FU_OFF_PAR + 3u * FU_FN * 4u;          // [ctx][4][TM][2] floats
+constexpr uint32_t FU_OFF_BAR = FU_OFF_LNX + FU_CTX * 4u * TM * 2u * 4u;
+constexpr uint32_t FU_SMEM = FU_OFF_BAR + 256u;
+constexpr int FU_NBAR = 7;  // per context: main, dZ0, dZ1, rdy_w2, done_w2, rdy_w1, done_w1
+
+__device__ __forceinline__ void fu_sync(int ctx) {
+  asm volatile("bar.sync %0, 256;" ::"r"(ctx + 1) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void unpack8(const uint4& q, float* v) {
+  v[0] = __uint_as_float(q.x << 16), v[1] = __uint_as_float(q.x & 0xffff0000u);
+  v[2] = __uint_as_float(q.y << 16), v[3] = __uint_as_float(q.y & 0xffff0000u);
+  v[4] = __uint_as_float(q.z << 16), v[5] = __uint_as_float(q.z & 0xffff0000u);
+  v[6] = __uint_as_float(q.w << 16), v[7] = __uint_as_float(q.w & 0xffff0000u);
+}
+
+__global__ void __launch_bounds__(FU_NT, 1)
+rowmlp_tc_bwd_fused_kernel(const __grid_constant__ KParams p, const __grid_constant__ BGeo g) {
+  extern __shared__ __align__(1024) uint8_t sm[];
+  if (smem_u32(sm) & 1023u) __trap();
+  constexpr int FN = FU_FN;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int ctx = tid >> 8;          // 0, 1: contexts; 2: issue warp
+  const int ltid = tid & 255, lwarp = ltid >> 5;
+  uint8_t* sW1 = sm + FU_OFF_W1;
+  uint8_t* sW2 = sm + FU_OFF_W2;
+  float* sPar = reinterpret_cast<float*>(sm + FU_OFF_PAR);  // b1 | b2 | gamma
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sm + FU_OFF_BAR);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + FU_CTX * FU_NBAR);
+  const bool has_ln = p.d.w.ln_g != nullptr;
+  const int n_src = p.d.n_src;
+
+  if (warp == 0) tmem_alloc(tmem_slot, 512u);
+  if (tid == 32) {
+    for (int i = 0; i < FU_CTX * FU_NBAR; ++i) mbar_init(&bars[i], 1);
+    mbar_fence_init();
+  }
+  {  // weights: once per SM
+    const int nch1 = (n_src * FN) >> 3;
+    for (int u = tid; u < FN * nch1; u += FU_NT) {
+      const int n = u / nch1, k0 = (u % nch1) * 8;
+      const float4* q = reinterpret_cast<const float4*>(p.d.w.w1 + (size_t)n * p.k_total + k0);
+      const float4 a = __ldg(q), c = __ldg(q + 1);
+      *reinterpret_cast<uint4*>(sW1 + sw128_off(n, k0, FN * 128u)) =
+          make_uint4(pack_bf16(a.x, a.y), pack_bf16(a.z, a.w), pack_bf16(c.x, c.y),
+                     pack_bf16(c.z, c.w));
+    }
+    for (int u = tid; u < FN * (FN >> 3); u += FU_NT) {
+      const int n = u / (FN >> 3), k0 = (u % (FN >> 3)) * 8;
+      const float4* q = reinterpret_cast<const float4*>(p.d.w.w2 + (size_t)n * FN + k0);
+      const float4 a = __ldg(q), c = __ldg(q + 1);
+      *reinterpret_cast<uint4*>(sW2 + sw128_off(n, k0, FN * 128u)) =
+          make_uint4(pack_bf16(a.x, a.y), pack_bf16(a.z, a.w), pack_bf16(c.x, c.y),
+                     pack_bf16(c.z, c.w));
+    }
+    for (int i = tid; i < 3 * FN; i += FU_NT) {
+      const int j = i % FN, which = i / FN;
+      sPar[i] = which == 0 ? __ldg(p.d.w.b1 + j)
+                : which == 1 ? __ldg(p.d.w.b2 + j)
+                             : (has_ln ? __ldg(p.d.w.ln_g + j) : 1.f);
+    }
+  }
+  fence_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tW1 = tmem_base + 256u;  // dW1^T rows 0..127 | rows 128..191 (+64 columns)
+  const uint32_t tW2 = tmem_base + 384u;
+  const int stride = gridDim.x * FU_CTX;
+  const int mch = (n_src + 1) / 2;  // 128-row chunks of dW1^T
+
+  // per-thread column sums (context threads only)
+  float acc_db1[2], acc_db2[2], acc_dg[2], acc_dbt[2];
+#pragma unroll
+  for (int i = 0; i < 2; ++i) acc_db1[i] = acc_db2[i] = acc_dg[i] = acc_dbt[i] = 0.f;
+
+  if (ctx == FU_CTX) {
+    // ======================= weight-gradient issue warp =======================
+    if (lane == 0) {
+      const uint32_t idesc_w = make_idesc_bf16(TM, FN, 1, 1);  // A and B viewed MN-major
+      uint32_t ph[FU_CTX] = {0u, 0u};
+      bool first = true;
+      for (int t0 = blockIdx.x * FU_CTX; t0 < g.total_tiles; t0 += stride) {
+#pragma unroll
+        for (int c = 0; c < FU_CTX; ++c) {
+          if (t0 + c >= g.total_tiles) continue;
+          uint64_t* cb = &bars[c * FU_NBAR];
+          const uint32_t z0 = smem_u32(sm + (uint32_t)c * FU_CTXB);
+          const uint32_t a0 = z0 + 3u * FU_BLK, y0 = z0 + 4u * FU_BLK;
+          mbar_wait(&cb[3], ph[c]);  // a and dY are in shared memory
+          tc_fence_after();
+          for (int ks = 0; ks < TM / 16; ++ks)
+            umma_bf16(tW2, make_desc_mn_sw128(a0 + (uint32_t)ks * 2048u, FU_BLK),
+                      make_desc_mn_sw128(y0 + (uint32_t)ks * 2048u, FU_BLK), idesc_w,
+                      (!first || ks > 0) ? 1u : 0u);
+          umma_commit(&cb[4]);
+          mbar_wait(&cb[5], ph[c]);  // dH replaced a; z is still there
+          tc_fence_after();
+          for (int mc = 0; mc < mch; ++mc)
+            for (int ks = 0; ks < TM / 16; ++ks)
+              umma_bf16(tW1 + (uint32_t)(mc * FN),
+                        make_desc_mn_sw128(z0 + (uint32_t)mc * 2u * FU_BLK + (uint32_t)ks * 2048u,
+                                           FU_BLK),
+                        make_desc_mn_sw128(a0 + (uint32_t)ks * 2048u, FU_BLK), idesc_w,
+                        (!first || ks > 0) ? 1u : 0u);
+          umma_commit(&cb[6]);
+          ph[c] ^= 1u;
+          first = false;
+        }
+      }
+    }
+    __syncwarp();
+  } else {
+    // ============================ tile contexts ============================
+    uint8_t* sA = sm + (uint32_t)ctx * FU_CTXB;           // z blocks | fp32 dZ staging
+    float* stg = reinterpret_cast<float*>(sA);
+    uint8_t* sT = sA + 3u * FU_BLK;                        // a -> dH
+    uint8_t* sD = sA + 4u * FU_BLK;                        // dOut (bf16) -> dY
+    float* sLnx = reinterpret_cast<float*>(sm + FU_OFF_LNX) + ctx * (4 * TM * 2);
+    uint64_t* cb = &bars[ctx * FU_NBAR];
+    uint64_t* bar_m = &cb[0];
+    uint64_t* bar_z = &cb[1];
+    const uint32_t tH = tmem_base + (uint32_t)ctx * 128u, tY = tH + 64u;
+    uint32_t ph_m = 0, ph_z = 0, ph_w = 0;
+
+    const uint32_t idesc = make_idesc_bf16(TM, FN);
+    const uint32_t idesc_mn = make_idesc_bf16(TM, FN, 0, 1);  // B operand viewed MN-major
+    const int q = lwarp & 3, hf = lwarp >> 2, r = q * 32 + lane;
+    const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
+    const float* sB1 = sPar;
+    const float* sB2 = sPar + FN;
+    const float* sG = sPar + 2 * FN;
+    const int k1steps = n_src * FN / 16;
+    const int gc = ltid & 7, grl = ltid >> 3;  // gather: 16-byte bf16 chunk / row of a 32-row pass
+
+    for (int t = blockIdx.x * FU_CTX + ctx; t < g.total_tiles; t += stride) {
+      const int b = t % p.d.batch, tile = t / p.d.batch;  // batch innermost: shared rows hit L2
+      int row0, cnt, chunk;
+      tile_range<TM>(p.d, tile, row0, cnt, chunk);
+      const size_t grow0 = (size_t)b * p.d.rows + row0;
+
+      // dOut = g0 rows (+ scale * gathered g1 rows): 4 units (row, 4 columns) per call
+      auto dm_load = [&](int base, float4 (&va)[4], float4 (&vb)[4], float (&gs)[4]) {
+        const float* g0p[4];
+        const float* g1p[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int u = base + j * FU_CT, row = u >> 4, col = (u & 15) * 4;
+          g0p[j] = g1p[j] = nullptr;
+          gs[j] = 1.f;
+          if (row < cnt) {
+            if (p.g0) {
+              const size_t gr = p.g0_idx ? (size_t)b * p.d.rows + __ldg(p.g0_idx + row0 + row)
+                                         : grow0 + row;
+              g0p[j] = p.g0 + gr * FN + col;
+            }
+            if (p.g1) {
+              const int gi = __ldg(p.g1_idx + row0 + row);
+              if (p.g1_scale) gs[j] = __ldg(p.g1_scale + gi);
+              g1p[j] = p.g1 + (size_t)b * p.g1_batch_stride + (size_t)gi * FN + col;
+            }
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          va[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+          vb[j] = va[j];
+          if (g0p[j]) va[j] = __ldg(reinterpret_cast<const float4*>(g0p[j]));
+          if (g1p[j]) vb[j] = __ldg(reinterpret_cast<const float4*>(g1p[j]));
+        }
+      };
+      auto dm_store = [&](int base, const float4 (&va)[4], const float4 (&vb)[4],
+                          const float (&gs)[4]) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int u = base + j * FU_CT, row = u >> 4, c4 = u & 15;
+          const uint2 pk = make_uint2(
+              pack_bf16(va[j].x + gs[j] * vb[j].x, va[j].y + gs[j] * vb[j].y),
+              pack_bf16(va[j].z + gs[j] * vb[j].z, va[j].w + gs[j] * vb[j].w));
+          *reinterpret_cast<uint2*>(sD + sw128_off(row, (c4 >> 1) * 8, FU_BLK) + (c4 & 1) * 8) = pk;
+        }
+      };
+
+      // ---------------- gather z (all sources) + GEMM 1: H = z . W1^T
+      for (int s = 0; s < n_src; ++s) {
+        const nlam_src& src = p.d.src[s];
+        const float* base = src.ptr + (long long)b * src.batch_stride + gc * 8;
+        const int32_t* idx = src.idx;
+        int ridx[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int row = i * 32 + grl;
+          ridx[i] = row < cnt ? (idx ? __ldg(idx + row0 + row) : row0 + row) : -1;
+        }
+        float4 x[4], y[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          x[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+          y[i] = x[i];
+          if (ridx[i] >= 0) {
+            const float4* qq = reinterpret_cast<const float4*>(base + (long long)ridx[i] * src.ld);
+            x[i] = __ldg(qq);
+            y[i] = __ldg(qq + 1);
+          }
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+          *reinterpret_cast<uint4*>(sA + sw128_off(i * 32 + grl, s * FN + gc * 8, FU_BLK)) =
+              make_uint4(pack_bf16(x[i].x, x[i].y), pack_bf16(x[i].z, x[i].w),
+                         pack_bf16(y[i].x, y[i].y), pack_bf16(y[i].z, y[i].w));
+      }
+      fence_async_smem();
+      fu_sync(ctx);
+      if (ltid == 0) {
+        tc_fence_after();
+        const uint32_t a0 = smem_u32(sA), w0 = smem_u32(sW1);
+        for (int ks = 0; ks < k1steps; ++ks) {
+          const uint32_t kb = ks >> 2, kin = (ks & 3) * 32;
+          umma_bf16(tH, make_desc_k_sw128(a0 + kb * FU_BLK + kin),
+                    make_desc_k_sw128(w0 + kb * (FN * 128u) + kin), idesc, ks > 0);
+        }
+        umma_commit(bar_m);
+      }
+      // while GEMM 1 runs: dOut rows -> bf16 tile (coalesced), next tile's rows -> L2
+      {
+        float4 va[4], vb[4];
+        float gs[4];
+        dm_load(ltid, va, vb, gs);
+        dm_store(ltid, va, vb, gs);
+        dm_load(ltid + 4 * FU_CT, va, vb, gs);
+        dm_store(ltid + 4 * FU_CT, va, vb, gs);
+      }
+      {
+        const int tn = t + stride;
+        if (tn < g.total_tiles && ltid < TM) {
+          int r0n, cn, chn;
+          tile_range<TM>(p.d, tn / p.d.batch, r0n, cn, chn);
+          const int bn = tn % p.d.batch;
+          if (ltid < cn) {
+            for (int s = 0; s < n_src; ++s) {
+              const nlam_src& src = p.d.src[s];
+              const int ri = src.idx ? __ldg(src.idx + r0n + ltid) : r0n + ltid;
+              const char* qq = reinterpret_cast<const char*>(
+                  src.ptr + (long long)bn * src.batch_stride + (long long)ri * src.ld);
+              prefetch_l2(qq);
+              prefetch_l2(qq + 128);
+            }
+            if (p.g0) {
+              const size_t gr = p.g0_idx ? (size_t)bn * p.d.rows + __ldg(p.g0_idx + r0n + ltid)
+                                         : (size_t)bn * p.d.rows + r0n + ltid;
+              prefetch_l2(p.g0 + gr * FN);
+              prefetch_l2(p.g0 + gr * FN + 32);
+            }
+            if (p.g1) {
+              const int gi = __ldg(p.g1_idx + r0n + ltid);
+              const float* qq = p.g1 + (size_t)bn * p.g1_batch_stride + (size_t)gi * FN;
+              prefetch_l2(qq);
+              prefetch_l2(qq + 32);
+            }
+          }
+        }
+      }
+      mbar_wait(bar_m, ph_m);
+      ph_m ^= 1;
+      tc_fence_after();
+
+      // ---------------- epilogue 1: a = SiLU(H + b1) -> bf16 tile
+#pragma unroll
+      for (int ci = 0; ci < 2; ++ci) {
+        const int c0 = hf * 32 + ci * 16;
+        float v[16];
+        tmem_ld16(tH + lane_addr + (uint32_t)c0, v);
+#pragma unroll
+        for (int j = 0; j < 16; ++j) v[j] = silu_fast(v[j] + sB1[c0 + j]);
+#pragma unroll
+        for (int h8 = 0; h8 < 2; ++h8)
+          *reinterpret_cast<uint4*>(sT + sw128_off(r, c0 + h8 * 8, FU_BLK)) =
+              make_uint4(pack_bf16(v[h8 * 8 + 0], v[h8 * 8 + 1]),
+                         pack_bf16(v[h8 * 8 + 2], v[h8 * 8 + 3]),
+                         pack_bf16(v[h8 * 8 + 4], v[h8 * 8 + 5]),
+                         pack_bf16(v[h8 * 8 + 6], v[h8 * 8 + 7]));
+      }
+      fence_async_smem();
+      tc_fence_before();
+      fu_sync(ctx);
+
+      // ---------------- GEMM 2: Y = a . W2^T
+      if (ltid == 0) {
+        tc_fence_after();
+        const uint32_t a0 = smem_u32(sT), w0 = smem_u32(sW2);
+        for (int ks = 0; ks < FN / 16; ++ks)
+          umma_bf16(tY, make_desc_k_sw128(a0 + ks * 32), make_desc_k_sw128(w0 + ks * 32), idesc,
+                    ks > 0);
+        umma_commit(bar_m);
+      }
+      mbar_wait(bar_m, ph_m);
+      ph_m ^= 1;
+      tc_fence_after();
+
+      // ---------------- epilogue 2: LayerNorm backward -> dY (bf16, in place of dOut)
+      {
+        float y[32];  // this thread's 32 columns of row r: y -> y_hat
+#pragma unroll
+        for (int ci = 0; ci < 2; ++ci) {
+          const int c0 = hf * 32 + ci * 16;
+          float v[16];
+          tmem_ld16(tY + lane_addr + (uint32_t)c0, v);
+#pragma unroll
+          for (int j = 0; j < 16; ++j) y[ci * 16 + j] = v[j] + sB2[c0 + j];
+        }
+        float rstd = 1.f, m1 = 0.f, m2 = 0.f;
+        if (has_ln) {
+          float s = 0.f;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) s += y[j];
+          sLnx[(0 * TM + r) * 2 + hf] = s;
+          fu_sync(ctx);
+          const float mean = (sLnx[(0 * TM + r) * 2] + sLnx[(0 * TM + r) * 2 + 1]) * (1.0f / FN);
+          float qq = 0.f;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            y[j] -= mean;
+            qq += y[j] * y[j];
+          }
+          sLnx[(1 * TM + r) * 2 + hf] = qq;
+          fu_sync(ctx);
+          rstd = rsqrtf((sLnx[(1 * TM + r) * 2] + sLnx[(1 * TM + r) * 2 + 1]) * (1.0f / FN) +
+                        LN_EPS);
+          float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+          for (int ci = 0; ci < 2; ++ci) {
+            const int c0 = hf * 32 + ci * 16;
+            float dmv[16], pv[16];
+            unpack8(*reinterpret_cast<const uint4*>(sD + sw128_off(r, c0, FU_BLK)), dmv);
+            unpack8(*reinterpret_cast<const uint4*>(sD + sw128_off(r, c0 + 8, FU_BLK)), dmv + 8);
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              const float yh = y[ci * 16 + j] * rstd;
+              const float dyh = dmv[j] * sG[c0 + j];
+              y[ci * 16 + j] = yh;  // keep y_hat
+              pv[j] = dmv[j] * yh;
+              s1 += dyh;
+              s2 += dyh * yh;
+            }
+            acc_dg[ci] += warp_colsum16(pv, lane);
+            acc_dbt[ci] += warp_colsum16(dmv, lane);
+          }
+          sLnx[(2 * TM + r) * 2 + hf] = s1;
+          sLnx[(3 * TM + r) * 2 + hf] = s2;
+          fu_sync(ctx);
+          m1 = (sLnx[(2 * TM + r) * 2] + sLnx[(2 * TM + r) * 2 + 1]) * (1.0f / FN);
+          m2 = (sLnx[(3 * TM + r) * 2] + sLnx[(3 * TM + r) * 2 + 1]) * (1.0f / FN);
+        }
+#pragma unroll
+        for (int ci = 0; ci < 2; ++ci) {
+          const int c0 = hf * 32 + ci * 16;
+          float v[16];
+          unpack8(*reinterpret_cast<const uint4*>(sD + sw128_off(r, c0, FU_BLK)), v);
+          unpack8(*reinterpret_cast<const uint4*>(sD + sw128_off(r, c0 + 8, FU_BLK)), v + 8);
+          if (has_ln) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              const float dyh = v[j] * sG[c0 + j];
+              v[j] = r < cnt ? rstd * (dyh - m1 - y[ci * 16 + j] * m2) : 0.f;
+            }
+          }
+          acc_db2[ci] += warp_colsum16(v, lane);
+#pragma unroll
+          for (int h8 = 0; h8 < 2; ++h8)
+            *reinterpret_cast<uint4*>(sD + sw128_off(r, c0 + h8 * 8, FU_BLK)) =
+                make_uint4(pack_bf16(v[h8 * 8 + 0], v[h8 * 8 + 1]),
+                           pack_bf16(v[h8 * 8 + 2], v[h8 * 8 + 3]),
+                           pack_bf16(v[h8 * 8 + 4], v[h8 * 8 + 5]),
+                           pack_bf16(v[h8 * 8 + 6], v[h8 * 8 + 7]));
+        }
+      }
+      fence_async_smem();
+      tc_fence_before();
+      fu_sync(ctx);
+
+      // ---------------- GEMM 3: dA = dY . W2 (into Y's columns); a, dY -> weight-gradient warp
+      if (ltid == 0) {
+        tc_fence_after();
+        const uint32_t a0 = smem_u32(sD), w0 = smem_u32(sW2);
+        for (int ks = 0; ks < FN / 16; ++ks)
+          umma_bf16(tY, make_desc_k_sw128(a0 + ks * 32),
+                    make_desc_mn_sw128(w0 + (uint32_t)ks * 2048u, FN * 128u), idesc_mn, ks > 0);
+        umma_commit(bar_m);
+        mbar_arrive(&cb[3]);
+      }
+      mbar_wait(bar_m, ph_m);
+      ph_m ^= 1;
+      mbar_wait(&cb[4], ph_w);  // dW2 UMMAs have read the a tile: it may become dH
+      tc_fence_after();
+
+      // ---------------- epilogue 3: dH = dA * SiLU'(H + b1) -> bf16 tile
+#pragma unroll
+      for (int ci = 0; ci < 2; ++ci) {
+        const int c0 = hf * 32 + ci * 16;
+        float v[16], h[16];
+        tmem_ld16(tY + lane_addr + (uint32_t)c0, v);
+        tmem_ld16(tH + lane_addr + (uint32_t)c0, h);
+#pragma unroll
+        for (int j = 0; j < 16; ++j) v[j] *= silu_grad_fast(h[j] + sB1[c0 + j]);
+        acc_db1[ci] += warp_colsum16(v, lane);
+#pragma unroll
+        for (int h8 = 0; h8 < 2; ++h8)
+          *reinterpret_cast<uint4*>(sT + sw128_off(r, c0 + h8 * 8, FU_BLK)) =
+              make_uint4(pack_bf16(v[h8 * 8 + 0], v[h8 * 8 + 1]),
+                         pack_bf16(v[h8 * 8 + 2], v[h8 * 8 + 3]),
+                         pack_bf16(v[h8 * 8 + 4], v[h8 * 8 + 5]),
+                         pack_bf16(v[h8 * 8 + 6], v[h8 * 8 + 7]));
+      }
+      fence_async_smem();
+      tc_fence_before();
+      fu_sync(ctx);
+
+      // ---------------- GEMM 4 + epilogue 4: dZ = dH . W1, one source (64 columns) at a
+      // time, double-buffered in the recycled H / Y columns; z, dH -> weight-gradient warp
+      auto issue_dz = [&](int kb) {
+        tc_fence_after();
+        const uint32_t a0 = smem_u32(sT);
+        const uint32_t w0 = smem_u32(sW1) + (uint32_t)kb * (FN * 128u);
+        for (int ks = 0; ks < FN / 16; ++ks)
+          umma_bf16((kb & 1) ? tY : tH, make_desc_k_sw128(a0 + ks * 32),
+                    make_desc_mn_sw128(w0 + (uint32_t)ks * 2048u, 0), idesc_mn, ks > 0);
+        umma_commit(&bar_z[kb & 1]);
+      };
+      if (ltid == 0) {
+        mbar_arrive(&cb[5]);
+        if (g.need_dz) issue_dz(0);
+      }
+      if (g.need_dz) {
+        for (int kb = 0; kb < n_src; ++kb) {
+          if (ltid == 0 && kb + 1 < n_src) issue_dz(kb + 1);
+          float* fdst = p.d_src[kb];
+          const bool fres = fdst && (kb == p.d.residual_src) && p.g0;
+          const bool reduce = fdst && kb == p.reduce_src;
+          const int32_t* didx = fdst ? p.d_src_idx[kb] : nullptr;
+          int orow_i[8];
+          if (didx && !reduce) {  // scatter targets, fetched while the MMA runs
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const int row = (ltid >> 4) + 16 * i;
+              orow_i[i] = row < cnt ? __ldg(didx + row0 + row) : 0;
+            }
+          }
+          float4 e[8];
+          if (fres) {  // residual rows requested early
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const int row = (ltid >> 4) + 16 * i;
+              e[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+              if (row < cnt) {
+                const size_t gr = p.g0_idx ? (size_t)b * p.d.rows + __ldg(p.g0_idx + row0 + row)
+                                           : grow0 + row;
+                e[i] = __ldg(reinterpret_cast<const float4*>(p.g0 + gr * FN) + (ltid & 15));
+              }
+            }
+          }
+          mbar_wait(&bar_z[kb & 1], (ph_z >> (kb & 1)) & 1u);
+          ph_z ^= 1u << (kb & 1);
+          if (kb == 0) mbar_wait(&cb[6], ph_w);  // dW1 UMMAs have read z: staging may reuse it
+          tc_fence_after();
+#pragma unroll
+          for (int ci = 0; ci < 2; ++ci) {
+            const int c0 = hf * 32 + ci * 16;
+            float v[16];
+            tmem_ld16(((kb & 1) ? tY : tH) + lane_addr + (uint32_t)c0, v);
+#pragma unroll
+            for (int j4 = 0; j4 < 4; ++j4)
+              *reinterpret_cast<float4*>(stg + stg_idx(r, (c0 >> 2) + j4, FN)) =
+                  make_float4(v[j4 * 4], v[j4 * 4 + 1], v[j4 * 4 + 2], v[j4 * 4 + 3]);
+          }
+          tc_fence_before();
+          fu_sync(ctx);
+          if (reduce) {
+            // receiver-aligned tile: sum the gradient rows of each segment (fixed order)
+            const int seg_lo = __ldg(p.d.agg.tile_seg + tile);
+            const int seg_hi = __ldg(p.d.agg.tile_seg + tile + 1);
+            float* ro = fdst + (size_t)b * p.d.agg.n_seg * FN + (ltid & 15) * 4;
+            for (int seg = seg_lo + (ltid >> 4); seg < seg_hi; seg += 16) {
+              const int r0 = __ldg(p.d.agg.seg_ptr + seg) - row0;
+              const int r1 = __ldg(p.d.agg.seg_ptr + seg + 1) - row0;
+              float4* o4 = reinterpret_cast<float4*>(ro + (size_t)seg * FN);
+              float4 old = make_float4(0.f, 0.f, 0.f, 0.f);
+              if (p.reduce_accumulate) old = *o4;
+              float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+              for (int rr = r0; rr < r1; ++rr) {
+                const float4 v = *reinterpret_cast<const float4*>(stg + stg_idx(rr, ltid & 15, FN));
+                acc.x += v.x, acc.y += v.y, acc.z += v.z, acc.w += v.w;
+              }
+              acc.x += old.x, acc.y += old.y, acc.z += old.z, acc.w += old.w;
+              *o4 = acc;
+            }
+          } else if (fdst) {
+            float* o = fdst + (ltid & 15) * 4;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const int row = (ltid >> 4) + 16 * i;
+              if (row < cnt) {
+                float4 v = *reinterpret_cast<const float4*>(stg + stg_idx(row, ltid & 15, FN));
+                if (fres) v.x += e[i].x, v.y += e[i].y, v.z += e[i].z, v.w += e[i].w;
+                const size_t orow = didx ? (size_t)b * p.d.rows + orow_i[i] : grow0 + row;
+                *reinterpret_cast<float4*>(o + orow * FN) = v;
+              }
+            }
+          }
+          fu_sync(ctx);
+        }
+      } else {
+        mbar_wait(&cb[6], ph_w);  // z must outlive the dW1 UMMAs
+      }
+      ph_w ^= 1;
+      tc_fence_before();
+      fu_sync(ctx);  // tiles / staging free for the next tile
+    }
+  }
+
+  // ---------------- accumulators and column sums -> this CTA's partial slot
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  float* sRed = reinterpret_cast<float*>(sm);  // [16 warps][4][32], context 0's dead z tile
+  if (ctx < FU_CTX) {
+    const ParamLayout lay = p.lay;
+    float* dst = g.partial + (size_t)blockIdx.x * g.p_total;
+    const int q = warp & 3, cq = warp >> 2, r = q * 32 + lane;  // 16 warps: 4 column quarters
+    const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
+    const int c0 = cq * 16;
+    for (int mc = 0; mc < mch; ++mc) {
+      const int kg = mc * 128 + r;  // input column
+      float v[16];
+      tmem_ld16(tW1 + (uint32_t)(mc * FN) + lane_addr + (uint32_t)c0, v);
+      if (kg < p.k_total) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) dst[lay.off_w1() + (size_t)(c0 + j) * p.k_total + kg] = v[j];
+      }
+    }
+    {
+      float v[16];
+      tmem_ld16(tW2 + lane_addr + (uint32_t)c0, v);
+      if (r < FN) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) dst[lay.off_w2() + (size_t)(c0 + j) * FN + r] = v[j];
+      }
+    }
+    if (lane < 16) {
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        sRed[(warp * 4 + 0) * 32 + i * 16 + lane] = acc_db1[i];
+        sRed[(warp * 4 + 1) * 32 + i * 16 + lane] = acc_db2[i];
+        sRed[(warp * 4 + 2) * 32 + i * 16 + lane] = acc_dg[i];
+        sRed[(warp * 4 + 3) * 32 + i * 16 + lane] = acc_dbt[i];
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (tid < 4 * FN) {
+    const int which = tid >> 6, col = tid & 63;
+    if (which < 2 || has_ln) {
+      const int h = col >> 5, cc = col & 31;
+      float s = 0.f;
+#pragma unroll
+      for (int c = 0; c < FU_CTX; ++c)
+#pragma unroll
+        for (int qq = 0; qq < 4; ++qq) s += sRed[((c * 8 + h * 4 + qq) * 4 + which) * 32 + cc];
+      g.vec_partial[(size_t)blockIdx.x * g.vec_len + which * FN + col] = s;
+    }
+  }
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem_base, 512u);
+}
+
+}  // namespace tc
+
+bool tc_bwd_fused_supported(const KParams& p) {
+  const nlam_rowmlp& d = p.d;
+  if (tc::fast_n(p) != tc::FU_FN || !tc::fast_gather(p) || d.n_chunks != 1) return false;
+  for (const float* w : {d.w.w1, d.w.w2})
+    if (((uintptr_t)w) % 16 != 0) return false;
+  return true;
+}
+
+int tc_bwd_fused_grid(const tc::BGeo& g) {
+  int grid = (g.total_tiles + tc::FU_CTX - 1) / tc::FU_CTX;
+  return grid > 148 ? 148 : grid;
+}
+
+int tc_rowmlp_bwd_fused(const KParams& p, const tc::BGeo& g, cudaStream_t st) {
+  static bool attr = false;
+  if (!attr) {
+    NLAM_CUDA(cudaFuncSetAttribute(tc::rowmlp_tc_bwd_fused_kernel,
+                                   cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::FU_SMEM));
+    attr = true;
+  }
+  tc::rowmlp_tc_bwd_fused_kernel<<<tc_bwd_fused_grid(g), tc::FU_NT, tc::FU_SMEM, st>>>(p, g);
+  NLAM_CUDA(cudaGetLastError());
+  count_launch();
+  return 0;
+}
+
+}  // namespace nlam

@@ -388,12 +388,22 @@ def rowmlp_bwd_raw(srcs, W, batch, rows, residual, tiles, precision, g0, need_sr
         fl = 2 * rows_all * (k * W.d_hidden + W.d_hidden * W.d_out)
         shape = f"rows={rows}|K={k}|dh={W.d_hidden}|dout={W.d_out}|B={batch}"
         agg = "_agg" if aligned is not None else ""
-        stages = (
-            (1, f"rowmlp_dgrad_{precision}{agg}|{shape}",
-             src_bytes + w_bytes + rows_all * (4 * W.d_out + 4 * dsrc + img), 2 * fl if dsrc else fl + fl // 2),
-            (2, f"rowmlp_wgrad_{precision}{agg}|{shape}", src_bytes + rows_all * img, fl),
-            (4, f"reduce_params_{precision}|{shape}", 2 * w_bytes, 0),
-        )
+        if lib.nlam_rowmlp_bwd_stages(ctypes.byref(bd.fwd)) == 2:
+            # one kernel: input rows + dOut rows in, per-source gradient rows out; no images
+            stages = (
+                (1, f"rowmlp_bwd_fused_{precision}{agg}|{shape}",
+                 src_bytes + w_bytes + rows_all * (4 * W.d_out + 4 * dsrc),
+                 (3 * fl if dsrc else 2 * fl + fl // 2)),
+                (4, f"reduce_params_{precision}|{shape}", 2 * w_bytes, 0),
+            )
+        else:
+            stages = (
+                (1, f"rowmlp_dgrad_{precision}{agg}|{shape}",
+                 src_bytes + w_bytes + rows_all * (4 * W.d_out + 4 * dsrc + img),
+                 2 * fl if dsrc else fl + fl // 2),
+                (2, f"rowmlp_wgrad_{precision}{agg}|{shape}", src_bytes + rows_all * img, fl),
+                (4, f"reduce_params_{precision}|{shape}", 2 * w_bytes, 0),
+            )
         for mask, tag, nbytes, flops in stages:
             bd.stage_mask = mask
             end = timer.start(tag, nbytes, flops) if timer.want(tag) else None

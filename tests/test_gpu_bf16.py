@@ -98,15 +98,19 @@ def test_interaction_net_bf16_vs_reference_golden(dev, bf16, name):
 
 @pytest.fixture(params=["default", "multi_context", "two_cta"])
 def kernel_choice(request):
-    """Exercise both kernel families of the d=64 path (nlam_set_option)."""
+    """Exercise every kernel family of the d=64 path (nlam_set_option): default =
+    fused backward kernel + automatic forward choice; the other two use the separate
+    input-gradient / weight-gradient kernels."""
     from neural_lam_b200 import lib
-    val = {"default": (-1, 0), "multi_context": (1, 1), "two_cta": (0, 0)}[request.param]
+    val = {"default": (-1, 0, -1), "multi_context": (1, 1, 0), "two_cta": (0, 0, 0)}[request.param]
     l = lib.load()
     l.nlam_set_option(b"fwd_mc", val[0])
     l.nlam_set_option(b"dgrad_mc", val[1])
+    l.nlam_set_option(b"bwd_fused", val[2])
     yield request.param
     l.nlam_set_option(b"fwd_mc", -1)
     l.nlam_set_option(b"dgrad_mc", 0)
+    l.nlam_set_option(b"bwd_fused", -1)
 
 
 @pytest.mark.parametrize("d,M,n_send,n_rec,B,update,aggr", [
@@ -142,9 +146,9 @@ def test_interaction_net_bf16_vs_oracle(dev, bf16, kernel_choice, d, M, n_send, 
         _close(x, y, "output")
     inet_loss(o_ref).backward()
     inet_loss(o).backward()
-    # 225 messages per receiver (M / n_rec) make the aggregated activations ~15x
+    # >= 125 messages per receiver (M / n_rec) make the aggregated activations > 10x
     # larger than the bf16-rounded inputs they came from: 4e-2 there, 2e-2 otherwise
-    tol = 4e-2 if M // n_rec > 128 else TOL
+    tol = 4e-2 if M // n_rec > 100 else TOL
     for x, y, n in zip(b, a, ("send", "rec", "edge")):
         _close(x.grad, y.grad, f"grad {n}", tol=tol)
     for (n, p), (_, q) in zip(ref.named_parameters(), net.named_parameters()):
