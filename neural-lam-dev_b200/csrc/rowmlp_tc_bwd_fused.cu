@@ -2,23 +2,24 @@
 // kernel) for the square 64-wide case (d_hidden = d_out = source widths = 64, one
 // weight set): every InteractionNet edge / node MLP of the d=64 models.
 //
-// One persistent CTA per SM, 544 threads:
-//   * two CONTEXTS of 256 threads, each an independent pipeline over 128-row tiles
-//     (gather z -> GEMM1 -> SiLU -> GEMM2 -> LayerNorm' -> GEMM3 -> SiLU' -> GEMM4 ->
-//     per-source gradient rows), same math as rowmlp_tc_dgrad_kernel;
-//   * one ISSUE warp that feeds the weight-gradient UMMAs
-//        dW2^T += a^T . dY      (when a context has a and dY in shared memory)
-//        dW1^T += z^T . dH      (when it has z and dH)
-//     into ONE set of fp32 TMEM accumulators that lives for the whole kernel.  The
-//     issue thread serves the contexts in a fixed round-robin order (context 0 tile
-//     k, context 1 tile k, context 0 tile k+1, ...): accumulation order -- and so
-//     the result -- is deterministic, and no bf16 tile image ever goes to HBM.
+// One persistent CTA per SM, 512 threads = two CONTEXTS of 256 threads.  Each context
+// is an independent pipeline over 128-row tiles (gather z -> GEMM1 -> SiLU -> GEMM2 ->
+// LayerNorm' -> GEMM3 -> SiLU' -> GEMM4 -> per-source gradient rows; same math as
+// rowmlp_tc_dgrad_kernel) and, with the operands it has in shared memory anyway,
+// also issues the weight-gradient UMMAs of its tile
+//      dW2^T += a^T . dY      (together with GEMM3)
+//      dW1^T += z^T . dH      (together with GEMM4)
+// into its own fp32 TMEM accumulators, which live for the whole kernel: no bf16 tile
+// image ever goes to HBM.  At the end the two contexts' accumulators are added in
+// a fixed order into the CTA's partial slot (deterministic).
 //
-// Shared memory (195 KB): W1 / W2 bf16 operands staged once per SM (32 KB) + per
+// Shared memory (201 KB): W1 / W2 bf16 operands staged once per SM (32 KB) + per
 // context 80 KB = z tile (48 KB, later the fp32 staging of the dZ rows) | a -> dH
 // tile (16 KB) | dOut (bf16, staged coalesced) -> dY tile (16 KB).
-// TMEM (448 of 512 columns): per context H (64) | Y (64), recycled as dA and the
-// double-buffered dZ; shared dW1^T (2 x 64) and dW2^T (64).
+// TMEM (512 columns, 256 per context): H (64) | Y (64), recycled as dA and the
+// double-buffered dZ | dW1^T rows 0..127 (64, M=128) | 64 columns shared by two M=64
+// accumulators -- an M=64 UMMA writes row i to lane 32*(i/16) + i%16, so dW1^T rows
+// 128..191 sit in lanes 0-15 of every 32-lane quarter and dW2^T in lanes 16-31.
 //
 // Reference: autograd of utils.make_mlp / InteractionNet.message / aggr_mlp
 // (utils.py:191-214, interaction_net.py:106,117-121).
@@ -29,7 +30,7 @@ namespace tc {
 
 constexpr int FU_CTX = 2;
 constexpr int FU_CT = 256;                     // threads per context
-constexpr int FU_NT = FU_CTX * FU_CT + 32;     // + the weight-gradient issue warp
+constexpr int FU_NT = FU_CTX * FU_CT;
 constexpr int FU_FN = 64;
 constexpr uint32_t FU_BLK = TM * 128u;         // one 64-column bf16 tile block: 16 KB
 constexpr uint32_t FU_CTXB = 5u * FU_BLK;      // z (3) | a/dH | dOut/dY
@@ -39,13 +40,10 @@ constexpr uint32_t FU_OFF_PAR = FU_OFF_W2 + FU_FN * 128u;
 constexpr uint32_t FU_OFF_LNX = FU_OFF_PAR + 3u * FU_FN * 4u;          // [ctx][4][TM][2] floats
 constexpr uint32_t FU_OFF_BAR = FU_OFF_LNX + FU_CTX * 4u * TM * 2u * 4u;
 constexpr uint32_t FU_SMEM = FU_OFF_BAR + 256u;
-constexpr int FU_NBAR = 7;  // per context: main, dZ0, dZ1, rdy_w2, done_w2, rdy_w1, done_w1
+constexpr int FU_NBAR = 3;  // per context: main, dZ0, dZ1
 
 __device__ __forceinline__ void fu_sync(int ctx) {
   asm volatile("bar.sync %0, 256;" ::"r"(ctx + 1) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ void unpack8(const uint4& q, float* v) {
   v[0] = __uint_as_float(q.x << 16), v[1] = __uint_as_float(q.x & 0xffff0000u);
@@ -60,7 +58,7 @@ rowmlp_tc_bwd_fused_kernel(const __grid_constant__ KParams p, const __grid_const
   if (smem_u32(sm) & 1023u) __trap();
   constexpr int FN = FU_FN;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int ctx = tid >> 8;          // 0, 1: contexts; 2: issue warp
+  const int ctx = tid >> 8;
   const int ltid = tid & 255, lwarp = ltid >> 5;
   uint8_t* sW1 = sm + FU_OFF_W1;
   uint8_t* sW2 = sm + FU_OFF_W2;
@@ -105,53 +103,15 @@ rowmlp_tc_bwd_fused_kernel(const __grid_constant__ KParams p, const __grid_const
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const uint32_t tW1 = tmem_base + 256u;  // dW1^T rows 0..127 | rows 128..191 (+64 columns)
-  const uint32_t tW2 = tmem_base + 384u;
   const int stride = gridDim.x * FU_CTX;
   const int mch = (n_src + 1) / 2;  // 128-row chunks of dW1^T
 
-  // per-thread column sums (context threads only)
+  // per-thread column sums
   float acc_db1[2], acc_db2[2], acc_dg[2], acc_dbt[2];
 #pragma unroll
   for (int i = 0; i < 2; ++i) acc_db1[i] = acc_db2[i] = acc_dg[i] = acc_dbt[i] = 0.f;
 
-  if (ctx == FU_CTX) {
-    // ======================= weight-gradient issue warp =======================
-    if (lane == 0) {
-      const uint32_t idesc_w = make_idesc_bf16(TM, FN, 1, 1);  // A and B viewed MN-major
-      uint32_t ph[FU_CTX] = {0u, 0u};
-      bool first = true;
-      for (int t0 = blockIdx.x * FU_CTX; t0 < g.total_tiles; t0 += stride) {
-#pragma unroll
-        for (int c = 0; c < FU_CTX; ++c) {
-          if (t0 + c >= g.total_tiles) continue;
-          uint64_t* cb = &bars[c * FU_NBAR];
-          const uint32_t z0 = smem_u32(sm + (uint32_t)c * FU_CTXB);
-          const uint32_t a0 = z0 + 3u * FU_BLK, y0 = z0 + 4u * FU_BLK;
-          mbar_wait(&cb[3], ph[c]);  // a and dY are in shared memory
-          tc_fence_after();
-          for (int ks = 0; ks < TM / 16; ++ks)
-            umma_bf16(tW2, make_desc_mn_sw128(a0 + (uint32_t)ks * 2048u, FU_BLK),
-                      make_desc_mn_sw128(y0 + (uint32_t)ks * 2048u, FU_BLK), idesc_w,
-                      (!first || ks > 0) ? 1u : 0u);
-          umma_commit(&cb[4]);
-          mbar_wait(&cb[5], ph[c]);  // dH replaced a; z is still there
-          tc_fence_after();
-          for (int mc = 0; mc < mch; ++mc)
-            for (int ks = 0; ks < TM / 16; ++ks)
-              umma_bf16(tW1 + (uint32_t)(mc * FN),
-                        make_desc_mn_sw128(z0 + (uint32_t)mc * 2u * FU_BLK + (uint32_t)ks * 2048u,
-                                           FU_BLK),
-                        make_desc_mn_sw128(a0 + (uint32_t)ks * 2048u, FU_BLK), idesc_w,
-                        (!first || ks > 0) ? 1u : 0u);
-          umma_commit(&cb[6]);
-          ph[c] ^= 1u;
-          first = false;
-        }
-      }
-    }
-    __syncwarp();
-  } else {
+  {
     // ============================ tile contexts ============================
     uint8_t* sA = sm + (uint32_t)ctx * FU_CTXB;           // z blocks | fp32 dZ staging
     float* stg = reinterpret_cast<float*>(sA);
@@ -161,8 +121,14 @@ rowmlp_tc_bwd_fused_kernel(const __grid_constant__ KParams p, const __grid_const
     uint64_t* cb = &bars[ctx * FU_NBAR];
     uint64_t* bar_m = &cb[0];
     uint64_t* bar_z = &cb[1];
-    const uint32_t tH = tmem_base + (uint32_t)ctx * 128u, tY = tH + 64u;
-    uint32_t ph_m = 0, ph_z = 0, ph_w = 0;
+    const uint32_t tH = tmem_base + (uint32_t)ctx * 256u, tY = tH + 64u;
+    const uint32_t tW1 = tH + 128u;             // dW1^T rows 0..127 (M = 128)
+    const uint32_t tWx = tH + 192u;             // dW1^T rows 128..191 (M = 64, lanes 0-15 of a quarter)
+    const uint32_t tW2 = tWx + (16u << 16);     // dW2^T (M = 64, lanes 16-31 of a quarter)
+    uint32_t ph_m = 0, ph_z = 0;
+    bool first = true;                          // first tile of this context: accumulators start
+    const uint32_t idesc_w128 = make_idesc_bf16(TM, FN, 1, 1);  // A and B viewed MN-major
+    const uint32_t idesc_w64 = make_idesc_bf16(64, FN, 1, 1);
 
     const uint32_t idesc = make_idesc_bf16(TM, FN);
     const uint32_t idesc_mn = make_idesc_bf16(TM, FN, 0, 1);  // B operand viewed MN-major
@@ -419,19 +385,21 @@ rowmlp_tc_bwd_fused_kernel(const __grid_constant__ KParams p, const __grid_const
       tc_fence_before();
       fu_sync(ctx);
 
-      // ---------------- GEMM 3: dA = dY . W2 (into Y's columns); a, dY -> weight-gradient warp
+      // ---------------- GEMM 3: dA = dY . W2 (into Y's columns), and dW2^T += a^T . dY
       if (ltid == 0) {
         tc_fence_after();
-        const uint32_t a0 = smem_u32(sD), w0 = smem_u32(sW2);
+        const uint32_t a0 = smem_u32(sD), w0 = smem_u32(sW2), t0 = smem_u32(sT);
         for (int ks = 0; ks < FN / 16; ++ks)
           umma_bf16(tY, make_desc_k_sw128(a0 + ks * 32),
                     make_desc_mn_sw128(w0 + (uint32_t)ks * 2048u, FN * 128u), idesc_mn, ks > 0);
-        umma_commit(bar_m);
-        mbar_arrive(&cb[3]);
+        for (int ks = 0; ks < TM / 16; ++ks)
+          umma_bf16(tW2, make_desc_mn_sw128(t0 + (uint32_t)ks * 2048u, FU_BLK),
+                    make_desc_mn_sw128(a0 + (uint32_t)ks * 2048u, FU_BLK), idesc_w64,
+                    (!first || ks > 0) ? 1u : 0u);
+        umma_commit(bar_m);  // covers both: the a tile may become dH afterwards
       }
       mbar_wait(bar_m, ph_m);
       ph_m ^= 1;
-      mbar_wait(&cb[4], ph_w);  // dW2 UMMAs have read the a tile: it may become dH
       tc_fence_after();
 
       // ---------------- epilogue 3: dH = dA * SiLU'(H + b1) -> bf16 tile
@@ -456,8 +424,8 @@ rowmlp_tc_bwd_fused_kernel(const __grid_constant__ KParams p, const __grid_const
       tc_fence_before();
       fu_sync(ctx);
 
-      // ---------------- GEMM 4 + epilogue 4: dZ = dH . W1, one source (64 columns) at a
-      // time, double-buffered in the recycled H / Y columns; z, dH -> weight-gradient warp
+      // ---------------- dW1^T += z^T . dH, then GEMM 4 + epilogue 4: dZ = dH . W1, one
+      // source (64 columns) at a time, double-buffered in the recycled H / Y columns
       auto issue_dz = [&](int kb) {
         tc_fence_after();
         const uint32_t a0 = smem_u32(sT);
@@ -468,9 +436,24 @@ rowmlp_tc_bwd_fused_kernel(const __grid_constant__ KParams p, const __grid_const
         umma_commit(&bar_z[kb & 1]);
       };
       if (ltid == 0) {
-        mbar_arrive(&cb[5]);
+        tc_fence_after();
+        const uint32_t z0 = smem_u32(sA), h0 = smem_u32(sT);
+        const uint32_t acc = first ? 0u : 1u;
+        for (int ks = 0; ks < TM / 16; ++ks)  // input columns 0..127 (z blocks 0, 1)
+          umma_bf16(tW1, make_desc_mn_sw128(z0 + (uint32_t)ks * 2048u, FU_BLK),
+                    make_desc_mn_sw128(h0 + (uint32_t)ks * 2048u, FU_BLK), idesc_w128,
+                    (acc || ks > 0) ? 1u : 0u);
+        if (mch > 1)
+          for (int ks = 0; ks < TM / 16; ++ks)  // input columns 128..191 (z block 2)
+            umma_bf16(tWx, make_desc_mn_sw128(z0 + 2u * FU_BLK + (uint32_t)ks * 2048u, FU_BLK),
+                      make_desc_mn_sw128(h0 + (uint32_t)ks * 2048u, FU_BLK), idesc_w64,
+                      (acc || ks > 0) ? 1u : 0u);
+        // UMMAs of one thread complete in order: the first dZ commit also says that z
+        // has been read and its shared memory may become the dZ staging
         if (g.need_dz) issue_dz(0);
+        else umma_commit(bar_m);
       }
+      first = false;
       if (g.need_dz) {
         for (int kb = 0; kb < n_src; ++kb) {
           if (ltid == 0 && kb + 1 < n_src) issue_dz(kb + 1);
@@ -501,7 +484,6 @@ rowmlp_tc_bwd_fused_kernel(const __grid_constant__ KParams p, const __grid_const
           }
           mbar_wait(&bar_z[kb & 1], (ph_z >> (kb & 1)) & 1u);
           ph_z ^= 1u << (kb & 1);
-          if (kb == 0) mbar_wait(&cb[6], ph_w);  // dW1 UMMAs have read z: staging may reuse it
           tc_fence_after();
 #pragma unroll
           for (int ci = 0; ci < 2; ++ci) {
@@ -550,41 +532,50 @@ rowmlp_tc_bwd_fused_kernel(const __grid_constant__ KParams p, const __grid_const
           fu_sync(ctx);
         }
       } else {
-        mbar_wait(&cb[6], ph_w);  // z must outlive the dW1 UMMAs
+        mbar_wait(bar_m, ph_m);  // z and dH must outlive the dW1 UMMAs
+        ph_m ^= 1;
       }
-      ph_w ^= 1;
       tc_fence_before();
       fu_sync(ctx);  // tiles / staging free for the next tile
     }
   }
 
-  // ---------------- accumulators and column sums -> this CTA's partial slot
+  // ---------------- accumulators (context 0 + context 1) and column sums -> this CTA's
+  // partial slot
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   float* sRed = reinterpret_cast<float*>(sm);  // [16 warps][4][32], context 0's dead z tile
-  if (ctx < FU_CTX) {
+  {
     const ParamLayout lay = p.lay;
     float* dst = g.partial + (size_t)blockIdx.x * g.p_total;
     const int q = warp & 3, cq = warp >> 2, r = q * 32 + lane;  // 16 warps: 4 column quarters
     const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
     const int c0 = cq * 16;
-    for (int mc = 0; mc < mch; ++mc) {
-      const int kg = mc * 128 + r;  // input column
-      float v[16];
-      tmem_ld16(tW1 + (uint32_t)(mc * FN) + lane_addr + (uint32_t)c0, v);
+    // a context without tiles (last CTA of a small launch) never wrote its accumulators
+    const bool two = (int)(blockIdx.x * FU_CTX + 1) < g.total_tiles;
+    float v[16], w[16];
+    tmem_ld16(tmem_base + 128u + lane_addr + (uint32_t)c0, v);
+    tmem_ld16(tmem_base + 256u + 128u + lane_addr + (uint32_t)c0, w);
+    if (r < p.k_total) {
+#pragma unroll
+      for (int j = 0; j < 16; ++j)  // input column r of W1
+        dst[lay.off_w1() + (size_t)(c0 + j) * p.k_total + r] = two ? v[j] + w[j] : v[j];
+    }
+    tmem_ld16(tmem_base + 192u + lane_addr + (uint32_t)c0, v);
+    tmem_ld16(tmem_base + 256u + 192u + lane_addr + (uint32_t)c0, w);
+    if (lane < 16) {
+      const int kg = 128 + q * 16 + lane;  // M=64 accumulator: row 16 q + lane
       if (kg < p.k_total) {
 #pragma unroll
-        for (int j = 0; j < 16; ++j) dst[lay.off_w1() + (size_t)(c0 + j) * p.k_total + kg] = v[j];
+        for (int j = 0; j < 16; ++j)
+          dst[lay.off_w1() + (size_t)(c0 + j) * p.k_total + kg] = two ? v[j] + w[j] : v[j];
       }
-    }
-    {
-      float v[16];
-      tmem_ld16(tW2 + lane_addr + (uint32_t)c0, v);
-      if (r < FN) {
+    } else {
+      const int h = q * 16 + lane - 16;  // hidden unit
 #pragma unroll
-        for (int j = 0; j < 16; ++j) dst[lay.off_w2() + (size_t)(c0 + j) * FN + r] = v[j];
-      }
+      for (int j = 0; j < 16; ++j)
+        dst[lay.off_w2() + (size_t)(c0 + j) * FN + h] = two ? v[j] + w[j] : v[j];
     }
     if (lane < 16) {
 #pragma unroll
