@@ -38,7 +38,8 @@ constexpr uint32_t FU_OFF_W1 = FU_CTX * FU_CTXB;
 constexpr uint32_t FU_OFF_W2 = FU_OFF_W1 + 3u * FU_FN * 128u;
 constexpr uint32_t FU_OFF_PAR = FU_OFF_W2 + FU_FN * 128u;
 constexpr uint32_t FU_OFF_LNX = FU_OFF_PAR + 3u * FU_FN * 4u;          // [ctx][4][TM][2] floats
-constexpr uint32_t FU_OFF_BAR = FU_OFF_LNX + FU_CTX * 4u * TM * 2u * 4u;
+constexpr uint32_t FU_OFF_IDX = FU_OFF_LNX + FU_CTX * 4u * TM * 2u * 4u;  // [ctx][2][6][TM] int32
+constexpr uint32_t FU_OFF_BAR = FU_OFF_IDX + FU_CTX * 2u * 6u * TM * 4u;
 constexpr uint32_t FU_SMEM = FU_OFF_BAR + 256u;
 constexpr int FU_NBAR = 3;  // per context: main, dZ0, dZ1
 
@@ -140,11 +141,63 @@ rowmlp_tc_bwd_fused_kernel(const __grid_constant__ KParams p, const __grid_const
     const int k1steps = n_src * FN / 16;
     const int gc = ltid & 7, grl = ltid >> 3;  // gather: 16-byte bf16 chunk / row of a 32-row pass
 
+    // Row indices of a tile are fetched ONE TILE AHEAD by one thread per row and parked in
+    // shared memory ([buffer][src0 | src1 | src2 | g0 row | g1 row | g1 scale][TM]); the same
+    // thread pulls the rows themselves into L2.  The gather / dOut loads of the tile then
+    // start from an LDS instead of a dependent global load.
+    int* sIx = reinterpret_cast<int*>(sm + FU_OFF_IDX) + ctx * (2 * 6 * TM);
+    auto stage_idx = [&](int tn, int* ix) {
+      if (ltid >= TM) return;
+      int r0n, cn, chn;
+      tile_range<TM>(p.d, tn / p.d.batch, r0n, cn, chn);
+      const int bn = tn % p.d.batch;
+      const bool valid = ltid < cn;
+#pragma unroll
+      for (int s = 0; s < NLAM_MAX_SRC; ++s) {
+        if (s < n_src) {
+          const nlam_src& src = p.d.src[s];
+          const int ri = valid ? (src.idx ? __ldg(src.idx + r0n + ltid) : r0n + ltid) : -1;
+          ix[s * TM + ltid] = ri;
+          if (valid) {
+            const char* qq = reinterpret_cast<const char*>(
+                src.ptr + (long long)bn * src.batch_stride + (long long)ri * src.ld);
+            prefetch_l2(qq);
+            prefetch_l2(qq + 128);
+          }
+        }
+      }
+      int g0r = -1, g1r = -1;
+      float sc = 1.f;
+      if (valid && p.g0) {
+        g0r = p.g0_idx ? __ldg(p.g0_idx + r0n + ltid) : r0n + ltid;
+        const float* qq = p.g0 + ((size_t)bn * p.d.rows + g0r) * FN;
+        prefetch_l2(qq);
+        prefetch_l2(qq + 32);
+      }
+      if (valid && p.g1) {
+        g1r = __ldg(p.g1_idx + r0n + ltid);
+        if (p.g1_scale) sc = __ldg(p.g1_scale + g1r);
+        const float* qq = p.g1 + (size_t)bn * p.g1_batch_stride + (size_t)g1r * FN;
+        prefetch_l2(qq);
+        prefetch_l2(qq + 32);
+      }
+      ix[3 * TM + ltid] = g0r;
+      ix[4 * TM + ltid] = g1r;
+      ix[5 * TM + ltid] = __float_as_int(sc);
+    };
+    int pb = 0;
+    {
+      const int t_first = blockIdx.x * FU_CTX + ctx;
+      if (t_first < g.total_tiles) stage_idx(t_first, sIx);
+      fu_sync(ctx);
+    }
+
     for (int t = blockIdx.x * FU_CTX + ctx; t < g.total_tiles; t += stride) {
       const int b = t % p.d.batch, tile = t / p.d.batch;  // batch innermost: shared rows hit L2
       int row0, cnt, chunk;
       tile_range<TM>(p.d, tile, row0, cnt, chunk);
       const size_t grow0 = (size_t)b * p.d.rows + row0;
+      const int* ix = sIx + pb * (6 * TM);
 
       // dOut = g0 rows (+ scale * gathered g1 rows): 4 units (row, 4 columns) per call
       auto dm_load = [&](int base, float4 (&va)[4], float4 (&vb)[4], float (&gs)[4]) {
@@ -154,19 +207,10 @@ rowmlp_tc_bwd_fused_kernel(const __grid_constant__ KParams p, const __grid_const
         for (int j = 0; j < 4; ++j) {
           const int u = base + j * FU_CT, row = u >> 4, col = (u & 15) * 4;
           g0p[j] = g1p[j] = nullptr;
-          gs[j] = 1.f;
-          if (row < cnt) {
-            if (p.g0) {
-              const size_t gr = p.g0_idx ? (size_t)b * p.d.rows + __ldg(p.g0_idx + row0 + row)
-                                         : grow0 + row;
-              g0p[j] = p.g0 + gr * FN + col;
-            }
-            if (p.g1) {
-              const int gi = __ldg(p.g1_idx + row0 + row);
-              if (p.g1_scale) gs[j] = __ldg(p.g1_scale + gi);
-              g1p[j] = p.g1 + (size_t)b * p.g1_batch_stride + (size_t)gi * FN + col;
-            }
-          }
+          const int g0r = ix[3 * TM + row], g1r = ix[4 * TM + row];
+          gs[j] = __int_as_float(ix[5 * TM + row]);
+          if (g0r >= 0) g0p[j] = p.g0 + ((size_t)b * p.d.rows + g0r) * FN + col;
+          if (g1r >= 0) g1p[j] = p.g1 + (size_t)b * p.g1_batch_stride + (size_t)g1r * FN + col;
         }
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
@@ -192,13 +236,9 @@ rowmlp_tc_bwd_fused_kernel(const __grid_constant__ KParams p, const __grid_const
       for (int s = 0; s < n_src; ++s) {
         const nlam_src& src = p.d.src[s];
         const float* base = src.ptr + (long long)b * src.batch_stride + gc * 8;
-        const int32_t* idx = src.idx;
         int ridx[4];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const int row = i * 32 + grl;
-          ridx[i] = row < cnt ? (idx ? __ldg(idx + row0 + row) : row0 + row) : -1;
-        }
+        for (int i = 0; i < 4; ++i) ridx[i] = ix[s * TM + i * 32 + grl];
         float4 x[4], y[4];
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
@@ -237,36 +277,7 @@ rowmlp_tc_bwd_fused_kernel(const __grid_constant__ KParams p, const __grid_const
         dm_load(ltid + 4 * FU_CT, va, vb, gs);
         dm_store(ltid + 4 * FU_CT, va, vb, gs);
       }
-      {
-        const int tn = t + stride;
-        if (tn < g.total_tiles && ltid < TM) {
-          int r0n, cn, chn;
-          tile_range<TM>(p.d, tn / p.d.batch, r0n, cn, chn);
-          const int bn = tn % p.d.batch;
-          if (ltid < cn) {
-            for (int s = 0; s < n_src; ++s) {
-              const nlam_src& src = p.d.src[s];
-              const int ri = src.idx ? __ldg(src.idx + r0n + ltid) : r0n + ltid;
-              const char* qq = reinterpret_cast<const char*>(
-                  src.ptr + (long long)bn * src.batch_stride + (long long)ri * src.ld);
-              prefetch_l2(qq);
-              prefetch_l2(qq + 128);
-            }
-            if (p.g0) {
-              const size_t gr = p.g0_idx ? (size_t)bn * p.d.rows + __ldg(p.g0_idx + r0n + ltid)
-                                         : (size_t)bn * p.d.rows + r0n + ltid;
-              prefetch_l2(p.g0 + gr * FN);
-              prefetch_l2(p.g0 + gr * FN + 32);
-            }
-            if (p.g1) {
-              const int gi = __ldg(p.g1_idx + r0n + ltid);
-              const float* qq = p.g1 + (size_t)bn * p.g1_batch_stride + (size_t)gi * FN;
-              prefetch_l2(qq);
-              prefetch_l2(qq + 32);
-            }
-          }
-        }
-      }
+      if (t + stride < g.total_tiles) stage_idx(t + stride, sIx + (pb ^ 1) * (6 * TM));
       mbar_wait(bar_m, ph_m);
       ph_m ^= 1;
       tc_fence_after();
@@ -476,8 +487,7 @@ rowmlp_tc_bwd_fused_kernel(const __grid_constant__ KParams p, const __grid_const
               const int row = (ltid >> 4) + 16 * i;
               e[i] = make_float4(0.f, 0.f, 0.f, 0.f);
               if (row < cnt) {
-                const size_t gr = p.g0_idx ? (size_t)b * p.d.rows + __ldg(p.g0_idx + row0 + row)
-                                           : grow0 + row;
+                const size_t gr = (size_t)b * p.d.rows + ix[3 * TM + row];
                 e[i] = __ldg(reinterpret_cast<const float4*>(p.g0 + gr * FN) + (ltid & 15));
               }
             }
@@ -535,6 +545,7 @@ rowmlp_tc_bwd_fused_kernel(const __grid_constant__ KParams p, const __grid_const
         mbar_wait(bar_m, ph_m);  // z and dH must outlive the dW1 UMMAs
         ph_m ^= 1;
       }
+      pb ^= 1;
       tc_fence_before();
       fu_sync(ctx);  // tiles / staging free for the next tile
     }
