@@ -38,8 +38,9 @@ constexpr uint32_t FU_OFF_W1 = FU_CTX * FU_CTXB;
 constexpr uint32_t FU_OFF_W2 = FU_OFF_W1 + 3u * FU_FN * 128u;
 constexpr uint32_t FU_OFF_PAR = FU_OFF_W2 + FU_FN * 128u;
 constexpr uint32_t FU_OFF_LNX = FU_OFF_PAR + 3u * FU_FN * 4u;          // [ctx][4][TM][2] floats
-constexpr uint32_t FU_OFF_IDX = FU_OFF_LNX + FU_CTX * 4u * TM * 2u * 4u;  // [ctx][2][6][TM] int32
-constexpr uint32_t FU_OFF_BAR = FU_OFF_IDX + FU_CTX * 2u * 6u * TM * 4u;
+constexpr int FU_IXN = 9 * TM + 136;  // int32 per staged-index buffer (see stage_idx)
+constexpr uint32_t FU_OFF_IDX = FU_OFF_LNX + FU_CTX * 4u * TM * 2u * 4u;  // [ctx][2][FU_IXN]
+constexpr uint32_t FU_OFF_BAR = FU_OFF_IDX + FU_CTX * 2u * FU_IXN * 4u;
 constexpr uint32_t FU_SMEM = FU_OFF_BAR + 256u;
 constexpr int FU_NBAR = 3;  // per context: main, dZ0, dZ1
 
@@ -141,49 +142,88 @@ rowmlp_tc_bwd_fused_kernel(const __grid_constant__ KParams p, const __grid_const
     const int k1steps = n_src * FN / 16;
     const int gc = ltid & 7, grl = ltid >> 3;  // gather: 16-byte bf16 chunk / row of a 32-row pass
 
-    // Row indices of a tile are fetched ONE TILE AHEAD by one thread per row and parked in
-    // shared memory ([buffer][src0 | src1 | src2 | g0 row | g1 row | g1 scale][TM]); the same
-    // thread pulls the rows themselves into L2.  The gather / dOut loads of the tile then
-    // start from an LDS instead of a dependent global load.
-    int* sIx = reinterpret_cast<int*>(sm + FU_OFF_IDX) + ctx * (2 * 6 * TM);
+    // Everything index-like a tile needs is fetched ONE TILE AHEAD, spread over the 256
+    // threads, and parked in shared memory:
+    //   [0..2][TM] source rows   [3][TM] g0 row   [4][TM] g1 row   [5][TM] g1 scale
+    //   [6..8][TM] scatter row of each source gradient (-1: direct)
+    //   [9 TM + 0 / 1] first / last+1 segment of a receiver-aligned tile, then the segment
+    //   boundaries relative to the tile (when it has <= 128 segments).
+    // The same threads pull the rows themselves into L2.  The gather / dOut loads / stores
+    // of the tile then start from an LDS instead of a dependent global load.
+    int* sIx = reinterpret_cast<int*>(sm + FU_OFF_IDX) + ctx * (2 * FU_IXN);
     auto stage_idx = [&](int tn, int* ix) {
-      if (ltid >= TM) return;
       int r0n, cn, chn;
-      tile_range<TM>(p.d, tn / p.d.batch, r0n, cn, chn);
-      const int bn = tn % p.d.batch;
-      const bool valid = ltid < cn;
+      const int tile_n = tn / p.d.batch, bn = tn % p.d.batch;
+      tile_range<TM>(p.d, tile_n, r0n, cn, chn);
+      const int row = ltid & (TM - 1);
+      const bool valid = row < cn;
+      if (ltid < TM) {
+        int ri[NLAM_MAX_SRC];
 #pragma unroll
-      for (int s = 0; s < NLAM_MAX_SRC; ++s) {
-        if (s < n_src) {
-          const nlam_src& src = p.d.src[s];
-          const int ri = valid ? (src.idx ? __ldg(src.idx + r0n + ltid) : r0n + ltid) : -1;
-          ix[s * TM + ltid] = ri;
-          if (valid) {
-            const char* qq = reinterpret_cast<const char*>(
-                src.ptr + (long long)bn * src.batch_stride + (long long)ri * src.ld);
-            prefetch_l2(qq);
-            prefetch_l2(qq + 128);
+        for (int s = 0; s < NLAM_MAX_SRC; ++s) {
+          ri[s] = -1;
+          if (s < n_src && valid) ri[s] = p.d.src[s].idx ? __ldg(p.d.src[s].idx + r0n + row) : r0n + row;
+        }
+#pragma unroll
+        for (int s = 0; s < NLAM_MAX_SRC; ++s) {
+          if (s < n_src) {
+            ix[s * TM + row] = ri[s];
+            if (ri[s] >= 0) {
+              const nlam_src& src = p.d.src[s];
+              const char* qq = reinterpret_cast<const char*>(
+                  src.ptr + (long long)bn * src.batch_stride + (long long)ri[s] * src.ld);
+              prefetch_l2(qq);
+              prefetch_l2(qq + 128);
+            }
+          }
+        }
+      } else {
+        int g0r = -1, g1r = -1, orow[NLAM_MAX_SRC];
+        float sc = 1.f;
+        if (valid && p.g0) g0r = p.g0_idx ? __ldg(p.g0_idx + r0n + row) : r0n + row;
+        if (valid && p.g1) g1r = __ldg(p.g1_idx + r0n + row);
+#pragma unroll
+        for (int s = 0; s < NLAM_MAX_SRC; ++s) {
+          orow[s] = -1;
+          if (s < n_src && valid && p.d_src[s] && p.d_src_idx[s] && s != p.reduce_src)
+            orow[s] = __ldg(p.d_src_idx[s] + r0n + row);
+        }
+        int seg_lo = 0, seg_hi = 0;
+        if (p.reduce_src >= 0) {
+          seg_lo = __ldg(p.d.agg.tile_seg + tile_n);
+          seg_hi = __ldg(p.d.agg.tile_seg + tile_n + 1);
+        }
+        if (g1r >= 0 && p.g1_scale) sc = __ldg(p.g1_scale + g1r);
+        if (g0r >= 0) {
+          const float* qq = p.g0 + ((size_t)bn * p.d.rows + g0r) * FN;
+          prefetch_l2(qq);
+          prefetch_l2(qq + 32);
+        }
+        if (g1r >= 0) {
+          const float* qq = p.g1 + (size_t)bn * p.g1_batch_stride + (size_t)g1r * FN;
+          prefetch_l2(qq);
+          prefetch_l2(qq + 32);
+        }
+        ix[3 * TM + row] = g0r;
+        ix[4 * TM + row] = g1r;
+        ix[5 * TM + row] = __float_as_int(sc);
+#pragma unroll
+        for (int s = 0; s < NLAM_MAX_SRC; ++s) ix[(6 + s) * TM + row] = orow[s];
+        if (p.reduce_src >= 0) {
+          const int nseg = seg_hi - seg_lo;
+          if (row == 0) ix[9 * TM] = seg_lo, ix[9 * TM + 1] = seg_hi;
+          if (nseg <= TM) {
+            if (row <= nseg) ix[9 * TM + 2 + row] = __ldg(p.d.agg.seg_ptr + seg_lo + row) - r0n;
+            if (row == 0) ix[9 * TM + 2 + nseg] = __ldg(p.d.agg.seg_ptr + seg_hi) - r0n;
+            if (row < nseg && p.reduce_accumulate) {  // rows the reduction will read-modify-write
+              const float* qq = p.d_src[p.reduce_src] +
+                                ((size_t)bn * p.d.agg.n_seg + seg_lo + row) * FN;
+              prefetch_l2(qq);
+              prefetch_l2(qq + 32);
+            }
           }
         }
       }
-      int g0r = -1, g1r = -1;
-      float sc = 1.f;
-      if (valid && p.g0) {
-        g0r = p.g0_idx ? __ldg(p.g0_idx + r0n + ltid) : r0n + ltid;
-        const float* qq = p.g0 + ((size_t)bn * p.d.rows + g0r) * FN;
-        prefetch_l2(qq);
-        prefetch_l2(qq + 32);
-      }
-      if (valid && p.g1) {
-        g1r = __ldg(p.g1_idx + r0n + ltid);
-        if (p.g1_scale) sc = __ldg(p.g1_scale + g1r);
-        const float* qq = p.g1 + (size_t)bn * p.g1_batch_stride + (size_t)g1r * FN;
-        prefetch_l2(qq);
-        prefetch_l2(qq + 32);
-      }
-      ix[3 * TM + ltid] = g0r;
-      ix[4 * TM + ltid] = g1r;
-      ix[5 * TM + ltid] = __float_as_int(sc);
     };
     int pb = 0;
     {
@@ -197,7 +237,7 @@ rowmlp_tc_bwd_fused_kernel(const __grid_constant__ KParams p, const __grid_const
       int row0, cnt, chunk;
       tile_range<TM>(p.d, tile, row0, cnt, chunk);
       const size_t grow0 = (size_t)b * p.d.rows + row0;
-      const int* ix = sIx + pb * (6 * TM);
+      const int* ix = sIx + pb * FU_IXN;
 
       // dOut = g0 rows (+ scale * gathered g1 rows): 4 units (row, 4 columns) per call
       auto dm_load = [&](int base, float4 (&va)[4], float4 (&vb)[4], float (&gs)[4]) {
@@ -277,7 +317,7 @@ rowmlp_tc_bwd_fused_kernel(const __grid_constant__ KParams p, const __grid_const
         dm_load(ltid + 4 * FU_CT, va, vb, gs);
         dm_store(ltid + 4 * FU_CT, va, vb, gs);
       }
-      if (t + stride < g.total_tiles) stage_idx(t + stride, sIx + (pb ^ 1) * (6 * TM));
+      if (t + stride < g.total_tiles) stage_idx(t + stride, sIx + (pb ^ 1) * FU_IXN);
       mbar_wait(bar_m, ph_m);
       ph_m ^= 1;
       tc_fence_after();
@@ -471,15 +511,7 @@ rowmlp_tc_bwd_fused_kernel(const __grid_constant__ KParams p, const __grid_const
           float* fdst = p.d_src[kb];
           const bool fres = fdst && (kb == p.d.residual_src) && p.g0;
           const bool reduce = fdst && kb == p.reduce_src;
-          const int32_t* didx = fdst ? p.d_src_idx[kb] : nullptr;
-          int orow_i[8];
-          if (didx && !reduce) {  // scatter targets, fetched while the MMA runs
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              const int row = (ltid >> 4) + 16 * i;
-              orow_i[i] = row < cnt ? __ldg(didx + row0 + row) : 0;
-            }
-          }
+          const bool scat = fdst && p.d_src_idx[kb] != nullptr;  // rows staged in ix[6 + kb]
           float4 e[8];
           if (fres) {  // residual rows requested early
 #pragma unroll
@@ -509,12 +541,13 @@ rowmlp_tc_bwd_fused_kernel(const __grid_constant__ KParams p, const __grid_const
           fu_sync(ctx);
           if (reduce) {
             // receiver-aligned tile: sum the gradient rows of each segment (fixed order)
-            const int seg_lo = __ldg(p.d.agg.tile_seg + tile);
-            const int seg_hi = __ldg(p.d.agg.tile_seg + tile + 1);
+            const int seg_lo = ix[9 * TM], seg_hi = ix[9 * TM + 1];
+            const bool staged = seg_hi - seg_lo <= TM;
+            const int* sp = ix + 9 * TM + 2 - seg_lo;
             float* ro = fdst + (size_t)b * p.d.agg.n_seg * FN + (ltid & 15) * 4;
             for (int seg = seg_lo + (ltid >> 4); seg < seg_hi; seg += 16) {
-              const int r0 = __ldg(p.d.agg.seg_ptr + seg) - row0;
-              const int r1 = __ldg(p.d.agg.seg_ptr + seg + 1) - row0;
+              const int r0 = staged ? sp[seg] : __ldg(p.d.agg.seg_ptr + seg) - row0;
+              const int r1 = staged ? sp[seg + 1] : __ldg(p.d.agg.seg_ptr + seg + 1) - row0;
               float4* o4 = reinterpret_cast<float4*>(ro + (size_t)seg * FN);
               float4 old = make_float4(0.f, 0.f, 0.f, 0.f);
               if (p.reduce_accumulate) old = *o4;
@@ -534,7 +567,7 @@ rowmlp_tc_bwd_fused_kernel(const __grid_constant__ KParams p, const __grid_const
               if (row < cnt) {
                 float4 v = *reinterpret_cast<const float4*>(stg + stg_idx(row, ltid & 15, FN));
                 if (fres) v.x += e[i].x, v.y += e[i].y, v.z += e[i].z, v.w += e[i].w;
-                const size_t orow = didx ? (size_t)b * p.d.rows + orow_i[i] : grow0 + row;
+                const size_t orow = scat ? (size_t)b * p.d.rows + ix[(6 + kb) * TM + row] : grow0 + row;
                 *reinterpret_cast<float4*>(o + orow * FN) = v;
               }
             }
