@@ -204,8 +204,9 @@ size_t nlam_rowmlp_bwd_workspace(const nlam_rowmlp* desc);
 size_t nlam_rowmlp_param_floats(const nlam_rowmlp* desc); /* per chunk */
 /* Kernels nlam_rowmlp_bwd_run launches for this descriptor: 3 = input gradients,
  * weight gradients, partial reduction (stage_mask bits 1, 2, 4); 2 = one fused
- * input + weight gradient kernel (bit 1; bit 2 is a no-op) and the reduction. */
-int nlam_rowmlp_bwd_stages(const nlam_rowmlp* desc);
+ * input + weight gradient kernel (bit 1; bit 2 is a no-op) and the reduction.  The
+ * choice can depend on which source gradients (d_src) the descriptor asks for. */
+int nlam_rowmlp_bwd_stages(const nlam_rowmlp_bwd* desc);
 int nlam_rowmlp_bwd_run(const nlam_rowmlp_bwd* desc, void* stream);
 int nlam_segsum_run(const nlam_segsum* desc, void* stream);
 int64_t nlam_state_step_partials(int64_t rows);

@@ -61,9 +61,10 @@ extern "C" size_t nlam_rowmlp_bwd_workspace(const nlam_rowmlp* d) {
   return simt_rowmlp_bwd_workspace(*d);
 }
 
-extern "C" int nlam_rowmlp_bwd_stages(const nlam_rowmlp* d) {
+extern "C" int nlam_rowmlp_bwd_stages(const nlam_rowmlp_bwd* d) {
   if (!d) return 0;
-  if (d->precision == NLAM_BF16 && tc::tc_supported(*d) && tc_rowmlp_bwd_is_fused(*d)) return 2;
+  if (d->fwd.precision == NLAM_BF16 && tc::tc_supported(d->fwd) && tc_rowmlp_bwd_is_fused(*d))
+    return 2;
   return 3;
 }
 

@@ -854,20 +854,23 @@ static bool use_dgrad_mc(const KParams& p, const BGeo& g) {
 }
 
 // one kernel for input and weight gradients (rowmlp_tc_bwd_fused.cu): square 64-wide MLPs
-static bool use_bwd_fused(const KParams& p) {
-  return option_bwd_fused() != 0 && tc_bwd_fused_supported(p);
+// `need_dz`: -1 unknown (workspace sizing), else whether a source gradient is requested
+static bool use_bwd_fused(const KParams& p, int need_dz) {
+  if (option_bwd_fused() == 0) return false;
+  const int kind = tc_bwd_fused_kind(p);
+  return kind == 2 || (kind == 1 && need_dz == 0);
 }
 
 struct TcBwdWs {
   size_t a_img, dy_img, dh_img, partial, vec_partial, total;  // float offsets
   int d_slots, w_slots;
 };
-static TcBwdWs tc_bwd_ws(const KParams& p, const BGeo& g) {
+static TcBwdWs tc_bwd_ws(const KParams& p, const BGeo& g, bool fused) {
   auto al = [](size_t x) { return (x + 255) / 256 * 256; };
   TcBwdWs w;
   const size_t blk_f = TM * 128 / 4;  // floats per 16 KB block
   size_t o = 0;
-  const bool fused = use_bwd_fused(p);  // no bf16 tile images, one partial slot per CTA
+  // fused: no bf16 tile images, one partial slot per CTA
   w.a_img = o, o += fused ? 0 : al((size_t)g.total_tiles * g.kb2 * blk_f);
   w.dy_img = o, o += fused ? 0 : al((size_t)g.total_tiles * g.kbo * blk_f);
   w.dh_img = o, o += fused ? 0 : al((size_t)g.total_tiles * g.kb2 * blk_f);
@@ -883,10 +886,12 @@ static TcBwdWs tc_bwd_ws(const KParams& p, const BGeo& g) {
 
 }  // namespace tc
 
-bool tc_rowmlp_bwd_is_fused(const nlam_rowmlp& d) {
+bool tc_rowmlp_bwd_is_fused(const nlam_rowmlp_bwd& bd) {
   KParams p{};
-  if (fill_params(d, p)) return false;
-  return tc::use_bwd_fused(p);
+  if (fill_params(bd.fwd, p)) return false;
+  int need_dz = 0;
+  for (int s = 0; s < bd.fwd.n_src; ++s) need_dz |= bd.d_src[s] != nullptr;
+  return tc::use_bwd_fused(p, need_dz);
 }
 
 size_t tc_rowmlp_bwd_workspace(const nlam_rowmlp& d) {
@@ -894,7 +899,14 @@ size_t tc_rowmlp_bwd_workspace(const nlam_rowmlp& d) {
   if (fill_params(d, p)) return 0;
   tc::BGeo g{};
   if (tc::make_bgeo(p, g)) return 0;
-  return tc::tc_bwd_ws(p, g).total;
+  // the kernel choice may depend on which gradients the run asks for: size for either
+  size_t n = 0;
+  if (!tc::use_bwd_fused(p, 1)) n = tc::tc_bwd_ws(p, g, false).total;
+  if (tc::use_bwd_fused(p, 0)) {
+    const size_t m = tc::tc_bwd_ws(p, g, true).total;
+    n = m > n ? m : n;
+  }
+  return n;
 }
 
 int tc_rowmlp_bwd(const nlam_rowmlp_bwd& bd, cudaStream_t st) {
@@ -911,7 +923,10 @@ int tc_rowmlp_bwd(const nlam_rowmlp_bwd& bd, cudaStream_t st) {
   NLAM_CHECK(!bd.g1 || bd.g1_idx, "rowmlp_bwd: g1 needs g1_idx");
   tc::BGeo g{};
   if (tc::make_bgeo(p, g)) return 1;
-  const tc::TcBwdWs ws = tc::tc_bwd_ws(p, g);
+  int want_dz = 0;
+  for (int s = 0; s < d.n_src; ++s) want_dz |= bd.d_src[s] != nullptr;
+  const bool fused = tc::use_bwd_fused(p, want_dz);
+  const tc::TcBwdWs ws = tc::tc_bwd_ws(p, g, fused);
   NLAM_CHECK(bd.workspace && bd.workspace_floats >= ws.total,
              "rowmlp_bwd: workspace too small (%zu < %zu floats)", bd.workspace_floats, ws.total);
   NLAM_CHECK(((uintptr_t)bd.workspace) % 16 == 0, "rowmlp_bwd: workspace must be 16B aligned");
@@ -962,7 +977,7 @@ int tc_rowmlp_bwd(const nlam_rowmlp_bwd& bd, cudaStream_t st) {
   int rc;
   const int mask = bd.stage_mask ? bd.stage_mask : 7;
   const bool dmc = tc::use_dgrad_mc(p, g);
-  if (tc::use_bwd_fused(p)) {  // stage bit 1 covers input AND weight gradients
+  if (fused) {  // stage bit 1 covers input AND weight gradients
     if ((mask & 1) && tc_rowmlp_bwd_fused(p, g, st)) return 1;
     if (!(mask & 4)) return 0;
     return launch_reduce_params(g.partial, ws.w_slots, d.n_chunks, g.p_total, bd.d_params,

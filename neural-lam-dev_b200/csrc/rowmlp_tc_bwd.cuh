@@ -103,7 +103,7 @@ bool tc_dgrad_mc_supported(const KParams& p, const tc::BGeo& g);
 int tc_dgrad_mc_grid(const tc::BGeo& g);
 int tc_rowmlp_dgrad_mc(const KParams& p, const tc::BGeo& g, cudaStream_t st);
 // fused input + weight gradient kernel (rowmlp_tc_bwd_fused.cu)
-bool tc_bwd_fused_supported(const KParams& p);
+int tc_bwd_fused_kind(const KParams& p);  // 0 no, 1 narrow inputs (no source gradients), 2 yes
 int tc_bwd_fused_grid(const tc::BGeo& g);
 int tc_rowmlp_bwd_fused(const KParams& p, const tc::BGeo& g, cudaStream_t st);
 

@@ -54,6 +54,9 @@ __device__ __forceinline__ void unpack8(const uint4& q, float* v) {
   v[6] = __uint_as_float(q.w << 16), v[7] = __uint_as_float(q.w & 0xffff0000u);
 }
 
+// FG = true : every source is 64 wide and 16-byte aligned (vector gather; source gradients)
+// FG = false: arbitrary source widths with k_total <= 64 (embedders; no source gradients)
+template <bool FG>
 __global__ void __launch_bounds__(FU_NT, 1)
 rowmlp_tc_bwd_fused_kernel(const __grid_constant__ KParams p, const __grid_constant__ BGeo g) {
   extern __shared__ __align__(1024) uint8_t sm[];
@@ -76,14 +79,27 @@ rowmlp_tc_bwd_fused_kernel(const __grid_constant__ KParams p, const __grid_const
     mbar_fence_init();
   }
   {  // weights: once per SM
-    const int nch1 = (n_src * FN) >> 3;
-    for (int u = tid; u < FN * nch1; u += FU_NT) {
-      const int n = u / nch1, k0 = (u % nch1) * 8;
-      const float4* q = reinterpret_cast<const float4*>(p.d.w.w1 + (size_t)n * p.k_total + k0);
-      const float4 a = __ldg(q), c = __ldg(q + 1);
-      *reinterpret_cast<uint4*>(sW1 + sw128_off(n, k0, FN * 128u)) =
-          make_uint4(pack_bf16(a.x, a.y), pack_bf16(a.z, a.w), pack_bf16(c.x, c.y),
-                     pack_bf16(c.z, c.w));
+    if constexpr (FG) {
+      const int nch1 = (n_src * FN) >> 3;
+      for (int u = tid; u < FN * nch1; u += FU_NT) {
+        const int n = u / nch1, k0 = (u % nch1) * 8;
+        const float4* q = reinterpret_cast<const float4*>(p.d.w.w1 + (size_t)n * p.k_total + k0);
+        const float4 a = __ldg(q), c = __ldg(q + 1);
+        *reinterpret_cast<uint4*>(sW1 + sw128_off(n, k0, FN * 128u)) =
+            make_uint4(pack_bf16(a.x, a.y), pack_bf16(a.z, a.w), pack_bf16(c.x, c.y),
+                       pack_bf16(c.z, c.w));
+      }
+    } else {  // one 64-column block, zero padded
+      for (int u = tid; u < FN * 8; u += FU_NT) {
+        const int n = u >> 3, k0 = (u & 7) * 8;
+        float v[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          v[j] = k0 + j < p.k_total ? __ldg(p.d.w.w1 + (size_t)n * p.k_total + k0 + j) : 0.f;
+        *reinterpret_cast<uint4*>(sW1 + sw128_off(n, k0, FN * 128u)) =
+            make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]),
+                       pack_bf16(v[6], v[7]));
+      }
     }
     for (int u = tid; u < FN * (FN >> 3); u += FU_NT) {
       const int n = u / (FN >> 3), k0 = (u % (FN >> 3)) * 8;
@@ -106,7 +122,7 @@ rowmlp_tc_bwd_fused_kernel(const __grid_constant__ KParams p, const __grid_const
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   const int stride = gridDim.x * FU_CTX;
-  const int mch = (n_src + 1) / 2;  // 128-row chunks of dW1^T
+  const int mch = FG ? (n_src + 1) / 2 : 1;  // 128-row chunks of dW1^T
 
   // per-thread column sums
   float acc_db1[2], acc_db2[2], acc_dg[2], acc_dbt[2];
@@ -139,7 +155,7 @@ rowmlp_tc_bwd_fused_kernel(const __grid_constant__ KParams p, const __grid_const
     const float* sB1 = sPar;
     const float* sB2 = sPar + FN;
     const float* sG = sPar + 2 * FN;
-    const int k1steps = n_src * FN / 16;
+    const int k1steps = FG ? n_src * FN / 16 : FN / 16;
     const int gc = ltid & 7, grl = ltid >> 3;  // gather: 16-byte bf16 chunk / row of a 32-row pass
 
     // Everything index-like a tile needs is fetched ONE TILE AHEAD, spread over the 256
@@ -173,7 +189,7 @@ rowmlp_tc_bwd_fused_kernel(const __grid_constant__ KParams p, const __grid_const
               const char* qq = reinterpret_cast<const char*>(
                   src.ptr + (long long)bn * src.batch_stride + (long long)ri[s] * src.ld);
               prefetch_l2(qq);
-              prefetch_l2(qq + 128);
+              if (src.width > 32) prefetch_l2(qq + 128);
             }
           }
         }
@@ -273,6 +289,31 @@ rowmlp_tc_bwd_fused_kernel(const __grid_constant__ KParams p, const __grid_const
       };
 
       // ---------------- gather z (all sources) + GEMM 1: H = z . W1^T
+      if constexpr (!FG) {
+        // narrow sources: unit = 8 concatenated input columns of one row (scalar loads)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int u = ltid + i * FU_CT, row = u >> 3, k0 = (u & 7) * 8;
+          float v[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const int k = k0 + j;
+            v[j] = 0.f;
+            if (k < p.k_total) {
+              int sx = 0;
+              while (sx + 1 < n_src && k >= p.koff[sx + 1]) ++sx;
+              const int ri = ix[sx * TM + row];
+              const nlam_src& src = p.d.src[sx];
+              if (ri >= 0)
+                v[j] = __ldg(src.ptr + (long long)b * src.batch_stride + (long long)ri * src.ld +
+                             (k - p.koff[sx]));
+            }
+          }
+          *reinterpret_cast<uint4*>(sA + sw128_off(row, k0, FU_BLK)) =
+              make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]),
+                         pack_bf16(v[6], v[7]));
+        }
+      } else
       for (int s = 0; s < n_src; ++s) {
         const nlam_src& src = p.d.src[s];
         const float* base = src.ptr + (long long)b * src.batch_stride + gc * 8;
@@ -501,11 +542,11 @@ rowmlp_tc_bwd_fused_kernel(const __grid_constant__ KParams p, const __grid_const
                       (acc || ks > 0) ? 1u : 0u);
         // UMMAs of one thread complete in order: the first dZ commit also says that z
         // has been read and its shared memory may become the dZ staging
-        if (g.need_dz) issue_dz(0);
+        if (FG && g.need_dz) issue_dz(0);
         else umma_commit(bar_m);
       }
       first = false;
-      if (g.need_dz) {
+      if (FG && g.need_dz) {
         for (int kb = 0; kb < n_src; ++kb) {
           if (ltid == 0 && kb + 1 < n_src) issue_dz(kb + 1);
           float* fdst = p.d_src[kb];
@@ -651,12 +692,14 @@ rowmlp_tc_bwd_fused_kernel(const __grid_constant__ KParams p, const __grid_const
 
 }  // namespace tc
 
-bool tc_bwd_fused_supported(const KParams& p) {
+// 2: every source 64 wide (source gradients supported); 1: narrow inputs (k_total <= 64),
+// only when no source gradient is requested; 0: not eligible
+int tc_bwd_fused_kind(const KParams& p) {
   const nlam_rowmlp& d = p.d;
-  if (tc::fast_n(p) != tc::FU_FN || !tc::fast_gather(p) || d.n_chunks != 1) return false;
-  for (const float* w : {d.w.w1, d.w.w2})
-    if (((uintptr_t)w) % 16 != 0) return false;
-  return true;
+  if (tc::fast_n(p) != tc::FU_FN || d.n_chunks != 1) return 0;
+  if (((uintptr_t)d.w.w2) % 16 != 0) return 0;
+  if (tc::fast_gather(p)) return ((uintptr_t)d.w.w1) % 16 == 0 ? 2 : 0;
+  return p.k_total <= 64 ? 1 : 0;
 }
 
 int tc_bwd_fused_grid(const tc::BGeo& g) {
@@ -667,11 +710,16 @@ int tc_bwd_fused_grid(const tc::BGeo& g) {
 int tc_rowmlp_bwd_fused(const KParams& p, const tc::BGeo& g, cudaStream_t st) {
   static bool attr = false;
   if (!attr) {
-    NLAM_CUDA(cudaFuncSetAttribute(tc::rowmlp_tc_bwd_fused_kernel,
+    NLAM_CUDA(cudaFuncSetAttribute(tc::rowmlp_tc_bwd_fused_kernel<true>,
+                                   cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::FU_SMEM));
+    NLAM_CUDA(cudaFuncSetAttribute(tc::rowmlp_tc_bwd_fused_kernel<false>,
                                    cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::FU_SMEM));
     attr = true;
   }
-  tc::rowmlp_tc_bwd_fused_kernel<<<tc_bwd_fused_grid(g), tc::FU_NT, tc::FU_SMEM, st>>>(p, g);
+  if (tc_bwd_fused_kind(p) == 2)
+    tc::rowmlp_tc_bwd_fused_kernel<true><<<tc_bwd_fused_grid(g), tc::FU_NT, tc::FU_SMEM, st>>>(p, g);
+  else
+    tc::rowmlp_tc_bwd_fused_kernel<false><<<tc_bwd_fused_grid(g), tc::FU_NT, tc::FU_SMEM, st>>>(p, g);
   NLAM_CUDA(cudaGetLastError());
   count_launch();
   return 0;

@@ -126,7 +126,7 @@ SYMBOLS = {
     "nlam_rowmlp_fwd": (ctypes.c_int, [ctypes.POINTER(RowMlp), ctypes.c_void_p]),
     "nlam_rowmlp_bwd_workspace": (ctypes.c_size_t, [ctypes.POINTER(RowMlp)]),
     "nlam_rowmlp_param_floats": (ctypes.c_size_t, [ctypes.POINTER(RowMlp)]),
-    "nlam_rowmlp_bwd_stages": (ctypes.c_int, [ctypes.POINTER(RowMlp)]),
+    "nlam_rowmlp_bwd_stages": (ctypes.c_int, [ctypes.POINTER(RowMlpBwd)]),
     "nlam_rowmlp_bwd_run": (ctypes.c_int, [ctypes.POINTER(RowMlpBwd), ctypes.c_void_p]),
     "nlam_segsum_run": (ctypes.c_int, [ctypes.POINTER(SegSum), ctypes.c_void_p]),
     "nlam_state_step_partials": (ctypes.c_int64, [ctypes.c_int64]),

@@ -388,7 +388,7 @@ def rowmlp_bwd_raw(srcs, W, batch, rows, residual, tiles, precision, g0, need_sr
         fl = 2 * rows_all * (k * W.d_hidden + W.d_hidden * W.d_out)
         shape = f"rows={rows}|K={k}|dh={W.d_hidden}|dout={W.d_out}|B={batch}"
         agg = "_agg" if aligned is not None else ""
-        if lib.nlam_rowmlp_bwd_stages(ctypes.byref(bd.fwd)) == 2:
+        if lib.nlam_rowmlp_bwd_stages(ctypes.byref(bd)) == 2:
             # one kernel: input rows + dOut rows in, per-source gradient rows out; no images
             stages = (
                 (1, f"rowmlp_bwd_fused_{precision}{agg}|{shape}",
