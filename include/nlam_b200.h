@@ -126,7 +126,9 @@ typedef struct nlam_rowmlp_bwd {
   int32_t stage_mask;     /* 0 = everything; else bit 0: input-gradient kernel, bit 1:
                              weight-gradient kernel, bit 2: partial reduction (lets a
                              profiler time the three launches separately; the stages
-                             must run in this order on the same workspace) */
+                             must run in this order on the same workspace); bit 3
+                             (value 8, alone = everything): queue the partial reduction
+                             for nlam_rowmlp_bwd_flush instead of launching it */
 } nlam_rowmlp_bwd;
 
 /* out[b,i,:] (+)= scale[i] * sum_{p in [ptr[i],ptr[i+1])} src[b, idx[p], :]
@@ -208,6 +210,13 @@ size_t nlam_rowmlp_param_floats(const nlam_rowmlp* desc); /* per chunk */
  * choice can depend on which source gradients (d_src) the descriptor asks for. */
 int nlam_rowmlp_bwd_stages(const nlam_rowmlp_bwd* desc);
 int nlam_rowmlp_bwd_run(const nlam_rowmlp_bwd* desc, void* stream);
+/* Deferred parameter-gradient reductions.  A run with stage_mask bit 3 (value 8) set
+ * does not launch its own partial reduction but queues it (process-wide, thread
+ * safe); nlam_rowmlp_bwd_flush runs every queued reduction in ONE launch on `stream`
+ * (which must be ordered after the runs).  The caller keeps the runs' workspaces and
+ * d_params alive until the flush.  nlam_rowmlp_bwd_pending = queued reductions. */
+int nlam_rowmlp_bwd_flush(void* stream);
+int nlam_rowmlp_bwd_pending(void);
 int nlam_segsum_run(const nlam_segsum* desc, void* stream);
 int64_t nlam_state_step_partials(int64_t rows);
 int nlam_state_step_fwd(const nlam_state_step* desc, void* stream);

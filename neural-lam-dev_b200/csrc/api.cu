@@ -83,3 +83,8 @@ extern "C" int nlam_rowmlp_bwd_run(const nlam_rowmlp_bwd* d, void* stream) {
   set_error("rowmlp_bwd: unknown precision mode %d", d->fwd.precision);
   return 1;
 }
+
+extern "C" int nlam_rowmlp_bwd_flush(void* stream) {
+  return reduce_params_flush((cudaStream_t)stream);
+}
+extern "C" int nlam_rowmlp_bwd_pending(void) { return reduce_params_pending(); }

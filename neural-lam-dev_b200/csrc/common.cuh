@@ -76,5 +76,7 @@ int tc_rowmlp_fwd(const nlam_rowmlp& d, cudaStream_t st);
 int tc_rowmlp_bwd(const nlam_rowmlp_bwd& d, cudaStream_t st);
 size_t tc_rowmlp_bwd_workspace(const nlam_rowmlp& d);
 bool tc_rowmlp_bwd_is_fused(const nlam_rowmlp_bwd& d);
+int reduce_params_flush(cudaStream_t st);  // rowmlp_simt.cu: deferred partial reductions
+int reduce_params_pending();
 
 }  // namespace nlam

@@ -17,6 +17,10 @@
 // .message / aggr_mlp (interaction_net.py:106,117-121), SplitMLPs (:134-163).
 #include <math.h>
 
+#include <algorithm>
+#include <mutex>
+#include <vector>
+
 #include "rowmlp_common.cuh"
 
 namespace nlam {
@@ -604,14 +608,13 @@ struct RParams {
   int vec_slots, vec_len;
   ParamLayout lay;
 };
-__global__ void __launch_bounds__(256) reduce_params_kernel(const __grid_constant__ RParams p) {
+__device__ __forceinline__ void reduce_params_block(const RParams& p, int bx, int chunk) {
   // Block = 32 consecutive output elements (coalesced 128-byte rows of the partial
   // matrix) x 8 warps; warp w sums partials w, w+8, ...; the 8 sub-sums are then
   // combined in a fixed order (deterministic).
   __shared__ float red[8][33];
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  const int j = blockIdx.x * 32 + lane;
-  const int chunk = blockIdx.y;
+  const int j = bx * 32 + lane;
   float s = 0.f;
   if (j < p.p_total) {
     int v = -1;
@@ -647,21 +650,93 @@ __global__ void __launch_bounds__(256) reduce_params_kernel(const __grid_constan
     *o = p.accumulate ? *o + t : t;
   }
 }
+__global__ void __launch_bounds__(256) reduce_params_kernel(const __grid_constant__ RParams p) {
+  reduce_params_block(p, blockIdx.x, blockIdx.y);
+}
+
+// Deferred reductions (stage_mask bit 8): the jobs of many backward calls are queued on
+// the host and run by ONE launch (nlam_rowmlp_bwd_flush) -- the per-MLP reductions are
+// ~7 us kernels whose launch gaps and tails would otherwise add up over 19 MLPs.
+constexpr int RB_MAX = 28;
+struct RBatch {
+  int n;
+  int blk_off[RB_MAX + 1];
+  RParams job[RB_MAX];
+};
+static_assert(sizeof(RBatch) <= 4000, "RBatch must fit the kernel parameter space");
+__global__ void __launch_bounds__(256) reduce_params_batch_kernel(const __grid_constant__ RBatch b) {
+  int j = 0;
+  while (j + 1 < b.n && (int)blockIdx.x >= b.blk_off[j + 1]) ++j;
+  const RParams& p = b.job[j];
+  const int local = blockIdx.x - b.blk_off[j];
+  const int bpc = (p.p_total + 31) / 32;
+  reduce_params_block(p, local % bpc, local / bpc);
+}
+
+// g_rq[w] = wave w: reductions into distinct outputs (one launch); a reduction that
+// accumulates into an output already queued (weights used several times in a step,
+// e.g. an unrolled rollout) goes to the next wave, so the order of accumulation is
+// that of the immediate mode
+static std::mutex g_rq_mutex;
+static std::vector<std::vector<RParams>> g_rq;
+static int queue_or_launch_reduce(const RParams& rp, bool defer, cudaStream_t st) {
+  if (defer) {
+    std::lock_guard<std::mutex> lk(g_rq_mutex);
+    size_t wave = 0;
+    for (size_t w = 0; w < g_rq.size(); ++w)
+      for (const RParams& q : g_rq[w])
+        if (q.out == rp.out) wave = w + 1;
+    if (wave >= g_rq.size()) g_rq.resize(wave + 1);
+    g_rq[wave].push_back(rp);
+    return 0;
+  }
+  dim3 rgrid((rp.p_total + 31) / 32, rp.n_chunks);
+  reduce_params_kernel<<<rgrid, 256, 0, st>>>(rp);
+  NLAM_CUDA(cudaGetLastError());
+  count_launch();
+  return 0;
+}
+int reduce_params_flush(cudaStream_t st) {
+  std::vector<std::vector<RParams>> waves;
+  {
+    std::lock_guard<std::mutex> lk(g_rq_mutex);
+    waves.swap(g_rq);
+  }
+  for (const std::vector<RParams>& jobs : waves)
+  for (size_t i = 0; i < jobs.size(); i += RB_MAX) {
+    RBatch b{};
+    b.n = (int)std::min<size_t>(RB_MAX, jobs.size() - i);
+    int off = 0;
+    for (int j = 0; j < b.n; ++j) {
+      b.job[j] = jobs[i + j];
+      b.blk_off[j] = off;
+      off += (b.job[j].p_total + 31) / 32 * b.job[j].n_chunks;
+    }
+    b.blk_off[b.n] = off;
+    if (off == 0) continue;
+    reduce_params_batch_kernel<<<off, 256, 0, st>>>(b);
+    NLAM_CUDA(cudaGetLastError());
+    count_launch();
+  }
+  return 0;
+}
+int reduce_params_pending() {
+  std::lock_guard<std::mutex> lk(g_rq_mutex);
+  size_t n = 0;
+  for (const auto& w : g_rq) n += w.size();
+  return (int)n;
+}
 
 int launch_reduce_params(const float* partial, int splits, int n_chunks, int p_total, float* out,
                          int accumulate, const float* vec_partial, int vec_slots, int vec_len,
-                         ParamLayout lay, cudaStream_t st) {
+                         ParamLayout lay, cudaStream_t st, bool defer) {
   RParams rp{};
   rp.accumulate = accumulate;
   rp.vec_partial = vec_partial, rp.vec_slots = vec_slots, rp.vec_len = vec_len, rp.lay = lay;
   rp.partial = partial, rp.splits = splits, rp.n_chunks = n_chunks;
   rp.p_total = p_total, rp.p_main = p_total;
   rp.out = out;
-  dim3 rgrid((p_total + 31) / 32, n_chunks);
-  reduce_params_kernel<<<rgrid, 256, 0, st>>>(rp);
-  NLAM_CUDA(cudaGetLastError());
-  count_launch();
-  return 0;
+  return queue_or_launch_reduce(rp, defer, st);
 }
 
 // -------------------------------------------------------------------- host side
@@ -758,12 +833,7 @@ static int launch_bwd(const KParams& p, const WParams& wp, const RParams& rp, in
     NLAM_CUDA(cudaGetLastError());
     count_launch();
   }
-  if (mask & 4) {
-    dim3 rgrid((rp.p_total + 31) / 32, rp.n_chunks);
-    reduce_params_kernel<<<rgrid, 256, 0, st>>>(rp);
-    NLAM_CUDA(cudaGetLastError());
-    count_launch();
-  }
+  if (mask & 4) return queue_or_launch_reduce(rp, (mask & 8) != 0, st);
   return 0;
 }
 
@@ -831,7 +901,7 @@ int simt_rowmlp_bwd(const nlam_rowmlp_bwd& bd, cudaStream_t st) {
   rp.accumulate = bd.params_accumulate;
 
   const int dp = pick_dp(d);
-  const int mask = bd.stage_mask ? bd.stage_mask : 7;
+  const int mask = (bd.stage_mask & 7) ? bd.stage_mask : (7 | (bd.stage_mask & 8));
   switch (dp) {
     case 16: return launch_bwd<16>(p, wp, rp, mask, st);
     case 32: return launch_bwd<32>(p, wp, rp, mask, st);

@@ -26,7 +26,7 @@ namespace nlam {
 // defined in rowmlp_simt.cu
 int launch_reduce_params(const float* partial, int splits, int n_chunks, int p_total,
                          float* out, int accumulate, const float* vec_partial, int vec_slots,
-                         int vec_len, ParamLayout lay, cudaStream_t st);
+                         int vec_len, ParamLayout lay, cudaStream_t st, bool defer);
 
 namespace tc {
 
@@ -975,14 +975,14 @@ int tc_rowmlp_bwd(const nlam_rowmlp_bwd& bd, cudaStream_t st) {
   const bool fg = tc::fast_gather(p);
   static int md[5] = {0, 0, 0, 0, 0}, mw[5] = {0, 0, 0, 0, 0};
   int rc;
-  const int mask = bd.stage_mask ? bd.stage_mask : 7;
+  const int mask = (bd.stage_mask & 7) ? bd.stage_mask : (7 | (bd.stage_mask & 8));
   const bool dmc = tc::use_dgrad_mc(p, g);
   if (fused) {  // stage bit 1 covers input AND weight gradients
     if ((mask & 1) && tc_rowmlp_bwd_fused(p, g, st)) return 1;
     if (!(mask & 4)) return 0;
     return launch_reduce_params(g.partial, ws.w_slots, d.n_chunks, g.p_total, bd.d_params,
                                 bd.params_accumulate, g.vec_partial, ws.d_slots, g.vec_len, p.lay,
-                                st);
+                                st, (mask & 8) != 0);
   }
 #define NLAM_BWD_PAIR(FNV, FGV, I)                                                          \
   rc = 0;                                                                                   \
@@ -1006,7 +1006,8 @@ int tc_rowmlp_bwd(const nlam_rowmlp_bwd& bd, cudaStream_t st) {
   if (rc) return rc;
   if (!(mask & 4)) return 0;
   return launch_reduce_params(g.partial, ws.w_slots, d.n_chunks, g.p_total, bd.d_params,
-                              bd.params_accumulate, g.vec_partial, ws.d_slots, g.vec_len, p.lay, st);
+                              bd.params_accumulate, g.vec_partial, ws.d_slots, g.vec_len, p.lay, st,
+                              (mask & 8) != 0);
 }
 
 }  // namespace nlam

@@ -128,6 +128,8 @@ SYMBOLS = {
     "nlam_rowmlp_param_floats": (ctypes.c_size_t, [ctypes.POINTER(RowMlp)]),
     "nlam_rowmlp_bwd_stages": (ctypes.c_int, [ctypes.POINTER(RowMlpBwd)]),
     "nlam_rowmlp_bwd_run": (ctypes.c_int, [ctypes.POINTER(RowMlpBwd), ctypes.c_void_p]),
+    "nlam_rowmlp_bwd_flush": (ctypes.c_int, [ctypes.c_void_p]),
+    "nlam_rowmlp_bwd_pending": (ctypes.c_int, []),
     "nlam_segsum_run": (ctypes.c_int, [ctypes.POINTER(SegSum), ctypes.c_void_p]),
     "nlam_state_step_partials": (ctypes.c_int64, [ctypes.c_int64]),
     "nlam_state_step_fwd": (ctypes.c_int, [ctypes.POINTER(StateStep), ctypes.c_void_p]),

@@ -41,6 +41,27 @@ def set_param_grad_sink(enabled):
     _state["grad_sink"] = bool(enabled)
 
 
+def set_deferred_param_reduce(enabled):
+    """Queue the per-MLP partial reductions of the parameter gradients and run them in
+    one launch when `flush_param_grads()` is called (the trainer does, right after
+    `loss.backward()`).  Off by default: with plain `loss.backward()` +
+    `optimizer.step()` nobody would call the flush."""
+    if not enabled:
+        flush_param_grads()
+    _state["defer_reduce"] = bool(enabled)
+
+
+_deferred_keep = []  # workspaces / gradient buffers of queued reductions
+
+
+def flush_param_grads():
+    """Run every queued parameter-gradient reduction (one kernel) on the current stream."""
+    lib = L.load()
+    if lib.nlam_rowmlp_bwd_pending() > 0:
+        L.check(lib.nlam_rowmlp_bwd_flush(_stream()), "nlam_rowmlp_bwd_flush")
+    _deferred_keep.clear()
+
+
 def _grad_sink(params):
     """Flat destination tensor for an MLP's parameter gradients, or None."""
     if not _state.get("grad_sink", False):
@@ -374,6 +395,11 @@ def rowmlp_bwd_raw(srcs, W, batch, rows, residual, tiles, precision, g0, need_sr
     keep.extend([g0, g1, ws])
     timer = _timer["t"]
     if timer is None:
+        # deferred reduction only when the gradients go to the sink: autograd must not
+        # hand out a d_params tensor whose values do not exist yet
+        if _state.get("defer_reduce", False) and sink is not None:
+            bd.stage_mask = 8
+            _deferred_keep.append((ws, sink))
         L.check(lib.nlam_rowmlp_bwd_run(ctypes.byref(bd), _stream()), "nlam_rowmlp_bwd_run")
     else:
         # time the three launches separately (stage_mask) with CUDA events.

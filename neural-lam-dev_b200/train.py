@@ -16,6 +16,8 @@ import os
 import torch
 import torch.distributed as dist
 
+from . import ops
+
 
 def init_distributed():
     """Read RANK/LOCAL_RANK/WORLD_SIZE/MASTER_* (torchrun) and set the device.
@@ -83,6 +85,7 @@ class FlatGradBuckets:
             return grad
         if self.overlap and self._early_work is None and not self._early_started:
             self._early_started = True
+            ops.flush_param_grads()  # the early bucket's gradients must be final
             self._launch_early()
         return grad
 
@@ -153,8 +156,10 @@ class DataParallelTrainer:
         # weight gradients go straight into the flat buffer (no per-parameter
         # accumulation kernels); autograd then never "sees" them, so the early
         # all-reduce is triggered by the backward of the encoder output instead
-        from . import ops
         ops.set_param_grad_sink(True)
+        # ... and their per-MLP partial reductions are queued and run by one launch
+        # (ops.flush_param_grads) after backward / before the early all-reduce
+        ops.set_deferred_param_reduce(True)
         if self.buckets.overlap and hasattr(model, "g2m_gnn"):
             model.g2m_gnn.register_forward_hook(self._encoder_output_hook)
 
@@ -168,6 +173,7 @@ class DataParallelTrainer:
         self.buckets.zero()
         loss = self.model.training_step(batch)
         loss.backward()
+        ops.flush_param_grads()  # queued parameter-gradient reductions: one launch
         return loss.detach()
 
     def _eager_step(self, batch):

@@ -37,11 +37,16 @@ def test_grad_sink_equals_autograd(dev):
     loss.backward()
     want = {n: p.grad.clone() for n, p in model.named_parameters()}
     model2, _ = _model(dev)
-    trainer = train.DataParallelTrainer(model2)  # enables the sink
+    trainer = train.DataParallelTrainer(model2)  # enables the sink + deferred reductions
     trainer.buckets.zero()
     loss2 = model2.training_step(batch)
     loss2.backward()
+    from neural_lam_b200 import lib
+    assert lib.load().nlam_rowmlp_bwd_pending() > 0  # queued, not yet reduced
+    ops.flush_param_grads()
+    assert lib.load().nlam_rowmlp_bwd_pending() == 0
     ops.set_param_grad_sink(False)
+    ops.set_deferred_param_reduce(False)
     assert torch.equal(loss, loss2)
     for n, p in model2.named_parameters():
         torch.testing.assert_close(p.grad, want[n], rtol=1e-6, atol=1e-7, msg=n)
@@ -59,6 +64,7 @@ def test_trainer_paths_agree(dev, graph):
     host = tuple(t.cpu().pin_memory() for t in batch)
     lb = tb.fit_from_host([host] * 3)
     ops.set_param_grad_sink(False)
+    ops.set_deferred_param_reduce(False)
     assert la == pytest.approx(lb, rel=1e-5)
     assert la[2] < la[0]  # it trains
     for p, q in zip(model_a.parameters(), model_b.parameters()):
