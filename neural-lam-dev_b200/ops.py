@@ -408,9 +408,20 @@ def rowmlp_bwd_raw(srcs, W, batch, rows, residual, tiles, precision, g0, need_sr
         k = sum(t.shape[2] for t, _ in srcs)
         src_bytes = sum(_src_bytes(t, i, batch) for t, i in srcs)
         w_bytes = 4 * W.n_chunks * W.param_floats()
+        rows_all = batch * rows
+        # output-gradient rows read: dense g0 rows + the DISTINCT gathered g1 rows
+        dout_bytes = (rows_all * 4 * W.d_out if g0 is not None else 0) \
+            + (4 * g1.numel() if g1 is not None else 0)
+        # source-gradient rows written: one row per (batch, row) and source, except the
+        # segment-reduced source (read-modify-write of its [batch, n_seg, width] target)
+        dsrc_bytes = 0
+        for i, ((t, _), need) in enumerate(zip(srcs, need_src)):
+            if need and i == reduce_src:
+                dsrc_bytes += 2 * 4 * reduce_into.numel()
+            elif need:
+                dsrc_bytes += rows_all * 4 * t.shape[2]
         dsrc = sum(t.shape[2] for (t, _), n in zip(srcs, need_src) if n)
         img = 2 * (2 * W.d_hidden + W.d_out) if precision == "bf16" else 4 * (2 * W.d_hidden + W.d_out)
-        rows_all = batch * rows
         fl = 2 * rows_all * (k * W.d_hidden + W.d_hidden * W.d_out)
         shape = f"rows={rows}|K={k}|dh={W.d_hidden}|dout={W.d_out}|B={batch}"
         agg = "_agg" if aligned is not None else ""
@@ -418,14 +429,14 @@ def rowmlp_bwd_raw(srcs, W, batch, rows, residual, tiles, precision, g0, need_sr
             # one kernel: input rows + dOut rows in, per-source gradient rows out; no images
             stages = (
                 (1, f"rowmlp_bwd_fused_{precision}{agg}|{shape}",
-                 src_bytes + w_bytes + rows_all * (4 * W.d_out + 4 * dsrc),
+                 src_bytes + w_bytes + dout_bytes + dsrc_bytes,
                  (3 * fl if dsrc else 2 * fl + fl // 2)),
                 (4, f"reduce_params_{precision}|{shape}", 2 * w_bytes, 0),
             )
         else:
             stages = (
                 (1, f"rowmlp_dgrad_{precision}{agg}|{shape}",
-                 src_bytes + w_bytes + rows_all * (4 * W.d_out + 4 * dsrc + img),
+                 src_bytes + w_bytes + dout_bytes + dsrc_bytes + rows_all * img,
                  2 * fl if dsrc else fl + fl // 2),
                 (2, f"rowmlp_wgrad_{precision}{agg}|{shape}", src_bytes + rows_all * img, fl),
                 (4, f"reduce_params_{precision}|{shape}", 2 * w_bytes, 0),
