@@ -133,8 +133,9 @@ rowmlp_tc_bwd_fused_kernel(const __grid_constant__ KParams p, const __grid_const
     // ============================ tile contexts ============================
     uint8_t* sA = sm + (uint32_t)ctx * FU_CTXB;           // z blocks | fp32 dZ staging
     float* stg = reinterpret_cast<float*>(sA);
-    uint8_t* sT = sA + 3u * FU_BLK;                        // a -> dH
-    uint8_t* sD = sA + 4u * FU_BLK;                        // dOut (bf16) -> dY
+    uint8_t* sD = sA + 3u * FU_BLK;                        // dOut (bf16) -> dY
+    uint8_t* sT = sA + 4u * FU_BLK;                        // a -> dH
+    // dZ staging: two fp32 [128][64] buffers = blocks 0-1 and 2-3 (z and dY are dead by then)
     float* sLnx = reinterpret_cast<float*>(sm + FU_OFF_LNX) + ctx * (4 * TM * 2);
     uint64_t* cb = &bars[ctx * FU_NBAR];
     uint64_t* bar_m = &cb[0];
@@ -409,22 +410,26 @@ rowmlp_tc_bwd_fused_kernel(const __grid_constant__ KParams p, const __grid_const
         }
         float rstd = 1.f, m1 = 0.f, m2 = 0.f;
         if (has_ln) {
+          // mean / variance of the 64-wide row from the two 32-column halves with ONE
+          // exchange: each half sends (sum, sum of squared deviations from its own mean),
+          // combined with the pairwise update of Chan et al. (two-pass accuracy)
           float s = 0.f;
 #pragma unroll
           for (int j = 0; j < 32; ++j) s += y[j];
-          sLnx[(0 * TM + r) * 2 + hf] = s;
-          fu_sync(ctx);
-          const float mean = (sLnx[(0 * TM + r) * 2] + sLnx[(0 * TM + r) * 2 + 1]) * (1.0f / FN);
-          float qq = 0.f;
+          const float mh = s * (1.0f / 32);
+          float qh = 0.f;
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            y[j] -= mean;
-            qq += y[j] * y[j];
-          }
-          sLnx[(1 * TM + r) * 2 + hf] = qq;
+          for (int j = 0; j < 32; ++j) qh += (y[j] - mh) * (y[j] - mh);
+          sLnx[(0 * TM + r) * 2 + hf] = s;
+          sLnx[(1 * TM + r) * 2 + hf] = qh;
           fu_sync(ctx);
-          rstd = rsqrtf((sLnx[(1 * TM + r) * 2] + sLnx[(1 * TM + r) * 2 + 1]) * (1.0f / FN) +
-                        LN_EPS);
+          const float so = sLnx[(0 * TM + r) * 2 + (hf ^ 1)], qo = sLnx[(1 * TM + r) * 2 + (hf ^ 1)];
+          const float mean = (s + so) * (1.0f / FN);
+          const float dlt = (s - so) * (1.0f / 32);  // difference of the half means
+          const float var = (qh + qo + dlt * dlt * 16.0f) * (1.0f / FN);
+          rstd = rsqrtf(var + LN_EPS);
+#pragma unroll
+          for (int j = 0; j < 32; ++j) y[j] -= mean;
           float s1 = 0.f, s2 = 0.f;
 #pragma unroll
           for (int ci = 0; ci < 2; ++ci) {
@@ -568,6 +573,8 @@ rowmlp_tc_bwd_fused_kernel(const __grid_constant__ KParams p, const __grid_const
           mbar_wait(&bar_z[kb & 1], (ph_z >> (kb & 1)) & 1u);
           ph_z ^= 1u << (kb & 1);
           tc_fence_after();
+          // double-buffered staging: block kb+1 is written while stragglers still read kb
+          float* stgk = stg + (kb & 1) * (TM * FN);
 #pragma unroll
           for (int ci = 0; ci < 2; ++ci) {
             const int c0 = hf * 32 + ci * 16;
@@ -575,7 +582,7 @@ rowmlp_tc_bwd_fused_kernel(const __grid_constant__ KParams p, const __grid_const
             tmem_ld16(((kb & 1) ? tY : tH) + lane_addr + (uint32_t)c0, v);
 #pragma unroll
             for (int j4 = 0; j4 < 4; ++j4)
-              *reinterpret_cast<float4*>(stg + stg_idx(r, (c0 >> 2) + j4, FN)) =
+              *reinterpret_cast<float4*>(stgk + stg_idx(r, (c0 >> 2) + j4, FN)) =
                   make_float4(v[j4 * 4], v[j4 * 4 + 1], v[j4 * 4 + 2], v[j4 * 4 + 3]);
           }
           tc_fence_before();
@@ -594,7 +601,7 @@ rowmlp_tc_bwd_fused_kernel(const __grid_constant__ KParams p, const __grid_const
               if (p.reduce_accumulate) old = *o4;
               float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
               for (int rr = r0; rr < r1; ++rr) {
-                const float4 v = *reinterpret_cast<const float4*>(stg + stg_idx(rr, ltid & 15, FN));
+                const float4 v = *reinterpret_cast<const float4*>(stgk + stg_idx(rr, ltid & 15, FN));
                 acc.x += v.x, acc.y += v.y, acc.z += v.z, acc.w += v.w;
               }
               acc.x += old.x, acc.y += old.y, acc.z += old.z, acc.w += old.w;
@@ -606,14 +613,13 @@ rowmlp_tc_bwd_fused_kernel(const __grid_constant__ KParams p, const __grid_const
             for (int i = 0; i < 8; ++i) {
               const int row = (ltid >> 4) + 16 * i;
               if (row < cnt) {
-                float4 v = *reinterpret_cast<const float4*>(stg + stg_idx(row, ltid & 15, FN));
+                float4 v = *reinterpret_cast<const float4*>(stgk + stg_idx(row, ltid & 15, FN));
                 if (fres) v.x += e[i].x, v.y += e[i].y, v.z += e[i].z, v.w += e[i].w;
                 const size_t orow = scat ? (size_t)b * p.d.rows + ix[(6 + kb) * TM + row] : grow0 + row;
                 *reinterpret_cast<float4*>(o + orow * FN) = v;
               }
             }
           }
-          fu_sync(ctx);
         }
       } else {
         mbar_wait(bar_m, ph_m);  // z and dH must outlive the dW1 UMMAs
