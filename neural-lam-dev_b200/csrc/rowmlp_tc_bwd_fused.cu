@@ -72,6 +72,7 @@ rowmlp_tc_bwd_fused_kernel(const __grid_constant__ KParams p, const __grid_const
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + FU_CTX * FU_NBAR);
   const bool has_ln = p.d.w.ln_g != nullptr;
   const int n_src = p.d.n_src;
+  const int dout = p.d.d_out;  // < 64 only without LayerNorm (output maps): zero-padded to 64
 
   if (warp == 0) tmem_alloc(tmem_slot, 512u);
   if (tid == 32) {
@@ -103,8 +104,11 @@ rowmlp_tc_bwd_fused_kernel(const __grid_constant__ KParams p, const __grid_const
     }
     for (int u = tid; u < FN * (FN >> 3); u += FU_NT) {
       const int n = u / (FN >> 3), k0 = (u % (FN >> 3)) * 8;
-      const float4* q = reinterpret_cast<const float4*>(p.d.w.w2 + (size_t)n * FN + k0);
-      const float4 a = __ldg(q), c = __ldg(q + 1);
+      float4 a = make_float4(0.f, 0.f, 0.f, 0.f), c = a;
+      if (n < dout) {
+        const float4* q = reinterpret_cast<const float4*>(p.d.w.w2 + (size_t)n * FN + k0);
+        a = __ldg(q), c = __ldg(q + 1);
+      }
       *reinterpret_cast<uint4*>(sW2 + sw128_off(n, k0, FN * 128u)) =
           make_uint4(pack_bf16(a.x, a.y), pack_bf16(a.z, a.w), pack_bf16(c.x, c.y),
                      pack_bf16(c.z, c.w));
@@ -112,7 +116,7 @@ rowmlp_tc_bwd_fused_kernel(const __grid_constant__ KParams p, const __grid_const
     for (int i = tid; i < 3 * FN; i += FU_NT) {
       const int j = i % FN, which = i / FN;
       sPar[i] = which == 0 ? __ldg(p.d.w.b1 + j)
-                : which == 1 ? __ldg(p.d.w.b2 + j)
+                : which == 1 ? (j < dout ? __ldg(p.d.w.b2 + j) : 0.f)
                              : (has_ln ? __ldg(p.d.w.ln_g + j) : 1.f);
     }
   }
@@ -125,9 +129,13 @@ rowmlp_tc_bwd_fused_kernel(const __grid_constant__ KParams p, const __grid_const
   const int mch = FG ? (n_src + 1) / 2 : 1;  // 128-row chunks of dW1^T
 
   // per-thread column sums
-  float acc_db1[2], acc_db2[2], acc_dg[2], acc_dbt[2];
+  float acc_db1[2], acc_db2[2], acc_dg[2];
 #pragma unroll
-  for (int i = 0; i < 2; ++i) acc_db1[i] = acc_db2[i] = acc_dg[i] = acc_dbt[i] = 0.f;
+  for (int i = 0; i < 2; ++i) acc_db1[i] = acc_db2[i] = acc_dg[i] = 0.f;
+  // column sums of the dOut rows in fp32, BEFORE they are rounded to bf16 (LayerNorm beta
+  // gradient; b2 gradient of an MLP without LayerNorm): this thread's 4 columns
+  // (ltid & 15) * 4 .. + 3 of the rows it loads
+  float acc_dm[4] = {0.f, 0.f, 0.f, 0.f};
 
   {
     // ============================ tile contexts ============================
@@ -212,12 +220,12 @@ rowmlp_tc_bwd_fused_kernel(const __grid_constant__ KParams p, const __grid_const
         }
         if (g1r >= 0 && p.g1_scale) sc = __ldg(p.g1_scale + g1r);
         if (g0r >= 0) {
-          const float* qq = p.g0 + ((size_t)bn * p.d.rows + g0r) * FN;
+          const float* qq = p.g0 + ((size_t)bn * p.d.rows + g0r) * dout;
           prefetch_l2(qq);
           prefetch_l2(qq + 32);
         }
         if (g1r >= 0) {
-          const float* qq = p.g1 + (size_t)bn * p.g1_batch_stride + (size_t)g1r * FN;
+          const float* qq = p.g1 + (size_t)bn * p.g1_batch_stride + (size_t)g1r * dout;
           prefetch_l2(qq);
           prefetch_l2(qq + 32);
         }
@@ -266,15 +274,31 @@ rowmlp_tc_bwd_fused_kernel(const __grid_constant__ KParams p, const __grid_const
           g0p[j] = g1p[j] = nullptr;
           const int g0r = ix[3 * TM + row], g1r = ix[4 * TM + row];
           gs[j] = __int_as_float(ix[5 * TM + row]);
-          if (g0r >= 0) g0p[j] = p.g0 + ((size_t)b * p.d.rows + g0r) * FN + col;
-          if (g1r >= 0) g1p[j] = p.g1 + (size_t)b * p.g1_batch_stride + (size_t)g1r * FN + col;
+          if (g0r >= 0) g0p[j] = p.g0 + ((size_t)b * p.d.rows + g0r) * dout + col;
+          if (g1r >= 0) g1p[j] = p.g1 + (size_t)b * p.g1_batch_stride + (size_t)g1r * dout + col;
         }
+        if (dout == FN) {
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          va[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-          vb[j] = va[j];
-          if (g0p[j]) va[j] = __ldg(reinterpret_cast<const float4*>(g0p[j]));
-          if (g1p[j]) vb[j] = __ldg(reinterpret_cast<const float4*>(g1p[j]));
+          for (int j = 0; j < 4; ++j) {
+            va[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+            vb[j] = va[j];
+            if (g0p[j]) va[j] = __ldg(reinterpret_cast<const float4*>(g0p[j]));
+            if (g1p[j]) vb[j] = __ldg(reinterpret_cast<const float4*>(g1p[j]));
+          }
+        } else {  // narrow output rows (stride dout floats): scalar loads, zero padding
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const int col = ((base + j * FU_CT) & 15) * 4;
+            float t0[4] = {0.f, 0.f, 0.f, 0.f}, t1[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+            for (int e = 0; e < 4; ++e)
+              if (col + e < dout) {
+                if (g0p[j]) t0[e] = __ldg(g0p[j] + e);
+                if (g1p[j]) t1[e] = __ldg(g1p[j] + e);
+              }
+            va[j] = make_float4(t0[0], t0[1], t0[2], t0[3]);
+            vb[j] = make_float4(t1[0], t1[1], t1[2], t1[3]);
+          }
         }
       };
       auto dm_store = [&](int base, const float4 (&va)[4], const float4 (&vb)[4],
@@ -282,9 +306,10 @@ rowmlp_tc_bwd_fused_kernel(const __grid_constant__ KParams p, const __grid_const
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           const int u = base + j * FU_CT, row = u >> 4, c4 = u & 15;
-          const uint2 pk = make_uint2(
-              pack_bf16(va[j].x + gs[j] * vb[j].x, va[j].y + gs[j] * vb[j].y),
-              pack_bf16(va[j].z + gs[j] * vb[j].z, va[j].w + gs[j] * vb[j].w));
+          const float d0 = va[j].x + gs[j] * vb[j].x, d1 = va[j].y + gs[j] * vb[j].y;
+          const float d2 = va[j].z + gs[j] * vb[j].z, d3 = va[j].w + gs[j] * vb[j].w;
+          acc_dm[0] += d0, acc_dm[1] += d1, acc_dm[2] += d2, acc_dm[3] += d3;
+          const uint2 pk = make_uint2(pack_bf16(d0, d1), pack_bf16(d2, d3));
           *reinterpret_cast<uint2*>(sD + sw128_off(row, (c4 >> 1) * 8, FU_BLK) + (c4 & 1) * 8) = pk;
         }
       };
@@ -447,7 +472,6 @@ rowmlp_tc_bwd_fused_kernel(const __grid_constant__ KParams p, const __grid_const
               s2 += dyh * yh;
             }
             acc_dg[ci] += warp_colsum16(pv, lane);
-            acc_dbt[ci] += warp_colsum16(dmv, lane);
           }
           sLnx[(2 * TM + r) * 2 + hf] = s1;
           sLnx[(3 * TM + r) * 2 + hf] = s2;
@@ -468,7 +492,7 @@ rowmlp_tc_bwd_fused_kernel(const __grid_constant__ KParams p, const __grid_const
               v[j] = r < cnt ? rstd * (dyh - m1 - y[ci * 16 + j] * m2) : 0.f;
             }
           }
-          acc_db2[ci] += warp_colsum16(v, lane);
+          if (has_ln) acc_db2[ci] += warp_colsum16(v, lane);  // else: db2 = fp32 sum of dOut
 #pragma unroll
           for (int h8 = 0; h8 < 2; ++h8)
             *reinterpret_cast<uint4*>(sD + sw128_off(r, c0 + h8 * 8, FU_BLK)) =
@@ -666,7 +690,7 @@ rowmlp_tc_bwd_fused_kernel(const __grid_constant__ KParams p, const __grid_const
       const int h = q * 16 + lane - 16;  // hidden unit
 #pragma unroll
       for (int j = 0; j < 16; ++j)
-        dst[lay.off_w2() + (size_t)(c0 + j) * FN + h] = two ? v[j] + w[j] : v[j];
+        if (c0 + j < dout) dst[lay.off_w2() + (size_t)(c0 + j) * FN + h] = two ? v[j] + w[j] : v[j];
     }
     if (lane < 16) {
 #pragma unroll
@@ -674,21 +698,30 @@ rowmlp_tc_bwd_fused_kernel(const __grid_constant__ KParams p, const __grid_const
         sRed[(warp * 4 + 0) * 32 + i * 16 + lane] = acc_db1[i];
         sRed[(warp * 4 + 1) * 32 + i * 16 + lane] = acc_db2[i];
         sRed[(warp * 4 + 2) * 32 + i * 16 + lane] = acc_dg[i];
-        sRed[(warp * 4 + 3) * 32 + i * 16 + lane] = acc_dbt[i];
       }
     }
+    // fp32 dOut column sums: [32 row groups (context, ltid >> 4)][64 columns]
+    float* sDm = sRed + 16 * 4 * 32;
+#pragma unroll
+    for (int e = 0; e < 4; ++e) sDm[(tid >> 4) * 64 + (tid & 15) * 4 + e] = acc_dm[e];
   }
   tc_fence_before();
   __syncthreads();
   if (tid < 4 * FN) {
     const int which = tid >> 6, col = tid & 63;
-    if (which < 2 || has_ln) {
+    if ((which < 2 || has_ln) && (which == 0 || col < dout)) {
       const int h = col >> 5, cc = col & 31;
       float s = 0.f;
+      // dLN beta, and db2 without LayerNorm (dY == dOut): the fp32 sums of the dOut rows
+      if (which == 3 || (which == 1 && !has_ln)) {
+        const float* sDm = sRed + 16 * 4 * 32;
+        for (int gI = 0; gI < 32; ++gI) s += sDm[gI * 64 + col];
+      } else {
 #pragma unroll
-      for (int c = 0; c < FU_CTX; ++c)
+        for (int c = 0; c < FU_CTX; ++c)
 #pragma unroll
-        for (int qq = 0; qq < 4; ++qq) s += sRed[((c * 8 + h * 4 + qq) * 4 + which) * 32 + cc];
+          for (int qq = 0; qq < 4; ++qq) s += sRed[((c * 8 + h * 4 + qq) * 4 + which) * 32 + cc];
+      }
       g.vec_partial[(size_t)blockIdx.x * g.vec_len + which * FN + col] = s;
     }
   }
@@ -702,8 +735,15 @@ rowmlp_tc_bwd_fused_kernel(const __grid_constant__ KParams p, const __grid_const
 // only when no source gradient is requested; 0: not eligible
 int tc_bwd_fused_kind(const KParams& p) {
   const nlam_rowmlp& d = p.d;
-  if (tc::fast_n(p) != tc::FU_FN || d.n_chunks != 1) return 0;
-  if (((uintptr_t)d.w.w2) % 16 != 0) return 0;
+  if (d.n_chunks != 1 || ((uintptr_t)d.w.w2) % 16 != 0) return 0;
+  if (d.d_hidden == tc::FU_FN && d.d_out < tc::FU_FN && d.d_out >= 1) {
+    // narrow output without LayerNorm / residual (output maps): 64-wide vector sources only
+    if (d.w.ln_g || d.residual_src >= 0 || ((uintptr_t)d.w.w1) % 16 != 0) return 0;
+    for (int s = 0; s < d.n_src; ++s)
+      if (d.src[s].width != tc::FU_FN || !p.vec_ok[s]) return 0;
+    return 2;
+  }
+  if (tc::fast_n(p) != tc::FU_FN) return 0;
   if (tc::fast_gather(p)) return ((uintptr_t)d.w.w1) % 16 == 0 ? 2 : 0;
   return p.k_total <= 64 ? 1 : 0;
 }

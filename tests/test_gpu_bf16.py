@@ -52,6 +52,8 @@ def _close(a, b, what, tol=TOL):
     ([3, 64, 64], True, 1000, 1), ([56, 64, 64], True, 700, 2), ([64, 64, 17], False, 513, 2),
     ([128, 128, 128], True, 300, 2), ([32, 32, 32], True, 64, 1), ([16, 16, 16], True, 200, 1),
     ([64, 64, 64], True, 129, 3),
+    ([64, 64, 34], False, 40000, 2),  # narrow-output fused backward, many tiles per context
+    ([64, 64, 1], False, 300, 1), ([64, 64, 63], False, 257, 2),
 ])
 def test_mlp_bf16(dev, bf16, blueprint, ln, rows, B):
     from neural_lam_b200 import utils
