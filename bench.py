@@ -44,8 +44,15 @@ def parse():
     ap.add_argument("--batch", type=int, default=4, help="samples per GPU per step")
     ap.add_argument("--hidden-dim", type=int, default=64)
     ap.add_argument("--processor-layers", type=int, default=4)
-    ap.add_argument("--graph", default="1level", choices=["1level", "multiscale"],
-                    help="mesh graph (BASELINE configs[1] = 1level; configs[2] = multiscale)")
+    ap.add_argument("--graph", default="1level", choices=["1level", "multiscale", "hierarchical"],
+                    help="mesh graph (BASELINE configs[1] = 1level; configs[2] = multiscale; "
+                         "configs[3], [4] = hierarchical)")
+    ap.add_argument("--model", default="graph_lam",
+                    choices=["graph_lam", "hi_lam", "hi_lam_parallel"],
+                    help="model family (hi_lam / hi_lam_parallel need --graph hierarchical)")
+    ap.add_argument("--ar-steps", type=int, default=1, help="rollout steps per sample")
+    ap.add_argument("--scale", type=int, default=1,
+                    help="domain scale of the synthetic MEPS grid (2 = 536x476, configs[4])")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cuda-graph", type=int, default=1,
                     help="replay the train step as one CUDA graph (single-GPU runs)")
@@ -55,23 +62,30 @@ def parse():
 def make_case(root, a):
     from neural_lam_b200 import create_graph, synthetic
 
-    ds = synthetic.meps_datastore(root, seed=0)
+    ds = synthetic.meps_datastore(root, scale=a.scale, seed=0)
     args = synthetic.ModelArgs(hidden_dim=a.hidden_dim, processor_layers=a.processor_layers,
                                graph=a.graph, loss="wmse")
     create_graph.create_graph(os.path.join(root, "graph", a.graph),
                               ds.get_xy("state", stacked=False),
                               n_max_levels=1 if a.graph == "1level" else None,
-                              hierarchical=False)
+                              hierarchical=a.graph == "hierarchical")
     return ds, args
+
+
+def is_default_case(a):
+    return (a.hidden_dim, a.processor_layers, a.graph, a.model, a.ar_steps, a.scale) == \
+        (64, 4, "1level", "graph_lam", 1, 1)
 
 
 def config_dict(a, extra=None):
     workload = WORKLOAD
-    if (a.hidden_dim, a.processor_layers, a.graph) != (64, 4, "1level"):
-        workload = (f"GraphLAM {a.graph} mesh, hidden_dim={a.hidden_dim}, {a.processor_layers} "
-                    "processor layers, synthetic MEPS 268x238 grid, 17 state vars, ar_steps=1")
+    if not is_default_case(a):
+        workload = (f"{a.model} on the {a.graph} mesh, hidden_dim={a.hidden_dim}, "
+                    f"{a.processor_layers} processor layers, synthetic MEPS "
+                    f"{268 * a.scale}x{238 * a.scale} grid, 17 state vars, ar_steps={a.ar_steps}")
     cfg = {"workload": workload, "global_batch": a.batch * a.gpus, "batch_per_gpu": a.batch,
-           "ar_steps": 1, "hidden_dim": a.hidden_dim, "processor_layers": a.processor_layers,
+           "ar_steps": a.ar_steps, "hidden_dim": a.hidden_dim,
+           "processor_layers": a.processor_layers,
            "parallelism": f"dp{a.gpus}" if a.gpus > 1 else "single"}
     if extra:
         cfg.update(extra)
@@ -146,9 +160,9 @@ def time_cpu_oracle(a, steps, warmup):
     with tempfile.TemporaryDirectory() as root:
         ds, args = make_case(root, a)
         torch.manual_seed(42)
-        model = port.GraphLAM(args, None, ds)
+        model = port.MODELS[a.model](args, None, ds)
     opt = model.configure_optimizers()
-    batch = synthetic.synthetic_batch(ds, 1, 1, seed=1)
+    batch = synthetic.synthetic_batch(ds, 1, a.ar_steps, seed=1)
     times = []
     for i in range(warmup + steps):
         t0 = time.perf_counter()
@@ -255,7 +269,7 @@ def run_ours(a):
     with tempfile.TemporaryDirectory() as root:
         ds, args = make_case(root, a)
         torch.manual_seed(42)
-        model = models.GraphLAM(args, nl_config.default_config(), ds)
+        model = models.MODELS[a.model](args, nl_config.default_config(), ds)
     model = model.to(device)
     use_graph = bool(a.cuda_graph)
     trainer = train.DataParallelTrainer(model, rank, world, use_cuda_graph=False)
@@ -263,7 +277,7 @@ def run_ours(a):
     # rotating set of distinct batches, > 2x L2 in total, so that no step finds its
     # inputs in L2 from the previous one (activations per step are GBs anyway)
     n_rot = 4
-    host = [synthetic.synthetic_batch(ds, a.batch, 1, seed=1000 * rank + i, pin_memory=True)
+    host = [synthetic.synthetic_batch(ds, a.batch, a.ar_steps, seed=1000 * rank + i, pin_memory=True)
             for i in range(n_rot)]
     dev_batches = [tuple(t.to(device) for t in hb) for hb in host]
     in_bytes = sum(t.numel() * t.element_size() for t in host[0])
@@ -378,7 +392,8 @@ def run_ours(a):
     if rank == 0 and world == 1:
         ops.set_param_grad_sink(False)
         ops.set_deferred_param_reduce(False)
-        layers = layer_edges_per_s(model, a.batch, device)
+        if a.model == "graph_lam":  # per-layer figure on the model's own g2m / m2m / m2g layers
+            layers = layer_edges_per_s(model, a.batch, device)
 
     cpu = None
     if rank == 0 and world == 1 and not a.no_cpu_baseline:
