@@ -8,7 +8,10 @@ def mask_and_reduce_metric(metric_entry_vals, mask, average_grid, sum_vars):
     """metrics.py:21-53: keep masked grid nodes, mean over grid (dim -2), then
     sum over variables (dim -1)."""
     if mask is not None:
-        metric_entry_vals = metric_entry_vals[..., mask, :]
+        if mask.dtype == torch.bool:
+            metric_entry_vals = metric_entry_vals[..., mask, :]
+        else:  # int64 node indices (== mask.nonzero()): same rows, no device->host sync
+            metric_entry_vals = metric_entry_vals.index_select(-2, mask)
     if average_grid:
         metric_entry_vals = torch.mean(metric_entry_vals, dim=-2)
     if sum_vars:

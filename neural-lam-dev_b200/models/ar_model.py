@@ -62,6 +62,17 @@ class ARModel(nn.Module):
     def interior_mask_bool(self):
         return self.interior_mask[:, 0].to(torch.bool)
 
+    @property
+    def interior_index(self):
+        """Indices of the interior grid nodes (== interior_mask_bool.nonzero()), cached:
+        the metrics accept them in place of the boolean mask and then run without the
+        device->host sync of boolean indexing (CUDA-graph capturable eval rollout)."""
+        idx = getattr(self, "_interior_index", None)
+        if idx is None or idx.device != self.interior_mask.device:
+            idx = self.interior_mask_bool.nonzero().squeeze(1)
+            self._interior_index = idx
+        return idx
+
     @staticmethod
     def expand_to_batch(x, batch_size):
         """Stride-0 batch view (ar_model.py:204-209)."""
@@ -94,6 +105,37 @@ class ARModel(nn.Module):
         prediction, pred_std = self.unroll_prediction(init_states, forcing_features,
                                                       target_states)
         return prediction, target_states, pred_std, batch_times
+
+    @torch.no_grad()
+    def validation_step(self, batch, batch_idx=0):
+        """ar_model.py:324-361 without the Lightning logging: forward-only rollout through
+        the same kernels; returns ({"val_loss_unroll{k}", "val_mean_loss"}, entry MSEs
+        (B, pred_steps, d_f)) -- what the reference logs / appends to `val_metrics`."""
+        prediction, target, pred_std, _ = self.common_step(batch)
+        mask = self.interior_index
+        time_step_loss = torch.mean(self.loss(prediction, target, pred_std, mask=mask), dim=0)
+        log = {f"val_loss_unroll{step}": time_step_loss[step - 1]
+               for step in self.args.val_steps_to_log if step <= len(time_step_loss)}
+        log["val_mean_loss"] = torch.mean(time_step_loss)
+        return log, metrics.mse(prediction, target, pred_std, mask=mask, sum_vars=False)
+
+    @torch.no_grad()
+    def test_step(self, batch, batch_idx=0):
+        """ar_model.py:375-435 without logging / plotting: ({"test_loss_unroll{k}",
+        "test_mean_loss"}, {"mse", "mae" [, "output_std"]: (B, pred_steps, d_f)}, spatial
+        loss maps (B, len(val_steps_to_log), num_grid_nodes))."""
+        prediction, target, pred_std, _ = self.common_step(batch)
+        mask = self.interior_index
+        time_step_loss = torch.mean(self.loss(prediction, target, pred_std, mask=mask), dim=0)
+        log = {f"test_loss_unroll{step}": time_step_loss[step - 1]
+               for step in self.args.val_steps_to_log}
+        log["test_mean_loss"] = torch.mean(time_step_loss)
+        entry = {name: metrics.get_metric(name)(prediction, target, pred_std, mask=mask,
+                                                sum_vars=False) for name in ("mse", "mae")}
+        if self.output_std:
+            entry["output_std"] = torch.mean(pred_std.index_select(-2, mask), dim=-2)
+        spatial = self.loss(prediction, target, pred_std, average_grid=False)
+        return log, entry, spatial[:, [step - 1 for step in self.args.val_steps_to_log]]
 
     def training_step(self, batch):
         """Mean over batch and unrolled steps of the masked loss (ar_model.py:287-309)."""

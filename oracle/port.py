@@ -122,25 +122,36 @@ class _Chain(nn.Module):
 
 
 # ------------------------------------------------------------------ metrics.py
-def wmse(pred, target, pred_std, mask=None):
-    """metrics.py:56-84 + 21-53 with average_grid=True, sum_vars=True."""
-    v = (pred - target) ** 2 / (pred_std**2)
+def _reduce(v, mask, average_grid, sum_vars):
+    """metrics.py:21-53: mask the grid nodes, mean over the grid, sum over variables."""
     if mask is not None:
         v = v[..., mask, :]
-    return v.mean(dim=-2).sum(dim=-1)
+    if average_grid:
+        v = v.mean(dim=-2)
+    if sum_vars:
+        v = v.sum(dim=-1)
+    return v
 
 
-def mse(pred, target, pred_std, mask=None):
+def wmse(pred, target, pred_std, mask=None, average_grid=True, sum_vars=True):
+    """metrics.py:56-84."""
+    return _reduce((pred - target) ** 2 / (pred_std**2), mask, average_grid, sum_vars)
+
+
+def mse(pred, target, pred_std, mask=None, average_grid=True, sum_vars=True):
     """metrics.py:87-113 (weights replaced by ones)."""
-    return wmse(pred, target, torch.ones_like(pred_std), mask)
+    return wmse(pred, target, torch.ones_like(pred_std), mask, average_grid, sum_vars)
 
 
-def nll(pred, target, pred_std, mask=None):
+def mae(pred, target, pred_std, mask=None, average_grid=True, sum_vars=True):
+    """metrics.py:142-163."""
+    return _reduce((pred - target).abs(), mask, average_grid, sum_vars)
+
+
+def nll(pred, target, pred_std, mask=None, average_grid=True, sum_vars=True):
     """metrics.py:176-201: Gaussian negative log-likelihood."""
     v = -torch.distributions.Normal(pred, pred_std).log_prob(target)
-    if mask is not None:
-        v = v[..., mask, :]
-    return v.mean(dim=-2).sum(dim=-1)
+    return _reduce(v, mask, average_grid, sum_vars)
 
 
 class _BufList(nn.Module):
@@ -245,6 +256,33 @@ class ARModel(nn.Module):
         pred, pred_std = self.unroll_prediction(init_states, forcing, target)
         mask = self.interior_mask[:, 0].to(torch.bool)
         return torch.mean(self.loss(pred, target, pred_std, mask=mask))
+
+    def validation_step(self, batch):
+        """ar_model.py:324-361 without the Lightning logging: ({name: value}, entry MSEs
+        (B, pred_steps, d_f))."""
+        init_states, target, forcing, _ = batch
+        pred, pred_std = self.unroll_prediction(init_states, forcing, target)
+        mask = self.interior_mask[:, 0].to(torch.bool)
+        time_step_loss = torch.mean(self.loss(pred, target, pred_std, mask=mask), dim=0)
+        log = {f"val_loss_unroll{step}": time_step_loss[step - 1]
+               for step in self.args.val_steps_to_log if step <= len(time_step_loss)}
+        log["val_mean_loss"] = torch.mean(time_step_loss)
+        return log, mse(pred, target, pred_std, mask=mask, sum_vars=False)
+
+    def test_step(self, batch):
+        """ar_model.py:375-435 without logging / plotting: ({name: value}, {"mse", "mae":
+        (B, pred_steps, d_f)}, spatial loss maps (B, N_log, num_grid_nodes))."""
+        init_states, target, forcing, _ = batch
+        pred, pred_std = self.unroll_prediction(init_states, forcing, target)
+        mask = self.interior_mask[:, 0].to(torch.bool)
+        time_step_loss = torch.mean(self.loss(pred, target, pred_std, mask=mask), dim=0)
+        log = {f"test_loss_unroll{step}": time_step_loss[step - 1]
+               for step in self.args.val_steps_to_log}
+        log["test_mean_loss"] = torch.mean(time_step_loss)
+        entry = {"mse": mse(pred, target, pred_std, mask=mask, sum_vars=False),
+                 "mae": mae(pred, target, pred_std, mask=mask, sum_vars=False)}
+        spatial = self.loss(pred, target, pred_std, average_grid=False)
+        return log, entry, spatial[:, [step - 1 for step in self.args.val_steps_to_log]]
 
     def configure_optimizers(self):
         return torch.optim.AdamW(self.parameters(), lr=self.args.lr, betas=(0.9, 0.95))

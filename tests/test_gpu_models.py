@@ -54,3 +54,39 @@ def test_train_step_matches_reference(dev, name):
         _close(pred, entry["pred_step"], 1e-4, f"{name} pred")
         for n, p in model.named_parameters():
             _close(p.grad, entry["param_grads"][n], 1e-3, f"{name} grad {n}")
+
+
+EVAL = load_golden("eval.pt")
+
+
+@pytest.mark.parametrize("precision,rtol", [("fp32", 1e-4), ("bf16", 2e-2)])
+@pytest.mark.parametrize("name", sorted(EVAL))
+def test_eval_path_matches_reference(dev, name, precision, rtol):
+    """validation_step / test_step (forward-only rollout through the CUDA kernels) against
+    the unmodified reference's logged values and metric entries (tests/golden/eval.pt)."""
+    from neural_lam_b200 import config as nl_config
+    from neural_lam_b200 import models, ops
+    entry = EVAL[name]
+    case, ref = entry["case"], entry["ref"]
+    with tempfile.TemporaryDirectory() as root:
+        ds, args, batch = build_model_case(case, root)
+        args.val_steps_to_log = entry["val_steps_to_log"]
+        model = models.MODELS[case["model"]](args, nl_config.default_config(), ds)
+    model.load_state_dict(MODELS[name]["state_dict"])
+    model = model.to(dev)
+    batch = tuple(t.to(dev) for t in batch)
+    ops.set_precision(precision)
+    try:
+        vlog, vmse = model.validation_step(batch)
+        tlog, tentry, spatial = model.test_step(batch)
+    finally:
+        ops.set_precision("fp32")
+    for k, v in ref["val_log"].items():
+        _close(vlog[k], v, rtol, f"{name} {k}")
+    for k, v in ref["test_log"].items():
+        _close(tlog[k], v, rtol, f"{name} {k}")
+    _close(vmse, ref["val_mse"], rtol, "val entry mse")
+    _close(tentry["mse"], ref["test_mse"], rtol, "test entry mse")
+    _close(tentry["mae"], ref["test_mae"], rtol, "test entry mae")
+    _close(spatial, ref["spatial"], rtol, "spatial loss maps")
+    assert not any(p.grad is not None for p in model.parameters())  # forward only

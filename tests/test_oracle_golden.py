@@ -80,3 +80,30 @@ def test_stub_scatter_equals_dense_adjacency():
         exp_rec = rec + net.aggr_mlp(torch.cat((rec, agg), -1))
         torch.testing.assert_close(new_rec, exp_rec, rtol=1e-5, atol=1e-6)
         torch.testing.assert_close(new_edge, edge + msg, rtol=1e-6, atol=1e-6)
+
+
+def test_port_eval_path_matches_reference_golden():
+    """validation_step / test_step of the oracle port against the unmodified reference's
+    (tests/golden/eval.pt, written by oracle/make_golden_eval.py)."""
+    ev = load_golden("eval.pt")
+    models_pt = load_golden("models.pt")
+    assert len(ev) >= 4
+    for name, entry in ev.items():
+        case = entry["case"]
+        with tempfile.TemporaryDirectory() as root:
+            ds, args, batch = build_model_case(case, root)
+            args.val_steps_to_log = entry["val_steps_to_log"]
+            model = port.MODELS[case["model"]](args, None, ds)
+        model.load_state_dict(models_pt[name]["state_dict"])
+        ref = entry["ref"]
+        with torch.no_grad():
+            vlog, vmse = model.validation_step(batch)
+            tlog, tentry, spatial = model.test_step(batch)
+        for k, v in ref["val_log"].items():
+            torch.testing.assert_close(vlog[k], v, rtol=1e-4, atol=1e-6, msg=f"{name} {k}")
+        for k, v in ref["test_log"].items():
+            torch.testing.assert_close(tlog[k], v, rtol=1e-4, atol=1e-6, msg=f"{name} {k}")
+        torch.testing.assert_close(vmse, ref["val_mse"], rtol=1e-4, atol=1e-6)
+        torch.testing.assert_close(tentry["mse"], ref["test_mse"], rtol=1e-4, atol=1e-6)
+        torch.testing.assert_close(tentry["mae"], ref["test_mae"], rtol=1e-4, atol=1e-6)
+        torch.testing.assert_close(spatial, ref["spatial"], rtol=1e-4, atol=1e-6)
