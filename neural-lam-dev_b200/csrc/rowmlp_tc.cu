@@ -305,7 +305,6 @@ bool tc_supported(const nlam_rowmlp& d) {
   if (pad_n(d.d_hidden) < 0 || pad_n(d.d_out) < 0) return false;
   int k = 0;
   for (int s = 0; s < d.n_src; ++s) {
-    if (d.n_src > 1 && d.src[s].width % 8 != 0) return false;
     k += d.src[s].width;
   }
   return k <= 384;

@@ -108,9 +108,24 @@ __device__ __forceinline__ void gather_rows(const KParams& p, int b, int row0, i
         x[j] = __ldg(reinterpret_cast<const float4*>(rp[j]));
         y[j] = __ldg(reinterpret_cast<const float4*>(rp[j]) + 1);
       } else if (nval[j] < 0) {
+        // scalar path; a chunk may straddle two sources (widths not multiples of 8)
         float v[8];
+        const int left = -nval[j];
 #pragma unroll
-        for (int e = 0; e < 8; ++e) v[e] = (e < -nval[j]) ? __ldg(rp[j] + e) : 0.f;
+        for (int e = 0; e < 8; ++e) {
+          v[e] = 0.f;
+          if (e < left) {
+            v[e] = __ldg(rp[j] + e);
+          } else if (k0v[j] + e < p.k_total) {
+            const int k = k0v[j] + e;
+            int s2 = 0;
+            while (s2 + 1 < p.d.n_src && k >= p.koff[s2 + 1]) ++s2;
+            const nlam_src& src2 = p.d.src[s2];
+            const int r2 = src2.idx ? __ldg(src2.idx + row0 + rowv[j]) : row0 + rowv[j];
+            v[e] = __ldg(src2.ptr + (long long)b * src2.batch_stride + (long long)r2 * src2.ld +
+                         (k - p.koff[s2]));
+          }
+        }
         x[j] = make_float4(v[0], v[1], v[2], v[3]);
         y[j] = make_float4(v[4], v[5], v[6], v[7]);
       }

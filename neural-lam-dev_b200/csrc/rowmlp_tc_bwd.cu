@@ -579,13 +579,12 @@ rowmlp_tc_dgrad_kernel(const __grid_constant__ KParams p, const __grid_constant_
             int s = 0;
             while (s + 1 < p.d.n_src && kg >= p.koff[s + 1]) ++s;
             float* dst = p.d_src[s];
-            if (!dst) continue;
             const int w = p.d.src[s].width, col = kg - p.koff[s];
             const float4 v = *reinterpret_cast<const float4*>(stg + stg_idx(row, c4, 64));
             float tmp[4] = {v.x, v.y, v.z, v.w};
             const bool res = (s == p.d.residual_src) && p.g0;
-            float* o = dst + (grow0 + row) * w + col;
-            if ((w & 3) == 0) {
+            if (dst && (w & 3) == 0) {
+              float* o = dst + (grow0 + row) * w + col;
               if (res) {
                 const float4 ee =
                     __ldg(reinterpret_cast<const float4*>(p.g0 + (grow0 + row) * dout + col));
@@ -593,10 +592,20 @@ rowmlp_tc_dgrad_kernel(const __grid_constant__ KParams p, const __grid_constant_
               }
               *reinterpret_cast<float4*>(o) = make_float4(tmp[0], tmp[1], tmp[2], tmp[3]);
             } else {
+              // element by element: a 4-column group may straddle sources (odd widths)
 #pragma unroll
-              for (int j = 0; j < 4; ++j)
-                if (col + j < w)
-                  o[j] = tmp[j] + (res ? __ldg(p.g0 + (grow0 + row) * dout + col + j) : 0.f);
+              for (int j = 0; j < 4; ++j) {
+                const int k = kg + j;
+                if (k >= p.k_total) continue;
+                int s2 = s;
+                while (s2 + 1 < p.d.n_src && k >= p.koff[s2 + 1]) ++s2;
+                float* d2 = p.d_src[s2];
+                if (!d2) continue;
+                const int c2 = k - p.koff[s2];
+                const bool res2 = (s2 == p.d.residual_src) && p.g0;
+                d2[(grow0 + row) * p.d.src[s2].width + c2] =
+                    tmp[j] + (res2 ? __ldg(p.g0 + (grow0 + row) * dout + c2) : 0.f);
+              }
             }
           }
         }

@@ -522,6 +522,58 @@ class _RowMLPFn(torch.autograd.Function):
         return (None, *gw, d_srcs[0])
 
 
+class _RowMLPCatFn(torch.autograd.Function):
+    """out = MLP([x0 | x1 | x2]) on direct rows: the concatenation along the feature
+    axis happens in the kernel's gather (no cat kernel, no concatenated copy).  Sources
+    with a batch dim of 1 are shared by the batch."""
+
+    @staticmethod
+    def forward(ctx, meta, w1, b1, w2, b2, ln_g, ln_b, *xs):
+        W = Weights(w1, b1, w2, b2, ln_g, ln_b, 1)
+        xs3 = [_rows3d(x, "mlp input") for x in xs]
+        B = max(x.shape[0] for x in xs3)
+        rows = xs3[0].shape[1]
+        if any(x.shape[1] != rows or x.shape[0] not in (1, B) for x in xs3):
+            raise ValueError(f"mlp_forward_cat: incompatible inputs {[tuple(x.shape) for x in xs3]}")
+        out = rowmlp_fwd_raw([(x, None) for x in xs3], W, B, rows, False, None, meta["precision"])
+        ctx.meta = meta
+        ctx.n_x = len(xs3)
+        ctx.save_for_backward(w1, b1, w2, b2, ln_g, ln_b, *xs3)
+        return out
+
+    @staticmethod
+    def backward(ctx, gout):
+        saved = ctx.saved_tensors
+        w1, b1, w2, b2, ln_g, ln_b = saved[:6]
+        xs3 = list(saved[6:])
+        meta = ctx.meta
+        W = Weights(w1, b1, w2, b2, ln_g, ln_b, 1)
+        B = max(x.shape[0] for x in xs3)
+        need = [bool(n) for n in ctx.needs_input_grad[7:7 + ctx.n_x]]
+        d_srcs, d_params = rowmlp_bwd_raw([(x, None) for x in xs3], W, B, xs3[0].shape[1], False,
+                                          None, meta["precision"], gout, need,
+                                          sink_params=meta.get("params"))
+        d_srcs = [g.sum(0, keepdim=True) if (g is not None and x.shape[0] == 1 and B > 1) else g
+                  for g, x in zip(d_srcs, xs3)]
+        return (None, *W.split_grads(d_params), *d_srcs)
+
+
+def mlp_forward_cat(module, xs):
+    """`module(torch.cat(xs, dim=-1))` for 2 or 3 tensors (B or 1, N, w_i) / (N, w_i) without
+    materialising the concatenation.  Measured on the grid features of
+    base_graph_model.py:118-131 (17 | 17 | 19 columns, 255 k rows): the three narrow
+    row gathers cost more than the cat kernel saves (3.54 vs 3.46 ms per step), so the
+    models keep the cat there; it pays for wide sources."""
+    W = weights_of(module)
+    if not 1 <= len(xs) <= L.MAX_SRC or W.n_chunks != 1:
+        raise ValueError("mlp_forward_cat: 1..3 inputs, one weight set")
+    xs3 = [x.unsqueeze(0) if x.dim() == 2 else x for x in xs]
+    if sum(x.shape[-1] for x in xs3) != W.k:
+        raise ValueError(f"mlp_forward_cat: widths {[x.shape[-1] for x in xs3]} != {W.k}")
+    meta = {"precision": get_precision(), "params": W.t}
+    return _RowMLPCatFn.apply(meta, *W.t, *xs3)
+
+
 def mlp_forward(module, x, residual=False):
     """Fused forward of a make_mlp module on x (..., K); `residual=True`
     returns x + MLP(x) (base_graph_model.py:143-145)."""

@@ -75,6 +75,47 @@ def test_mlp_bf16(dev, bf16, blueprint, ln, rows, B):
         _close(q.grad, p.grad, f"d{n}")
 
 
+@pytest.mark.parametrize("precision", ["bf16", "fp32"])
+@pytest.mark.parametrize("widths,shared_last,grads", [
+    ((17, 17, 19), True, (False, False, False)),   # grid features: fused narrow backward
+    ((17, 17, 19), True, (True, True, False)),     # rollout: state inputs need gradients
+    ((8, 24), False, (True, True)), ((5, 3, 1), False, (True, False, True)),
+])
+def test_mlp_cat(dev, precision, widths, shared_last, grads):
+    """ops.mlp_forward_cat == module(torch.cat(xs, -1)) (base_graph_model.py:118-131),
+    sources of any width, the last one optionally shared by the batch."""
+    from neural_lam_b200 import ops, utils
+    from oracle import port
+    torch.manual_seed(1)
+    B, rows = 3, 1500
+    ref = port.make_mlp([sum(widths), 64, 64])
+    mlp = utils.make_mlp([sum(widths), 64, 64])
+    mlp.load_state_dict(ref.state_dict())
+    mlp = mlp.to(dev)
+    xs = [torch.randn((rows, w) if (shared_last and i == len(widths) - 1) else (B, rows, w))
+          for i, w in enumerate(widths)]
+    xr = [x.clone().requires_grad_(g) for x, g in zip(xs, grads)]
+    xg = [x.clone().to(dev).requires_grad_(g) for x, g in zip(xs, grads)]
+    w = torch.randn(B, rows, 64)
+    yr = ref(torch.cat([x if x.dim() == 3 else x.unsqueeze(0).expand(B, -1, -1) for x in xr], -1))
+    ops.set_precision(precision)
+    try:
+        yg = ops.mlp_forward_cat(mlp, xg)
+        tol = TOL if precision == "bf16" else 1e-4
+        _close(yg, yr, "out", tol=tol)
+        (yr * w).sum().backward()
+        (yg * w.to(dev)).sum().backward()
+    finally:
+        ops.set_precision("fp32")
+    gtol = TOL if precision == "bf16" else 1e-3
+    for i, (a, b) in enumerate(zip(xg, xr)):
+        if grads[i]:
+            assert a.grad.shape == b.grad.shape
+            _close(a.grad, b.grad, f"dx{i}", tol=gtol)
+    for (n, p), (_, q) in zip(ref.named_parameters(), mlp.named_parameters()):
+        _close(q.grad, p.grad, f"d{n}", tol=gtol)
+
+
 @pytest.mark.parametrize("name", sorted(INET))
 def test_interaction_net_bf16_vs_reference_golden(dev, bf16, name):
     from neural_lam_b200.interaction_net import InteractionNet
