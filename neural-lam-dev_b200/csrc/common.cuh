@@ -12,7 +12,32 @@ void set_error(const char* fmt, ...);
 void count_launch(int n = 1);
 int option_fwd_mc();    // -1 auto, 0 off, 1 force
 int option_dgrad_mc();
-int option_bwd_fused();  // -1 / 1: fused dgrad + wgrad kernel where eligible, 0: two kernels
+int option_bwd_fused();
+int option_pdl();        // 1: launch with programmatic dependent launch (see launch_k)  // -1 / 1: fused dgrad + wgrad kernel where eligible, 0: two kernels
+
+// Programmatic dependent launch: a kernel launched with this attribute may start while
+// its predecessor in the stream is still running (once every CTA of the predecessor has
+// executed griddepcontrol.launch_dependents or exited); it must execute pdl_wait() before
+// it touches anything the predecessor writes.  Used to overlap a kernel's prologue (TMEM
+// allocation, weights -> bf16 shared-memory operands) with the tail of the previous one.
+#ifdef __CUDACC__
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_k(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem,
+                            cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid, cfg.blockDim = block, cfg.dynamicSmemBytes = smem, cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = option_pdl() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+#endif
 
 #define NLAM_CHECK(cond, ...)        \
   do {                               \

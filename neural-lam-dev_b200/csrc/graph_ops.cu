@@ -87,6 +87,7 @@ __global__ void csr_sort_kernel(const int32_t* __restrict__ ptr, int32_t n, int3
 
 template <int VEC>
 __global__ void segsum_kernel(const __grid_constant__ nlam_segsum p) {
+  pdl_wait();
   const int wv = p.width / VEC;  // column groups per row
   const long long total = (long long)p.batch * p.n_out * wv;
   const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -158,9 +159,9 @@ extern "C" int nlam_segsum_run(const nlam_segsum* d, void* stream) {
   const long long total = (long long)d->batch * d->n_out * (vec ? d->width / 4 : d->width);
   const int nb = (int)((total + 255) / 256);
   if (vec)
-    segsum_kernel<4><<<nb, 256, 0, st>>>(*d);
+    NLAM_CUDA(launch_k(segsum_kernel<4>, nb, 256, 0, st, *d));
   else
-    segsum_kernel<1><<<nb, 256, 0, st>>>(*d);
+    NLAM_CUDA(launch_k(segsum_kernel<1>, nb, 256, 0, st, *d));
   NLAM_CUDA(cudaGetLastError());
   count_launch();
   return 0;

@@ -651,6 +651,7 @@ __device__ __forceinline__ void reduce_params_block(const RParams& p, int bx, in
   }
 }
 __global__ void __launch_bounds__(256) reduce_params_kernel(const __grid_constant__ RParams p) {
+  pdl_wait();
   reduce_params_block(p, blockIdx.x, blockIdx.y);
 }
 
@@ -665,6 +666,7 @@ struct RBatch {
 };
 static_assert(sizeof(RBatch) <= 4000, "RBatch must fit the kernel parameter space");
 __global__ void __launch_bounds__(256) reduce_params_batch_kernel(const __grid_constant__ RBatch b) {
+  pdl_wait();
   int j = 0;
   while (j + 1 < b.n && (int)blockIdx.x >= b.blk_off[j + 1]) ++j;
   const RParams& p = b.job[j];
@@ -691,7 +693,7 @@ static int queue_or_launch_reduce(const RParams& rp, bool defer, cudaStream_t st
     return 0;
   }
   dim3 rgrid((rp.p_total + 31) / 32, rp.n_chunks);
-  reduce_params_kernel<<<rgrid, 256, 0, st>>>(rp);
+  NLAM_CUDA(launch_k(reduce_params_kernel, rgrid, 256, 0, st, rp));
   NLAM_CUDA(cudaGetLastError());
   count_launch();
   return 0;
@@ -714,7 +716,7 @@ int reduce_params_flush(cudaStream_t st) {
     }
     b.blk_off[b.n] = off;
     if (off == 0) continue;
-    reduce_params_batch_kernel<<<off, 256, 0, st>>>(b);
+    NLAM_CUDA(launch_k(reduce_params_batch_kernel, off, 256, 0, st, b));
     NLAM_CUDA(cudaGetLastError());
     count_launch();
   }

@@ -60,6 +60,16 @@ rowmlp_tc_fwd_kernel(const __grid_constant__ KParams p, const __grid_constant__ 
   const uint32_t tH = tmem_base, tY = tmem_base + (uint32_t)n1;
   uint32_t ph0 = 0, ph1 = 0;
   int loaded_chunk = -1;
+  if (p.d.n_chunks == 1) {  // single weight set: staged while the previous kernel drains
+    stage_weight(p.d.w.w1, dh, p.k_total, n1, g.k1, sW1);
+    stage_weight(p.d.w.w2, dout, dh, n2, k2, sW2);
+    stage_params(p.d, 0, n1, n2, sPar);
+    loaded_chunk = 0;
+  }
+  pdl_wait();
+  // all CTAs of this persistent grid are resident: let the next kernel's CTAs take over
+  // each SM (and run their prologue) as soon as this kernel's CTA there exits
+  pdl_trigger();
 
   const uint32_t idesc1 = make_idesc_bf16(TM, n1);
   const uint32_t idesc2 = make_idesc_bf16(TM, n2);
@@ -368,7 +378,7 @@ int tc_rowmlp_fwd(const nlam_rowmlp& d, cudaStream_t st) {
                                      (int)g.smem_bytes));
       max_set = (int)g.smem_bytes;
     }
-    kern<<<grid, tc::NT, g.smem_bytes, st>>>(p, g);
+    NLAM_CUDA(launch_k(kern, grid, tc::NT, g.smem_bytes, st, p, g));
     return 0;
   };
   const bool fg = tc::fast_gather(p);

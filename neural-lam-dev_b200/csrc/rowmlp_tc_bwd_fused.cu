@@ -256,6 +256,14 @@ rowmlp_tc_bwd_fused_kernel(const __grid_constant__ KParams p, const __grid_const
       if (t_first < g.total_tiles) stage_idx(t_first, sIx);
       fu_sync(ctx);
     }
+    // Programmatic dependent launch: everything above -- TMEM allocation, weights -> bf16
+    // operands, the first tile's index tables (static graph data; its L2 prefetches of
+    // rows the previous kernel may still be writing are harmless) -- overlapped the
+    // previous kernel's tail.  From here on its outputs are read.
+    pdl_wait();
+    // all CTAs of this persistent grid are resident: let the next kernel's CTAs take over
+    // each SM (and run their prologue) as soon as this kernel's CTA there exits
+    pdl_trigger();
 
     for (int t = blockIdx.x * FU_CTX + ctx; t < g.total_tiles; t += stride) {
       const int b = t % p.d.batch, tile = t / p.d.batch;  // batch innermost: shared rows hit L2
@@ -763,9 +771,11 @@ int tc_rowmlp_bwd_fused(const KParams& p, const tc::BGeo& g, cudaStream_t st) {
     attr = true;
   }
   if (tc_bwd_fused_kind(p) == 2)
-    tc::rowmlp_tc_bwd_fused_kernel<true><<<tc_bwd_fused_grid(g), tc::FU_NT, tc::FU_SMEM, st>>>(p, g);
+    NLAM_CUDA(launch_k(tc::rowmlp_tc_bwd_fused_kernel<true>, tc_bwd_fused_grid(g), tc::FU_NT,
+                       tc::FU_SMEM, st, p, g));
   else
-    tc::rowmlp_tc_bwd_fused_kernel<false><<<tc_bwd_fused_grid(g), tc::FU_NT, tc::FU_SMEM, st>>>(p, g);
+    NLAM_CUDA(launch_k(tc::rowmlp_tc_bwd_fused_kernel<false>, tc_bwd_fused_grid(g), tc::FU_NT,
+                       tc::FU_SMEM, st, p, g));
   NLAM_CUDA(cudaGetLastError());
   count_launch();
   return 0;

@@ -84,6 +84,10 @@ rowmlp_tc_fwd_mc_kernel(const __grid_constant__ KParams p, const __grid_constant
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  pdl_wait();  // the prologue above overlapped the previous kernel's tail
+  // all CTAs of this persistent grid are resident: let the next kernel's CTAs take over
+  // each SM (and run their prologue) as soon as this kernel's CTA there exits
+  pdl_trigger();
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t tH = tmem_base + (uint32_t)wg * 128u, tY = tH + 64u;
   uint64_t* bar0 = &bars[2 * wg];
@@ -298,7 +302,7 @@ int tc_rowmlp_fwd_mc(const KParams& p, const tc::Geo& g, cudaStream_t st) {
   }
   int grid = (g.total_tiles + tc::MC_WG - 1) / tc::MC_WG;
   if (grid > 148) grid = 148;
-  tc::rowmlp_tc_fwd_mc_kernel<<<grid, tc::MC_NT, tc::MC_SMEM, st>>>(p, g);
+  NLAM_CUDA(launch_k(tc::rowmlp_tc_fwd_mc_kernel, grid, tc::MC_NT, tc::MC_SMEM, st, p, g));
   NLAM_CUDA(cudaGetLastError());
   count_launch();
   return 0;
