@@ -187,7 +187,9 @@ int nlam_version(void);
  * 3-pipeline shared-weight input-gradient kernel.  Returns 0, or 1 for an
  * unknown name.  "bwd_fused" (default on) = single input + weight gradient kernel
  * for square 64-wide MLPs.  Environment NLAM_FWD_MC / NLAM_DGRAD_MC /
- * NLAM_BWD_FUSED give the initial values. */
+ * NLAM_BWD_FUSED give the initial values.  "pdl" (default 1, env NLAM_PDL): launch with
+ * programmatic dependent launch so that a kernel's prologue overlaps the tail of the
+ * previous one (every kernel waits with griddepcontrol.wait before reading its inputs). */
 int nlam_set_option(const char* name, int value);
 /* Number of kernels this library has launched in this process (monotonic;
  * bench.py reports the delta over its timed region as "gpu_launches"). */

@@ -84,10 +84,6 @@ rowmlp_tc_fwd_mc_kernel(const __grid_constant__ KParams p, const __grid_constant
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  pdl_wait();  // the prologue above overlapped the previous kernel's tail
-  // all CTAs of this persistent grid are resident: let the next kernel's CTAs take over
-  // each SM (and run their prologue) as soon as this kernel's CTA there exits
-  pdl_trigger();
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t tH = tmem_base + (uint32_t)wg * 128u, tY = tH + 64u;
   uint64_t* bar0 = &bars[2 * wg];
@@ -116,6 +112,12 @@ rowmlp_tc_fwd_mc_kernel(const __grid_constant__ KParams p, const __grid_constant
       load_row_idx<128>(p, r0, c0, wtid, nidx);
     }
   }
+  // Programmatic dependent launch: the prologue above (TMEM, weights, the first tile's
+  // static row indices) overlapped the previous kernel's tail; its outputs are read from
+  // here on.  All CTAs of this persistent grid are resident, so the next kernel's CTAs
+  // may take over each SM as soon as this kernel's CTA there exits.
+  pdl_wait();
+  pdl_trigger();
   for (int t = blockIdx.x * MC_WG + wg; t < g.total_tiles; t += stride) {
     const int b = t % p.d.batch, tile = t / p.d.batch;  // batch innermost: shared rows hit L2
     int row0, cnt, chunk;

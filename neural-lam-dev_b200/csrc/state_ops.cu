@@ -14,6 +14,7 @@ constexpr int SS_ROWS_PER_BLOCK = 256;  // one row per thread
 
 __global__ void __launch_bounds__(SS_THREADS) state_step_fwd_kernel(const nlam_state_step p) {
   __shared__ float red[SS_THREADS / 32];
+  pdl_wait();
   const long long row = (long long)blockIdx.x * SS_ROWS_PER_BLOCK + threadIdx.x;
   float acc = 0.f;
   if (row < p.rows) {
@@ -47,6 +48,7 @@ __global__ void __launch_bounds__(SS_THREADS) state_step_fwd_kernel(const nlam_s
 // loss_sum[0] = sum of the per-block partials, fixed order (single block)
 __global__ void __launch_bounds__(256) state_step_sum_kernel(const float* partial, int n, float* out) {
   __shared__ float red[256];
+  pdl_wait();
   float s = 0.f;
   for (int i = threadIdx.x; i < n; i += 256) s += partial[i];
   red[threadIdx.x] = s;
@@ -61,6 +63,7 @@ __global__ void __launch_bounds__(256) state_step_sum_kernel(const float* partia
 // d_pred = interior * (d_new + d_loss * 2 * (new - truth) * inv_std^2)
 // d_net_out = d_pred * diff_std ; d_prev = d_pred
 __global__ void __launch_bounds__(SS_THREADS) state_step_bwd_kernel(const nlam_state_step_bwd p) {
+  pdl_wait();
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const long long total = p.fwd.rows * p.fwd.features;
   if (i >= total) return;
@@ -95,10 +98,11 @@ extern "C" int nlam_state_step_fwd(const nlam_state_step* d, void* stream) {
   NLAM_CHECK(d->rows > 0 && d->nodes > 0 && d->features > 0 && d->rows % d->nodes == 0,
              "state_step_fwd: bad sizes");
   const int nb = (int)nlam_state_step_partials(d->rows);
-  state_step_fwd_kernel<<<nb, SS_THREADS, 0, st>>>(*d);
+  NLAM_CUDA(launch_k(state_step_fwd_kernel, nb, SS_THREADS, 0, st, *d));
   NLAM_CUDA(cudaGetLastError());
   count_launch();
-  state_step_sum_kernel<<<1, 256, 0, st>>>(d->loss_partial, nb, d->loss_sum);
+  NLAM_CUDA(launch_k(state_step_sum_kernel, 1, 256, 0, st, (const float*)d->loss_partial, nb,
+                     d->loss_sum));
   NLAM_CUDA(cudaGetLastError());
   count_launch();
   return 0;
@@ -110,7 +114,8 @@ extern "C" int nlam_state_step_bwd_run(const nlam_state_step_bwd* d, void* strea
              "state_step_bwd: NULL argument");
   NLAM_CHECK(d->d_net_out || d->d_prev, "state_step_bwd: nothing to compute");
   const long long total = d->fwd.rows * d->fwd.features;
-  state_step_bwd_kernel<<<(int)((total + SS_THREADS - 1) / SS_THREADS), SS_THREADS, 0, st>>>(*d);
+  NLAM_CUDA(launch_k(state_step_bwd_kernel, (int)((total + SS_THREADS - 1) / SS_THREADS),
+                     SS_THREADS, 0, st, *d));
   NLAM_CUDA(cudaGetLastError());
   count_launch();
   return 0;
