@@ -128,7 +128,12 @@ typedef struct nlam_rowmlp_bwd {
                              profiler time the three launches separately; the stages
                              must run in this order on the same workspace); bit 3
                              (value 8, alone = everything): queue the partial reduction
-                             for nlam_rowmlp_bwd_flush instead of launching it */
+                             for nlam_rowmlp_bwd_flush instead of launching it; bit 4
+                             (value 16): the rows of fwd.src were NOT written by the
+                             kernel launched just before this call on the stream (true
+                             under autograd: they were saved by the forward pass) -- the
+                             fused kernel then gathers its first tile before it waits
+                             for that kernel (programmatic dependent launch) */
 } nlam_rowmlp_bwd;
 
 /* out[b,i,:] (+)= scale[i] * sum_{p in [ptr[i],ptr[i+1])} src[b, idx[p], :]

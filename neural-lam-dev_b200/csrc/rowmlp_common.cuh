@@ -24,6 +24,7 @@ struct KParams {
   const int32_t* g0_idx;
   const int32_t* d_src_idx[NLAM_MAX_SRC];
   int reduce_src, reduce_accumulate;
+  int inputs_stable;  // fwd.src rows were not written by the kernel just before this one
   float* a_save;
   float* dy_save;
   float* dh_save;

@@ -943,6 +943,7 @@ int tc_rowmlp_bwd(const nlam_rowmlp_bwd& bd, cudaStream_t st) {
   p.g1_batch_stride = bd.g1_batch_stride;
   p.g0_idx = bd.g0_idx;
   p.reduce_src = bd.reduce_src, p.reduce_accumulate = bd.reduce_accumulate;
+  p.inputs_stable = (bd.stage_mask & 16) ? 1 : 0;
   {
     bool special = bd.g0_idx || bd.reduce_src >= 0;
     for (int s = 0; s < NLAM_MAX_SRC; ++s) {
@@ -965,7 +966,7 @@ int tc_rowmlp_bwd(const nlam_rowmlp_bwd& bd, cudaStream_t st) {
   g.dh_img = reinterpret_cast<uint8_t*>(bd.workspace + ws.dh_img);
   g.partial = bd.workspace + ws.partial;
   g.vec_partial = bd.workspace + ws.vec_partial;
-  if (d.n_chunks > 1 && (!bd.stage_mask || (bd.stage_mask & 1)))  // CTAs write visited chunks only
+  if (d.n_chunks > 1 && (!(bd.stage_mask & 7) || (bd.stage_mask & 1)))  // CTAs write visited chunks only
     NLAM_CUDA(cudaMemsetAsync(g.partial, 0,
                               sizeof(float) * (ws.vec_partial + (size_t)ws.d_slots * d.n_chunks *
                                                                     g.vec_len - ws.partial), st));

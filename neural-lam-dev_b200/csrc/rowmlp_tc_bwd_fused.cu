@@ -260,10 +260,15 @@ rowmlp_tc_bwd_fused_kernel(const __grid_constant__ KParams p, const __grid_const
     // operands, the first tile's index tables (static graph data; its L2 prefetches of
     // rows the previous kernel may still be writing are harmless) -- overlapped the
     // previous kernel's tail.  From here on its outputs are read.
-    pdl_wait();
-    // all CTAs of this persistent grid are resident: let the next kernel's CTAs take over
-    // each SM (and run their prologue) as soon as this kernel's CTA there exits
-    pdl_trigger();
+    // When the caller guarantees that the forward inputs are old (autograd: they were saved
+    // during the forward pass; the kernel just before this one only produced upstream
+    // gradients), the first tile's gather, GEMM 1 also run before the wait.
+    if (!p.inputs_stable) {
+      pdl_wait();
+      // all CTAs of this persistent grid are resident: let the next kernel's CTAs take
+      // over each SM (and run their prologue) as soon as this kernel's CTA there exits
+      pdl_trigger();
+    }
 
     for (int t = blockIdx.x * FU_CTX + ctx; t < g.total_tiles; t += stride) {
       const int b = t % p.d.batch, tile = t / p.d.batch;  // batch innermost: shared rows hit L2
@@ -385,6 +390,10 @@ rowmlp_tc_bwd_fused_kernel(const __grid_constant__ KParams p, const __grid_const
       }
       // while GEMM 1 runs: dOut rows -> bf16 tile (coalesced), next tile's rows -> L2
       {
+        if (p.inputs_stable && first) {  // upstream gradients: the previous kernel's output
+          pdl_wait();
+          pdl_trigger();
+        }
         float4 va[4], vb[4];
         float gs[4];
         dm_load(ltid, va, vb, gs);
@@ -665,6 +674,7 @@ rowmlp_tc_bwd_fused_kernel(const __grid_constant__ KParams p, const __grid_const
 
   // ---------------- accumulators (context 0 + context 1) and column sums -> this CTA's
   // partial slot
+  pdl_wait();  // (a context without tiles has not waited yet; the partial slots are fresh memory)
   tc_fence_before();
   __syncthreads();
   tc_fence_after();

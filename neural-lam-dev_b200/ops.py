@@ -397,8 +397,11 @@ def rowmlp_bwd_raw(srcs, W, batch, rows, residual, tiles, precision, g0, need_sr
     if timer is None:
         # deferred reduction only when the gradients go to the sink: autograd must not
         # hand out a d_params tensor whose values do not exist yet
+        # 16: the inputs were saved by the forward pass, the kernel that ran just before this
+        # one (upstream backward) did not write them
+        bd.stage_mask = 16
         if _state.get("defer_reduce", False) and sink is not None:
-            bd.stage_mask = 8
+            bd.stage_mask = 8 | 16
             _deferred_keep.append((ws, sink))
         L.check(lib.nlam_rowmlp_bwd_run(ctypes.byref(bd), _stream()), "nlam_rowmlp_bwd_run")
     else:
