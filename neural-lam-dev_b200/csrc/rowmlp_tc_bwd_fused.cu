@@ -252,7 +252,7 @@ rowmlp_tc_bwd_fused_kernel(const __grid_constant__ KParams p, const __grid_const
     };
     int pb = 0;
     {
-      const int t_first = blockIdx.x * FU_CTX + ctx;
+      const int t_first = blockIdx.x + gridDim.x * ctx;
       if (t_first < g.total_tiles) stage_idx(t_first, sIx);
       fu_sync(ctx);
     }
@@ -270,7 +270,9 @@ rowmlp_tc_bwd_fused_kernel(const __grid_constant__ KParams p, const __grid_const
       pdl_trigger();
     }
 
-    for (int t = blockIdx.x * FU_CTX + ctx; t < g.total_tiles; t += stride) {
+    // SM-major round robin: this SM's tiles are blockIdx.x, + gridDim.x, + 2 gridDim.x, ...
+    // (counts differ by at most one ACROSS SMs), dealt alternately to its contexts
+    for (int t = blockIdx.x + gridDim.x * ctx; t < g.total_tiles; t += stride) {
       const int b = t % p.d.batch, tile = t / p.d.batch;  // batch innermost: shared rows hit L2
       int row0, cnt, chunk;
       tile_range<TM>(p.d, tile, row0, cnt, chunk);
@@ -686,7 +688,7 @@ rowmlp_tc_bwd_fused_kernel(const __grid_constant__ KParams p, const __grid_const
     const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
     const int c0 = cq * 16;
     // a context without tiles (last CTA of a small launch) never wrote its accumulators
-    const bool two = (int)(blockIdx.x * FU_CTX + 1) < g.total_tiles;
+    const bool two = (int)(blockIdx.x + gridDim.x) < g.total_tiles;
     float v[16], w[16];
     tmem_ld16(tmem_base + 128u + lane_addr + (uint32_t)c0, v);
     tmem_ld16(tmem_base + 256u + 128u + lane_addr + (uint32_t)c0, w);

@@ -105,7 +105,7 @@ rowmlp_tc_fwd_mc_kernel(const __grid_constant__ KParams p, const __grid_constant
   // source-row indices of this thread's row, loaded one tile ahead
   int nidx[NLAM_MAX_SRC] = {-1, -1, -1};
   {
-    const int t0 = blockIdx.x * MC_WG + wg;
+    const int t0 = blockIdx.x + gridDim.x * wg;
     if (t0 < g.total_tiles) {
       int r0, c0, ch0;
       tile_range<TM>(p.d, t0 / p.d.batch, r0, c0, ch0);
@@ -118,7 +118,8 @@ rowmlp_tc_fwd_mc_kernel(const __grid_constant__ KParams p, const __grid_constant
   // may take over each SM as soon as this kernel's CTA there exits.
   pdl_wait();
   pdl_trigger();
-  for (int t = blockIdx.x * MC_WG + wg; t < g.total_tiles; t += stride) {
+  // SM-major round robin: tile counts differ by at most one across SMs
+  for (int t = blockIdx.x + gridDim.x * wg; t < g.total_tiles; t += stride) {
     const int b = t % p.d.batch, tile = t / p.d.batch;  // batch innermost: shared rows hit L2
     int row0, cnt, chunk;
     tile_range<TM>(p.d, tile, row0, cnt, chunk);
