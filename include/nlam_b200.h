@@ -172,6 +172,9 @@ typedef struct nlam_state_step {
   int64_t rows;
   int32_t nodes;
   int32_t features;
+  int64_t prev_batch_stride;  /* floats between batch items of prev / truth (rows of a batch */
+  int64_t truth_batch_stride; /* item stay dense); 0 = nodes * features.  Lets the caller  */
+                              /* pass slices like init_states[:, 1] without a copy        */
 } nlam_state_step;
 
 /* Backward: d_pred = interior * (d_new + d_loss * 2 (new - truth) inv_std^2);

@@ -21,8 +21,11 @@ __global__ void __launch_bounds__(SS_THREADS) state_step_fwd_kernel(const nlam_s
     const int node = (int)(row % p.nodes);
     const float in = __ldg(p.interior + node);
     const float* no = p.net_out + row * p.features;
-    const float* pv = p.prev + row * p.features;
-    const float* tr = p.truth + row * p.features;
+    const long long bi = row / p.nodes, dense = (long long)p.nodes * p.features;
+    const float* pv = p.prev + bi * (p.prev_batch_stride ? p.prev_batch_stride : dense) +
+                      (long long)node * p.features;
+    const float* tr = p.truth + bi * (p.truth_batch_stride ? p.truth_batch_stride : dense) +
+                      (long long)node * p.features;
     float* ns = p.new_state + row * p.features;
     for (int f = 0; f < p.features; ++f) {
       const float t = __ldg(tr + f);
@@ -75,7 +78,11 @@ __global__ void __launch_bounds__(SS_THREADS) state_step_bwd_kernel(const nlam_s
     if (p.d_new) d = __ldg(p.d_new + i);
     if (p.d_loss) {
       const float is = p.fwd.inv_std ? __ldg(p.fwd.inv_std + f) : 1.f;
-      d += __ldg(p.d_loss) * 2.f * (__ldg(p.fwd.new_state + i) - __ldg(p.fwd.truth + i)) * is * is;
+      const long long bi = row / p.fwd.nodes, node = row % p.fwd.nodes;
+      const long long ts = p.fwd.truth_batch_stride ? p.fwd.truth_batch_stride
+                                                    : (long long)p.fwd.nodes * p.fwd.features;
+      const float tr = __ldg(p.fwd.truth + bi * ts + node * p.fwd.features + f);
+      d += __ldg(p.d_loss) * 2.f * (__ldg(p.fwd.new_state + i) - tr) * is * is;
     }
   }
   if (p.d_net_out) p.d_net_out[i] = d * __ldg(p.fwd.diff_std + f);

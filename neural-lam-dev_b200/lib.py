@@ -104,7 +104,8 @@ class StateStep(ctypes.Structure):
     _fields_ = [(n, c_float_p) for n in ("net_out", "prev", "truth", "diff_std", "diff_mean",
                                          "inv_std", "interior", "new_state", "loss_partial",
                                          "loss_sum")] + [
-        ("rows", ctypes.c_int64), ("nodes", ctypes.c_int32), ("features", ctypes.c_int32)]
+        ("rows", ctypes.c_int64), ("nodes", ctypes.c_int32), ("features", ctypes.c_int32),
+        ("prev_batch_stride", ctypes.c_int64), ("truth_batch_stride", ctypes.c_int64)]
 
 
 class StateStepBwd(ctypes.Structure):

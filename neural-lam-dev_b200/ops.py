@@ -648,7 +648,9 @@ class _InteractionNetFn(torch.autograd.Function):
                               scale=plan.inv_deg if meta["aggr"] == "mean" else None)
         rec_out = rowmlp_fwd_raw([(rec3, None), (aggr, None)], Wa, B, n_rec, True,
                                  plan.aggr_tiles, prec)
-        meta = dict(meta, aligned=al is not None)
+        same = (send3.data_ptr() == rec3.data_ptr() and send3.shape == rec3.shape
+                and send3.stride() == rec3.stride())
+        meta = dict(meta, aligned=al is not None, same_send_rec=same)
         ctx.meta = meta
         ctx.set_materialize_grads(False)  # unused outputs arrive as None, not zeros
         ctx.save_for_backward(*ew, *aw, send3, rec3, edge3, aggr)
@@ -691,7 +693,15 @@ class _InteractionNetFn(torch.autograd.Function):
                 reduce_into=dR, sink_params=meta.get("edge_params"))
             d_send = None
             if need_send:
-                d_send = segsum_raw(dzS, plan.ts_rowptr, plan.ts_perm, plan.n_send_idx)
+                if (meta.get("same_send_rec") and need_rec and plan.n_send_idx == n_rec
+                        and d_rec is dR and dR.shape[0] == B):
+                    # sender and receiver rows are the SAME tensor (m2m layers,
+                    # graph_lam.py:51-57): its gradient is d_send + d_rec -- accumulate the
+                    # sender part into the receiver gradient instead of returning two
+                    # tensors for autograd to add
+                    segsum_raw(dzS, plan.ts_rowptr, plan.ts_perm, n_rec, out=dR, accumulate=True)
+                else:
+                    d_send = segsum_raw(dzS, plan.ts_rowptr, plan.ts_perm, plan.n_send_idx)
         else:
             (dzE, dzS, dzR), dPe = rowmlp_bwd_raw(
                 [(edge3, None), (send3, plan.send32), (rec3, plan.recv32)], We, B, M,
@@ -725,8 +735,16 @@ class _StateStepFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, net_out, prev, truth, diff_std, diff_mean, inv_std, interior):
         lib = L.load()
-        net_out, prev, truth = (_rows3d(t, "state").contiguous() for t in (net_out, prev, truth))
+        net_out = _rows3d(net_out, "state").contiguous()
         B, N, F = net_out.shape
+
+        def dense_rows(t):  # batch-strided slices (init_states[:, 1]) are taken as they are
+            t = _rows3d(t, "state")
+            if t.stride(2) != 1 or t.stride(1) != F or (B > 1 and t.stride(0) < N * F):
+                t = t.contiguous()
+            return t
+
+        prev, truth = dense_rows(prev), dense_rows(truth)
         d = L.StateStep()
         new_state = torch.empty_like(net_out)
         n_part = int(lib.nlam_state_step_partials(B * N))
@@ -739,6 +757,8 @@ class _StateStepFn(torch.autograd.Function):
         d.new_state, d.loss_partial, d.loss_sum = (new_state.data_ptr(), partial.data_ptr(),
                                                    loss_sum.data_ptr())
         d.rows, d.nodes, d.features = B * N, N, F
+        d.prev_batch_stride = prev.stride(0) if B > 1 else 0
+        d.truth_batch_stride = truth.stride(0) if B > 1 else 0
         L.check(lib.nlam_state_step_fwd(ctypes.byref(d), _stream()), "nlam_state_step_fwd")
         ctx.set_materialize_grads(False)
         ctx.save_for_backward(new_state, truth, diff_std, inv_std, interior)
@@ -755,6 +775,7 @@ class _StateStepFn(torch.autograd.Function):
         bd.fwd.diff_std, bd.fwd.interior = diff_std.data_ptr(), interior.data_ptr()
         bd.fwd.inv_std = inv_std.data_ptr() if inv_std is not None else None
         bd.fwd.rows, bd.fwd.nodes, bd.fwd.features = B * N, N, F
+        bd.fwd.truth_batch_stride = truth.stride(0) if B > 1 else 0
         if d_new is not None:
             d_new = d_new.contiguous()
             bd.d_new = d_new.data_ptr()
