@@ -134,6 +134,10 @@ typedef struct nlam_rowmlp_bwd {
                              under autograd: they were saved by the forward pass) -- the
                              fused kernel then gathers its first tile before it waits
                              for that kernel (programmatic dependent launch) */
+  int32_t g0_sum_count;   /* > 1: dOut row r = sum over k < g0_sum_count of the g0 rows at    */
+  int64_t g0_sum_stride;  /* g0 + k * g0_sum_stride floats (fwd.batch must be 1): the backward */
+                          /* of an output that was expand()-ed over a batch, without the       */
+                          /* summed copy; only where nlam_rowmlp_bwd_stages() == 2             */
 } nlam_rowmlp_bwd;
 
 /* out[b,i,:] (+)= scale[i] * sum_{p in [ptr[i],ptr[i+1])} src[b, idx[p], :]

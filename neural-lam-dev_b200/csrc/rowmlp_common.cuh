@@ -24,6 +24,8 @@ struct KParams {
   const int32_t* g0_idx;
   const int32_t* d_src_idx[NLAM_MAX_SRC];
   int reduce_src, reduce_accumulate;
+  int g0_nsum;              // > 1: dOut = sum of g0_nsum slices of g0, g0_sum_stride floats apart
+  long long g0_sum_stride;
   int inputs_stable;  // fwd.src rows were not written by the kernel just before this one
   float* a_save;
   float* dy_save;

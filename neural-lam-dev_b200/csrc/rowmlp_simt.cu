@@ -844,6 +844,7 @@ int simt_rowmlp_bwd(const nlam_rowmlp_bwd& bd, cudaStream_t st) {
   KParams p{};
   if (fill_params(d, p)) return 1;
   NLAM_CHECK(bd.d_params, "rowmlp_bwd: d_params is NULL");
+  NLAM_CHECK(bd.g0_sum_count <= 1, "rowmlp_bwd: g0_sum_count exists only on the fused bf16 path");
   const ParamLayout lay = p.lay;
   if (d.rows == 0) {
     if (!bd.params_accumulate)

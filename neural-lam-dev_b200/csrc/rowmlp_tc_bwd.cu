@@ -944,6 +944,11 @@ int tc_rowmlp_bwd(const nlam_rowmlp_bwd& bd, cudaStream_t st) {
   p.g0_idx = bd.g0_idx;
   p.reduce_src = bd.reduce_src, p.reduce_accumulate = bd.reduce_accumulate;
   p.inputs_stable = (bd.stage_mask & 16) ? 1 : 0;
+  p.g0_nsum = bd.g0_sum_count > 1 ? bd.g0_sum_count : 1;
+  p.g0_sum_stride = bd.g0_sum_stride;
+  NLAM_CHECK(p.g0_nsum == 1 || (fused && d.batch == 1 && d.d_out == 64 && bd.g0 && !bd.g0_idx &&
+                                   d.residual_src < 0),
+             "rowmlp_bwd: g0_sum_count needs the fused backward kernel, batch 1, dense g0 rows");
   {
     bool special = bd.g0_idx || bd.reduce_src >= 0;
     for (int s = 0; s < NLAM_MAX_SRC; ++s) {

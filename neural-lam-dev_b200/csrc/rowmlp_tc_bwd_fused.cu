@@ -300,6 +300,16 @@ rowmlp_tc_bwd_fused_kernel(const __grid_constant__ KParams p, const __grid_const
             if (g0p[j]) va[j] = __ldg(reinterpret_cast<const float4*>(g0p[j]));
             if (g1p[j]) vb[j] = __ldg(reinterpret_cast<const float4*>(g1p[j]));
           }
+          if (p.g0_nsum > 1) {  // dOut of an expand()-ed output: sum of the batch slices
+            for (int k = 1; k < p.g0_nsum; ++k)
+#pragma unroll
+              for (int j = 0; j < 4; ++j)
+                if (g0p[j]) {
+                  const float4 t = __ldg(reinterpret_cast<const float4*>(
+                      g0p[j] + (long long)k * p.g0_sum_stride));
+                  va[j].x += t.x, va[j].y += t.y, va[j].z += t.z, va[j].w += t.w;
+                }
+          }
         } else {  // narrow output rows (stride dout floats): scalar loads, zero padding
 #pragma unroll
           for (int j = 0; j < 4; ++j) {

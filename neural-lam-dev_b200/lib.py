@@ -82,6 +82,8 @@ class RowMlpBwd(ctypes.Structure):
         ("workspace", c_float_p),
         ("workspace_floats", ctypes.c_size_t),
         ("stage_mask", ctypes.c_int32),
+        ("g0_sum_count", ctypes.c_int32),
+        ("g0_sum_stride", ctypes.c_int64),
     ]
 
 

@@ -57,6 +57,13 @@ class BaseGraphModel(ARModel):
         rescaled_delta_mean = pred_delta_mean * self.diff_std + self.diff_mean
         return prev_state + rescaled_delta_mean, pred_std
 
+    def embed_static(self, embedder, features, batch_size):
+        """`expand_to_batch(embedder(features), B)`; on the GPU as one autograd node whose
+        backward sums the batch slices of the incoming gradient inside the kernel."""
+        if features.is_cuda and features.dim() == 2 and isinstance(embedder, utils.FusedMLP):
+            return ops.mlp_forward_expand(embedder, features, batch_size)
+        return self.expand_to_batch(embedder(features), batch_size)
+
     def net_output(self, prev_state, prev_prev_state, forcing):
         """Encode-process-decode up to the output map (base_graph_model.py:106-159)."""
         batch_size = prev_state.shape[0]
@@ -64,13 +71,13 @@ class BaseGraphModel(ARModel):
             (prev_state, prev_prev_state, forcing,
              self.expand_to_batch(self.grid_static_features, batch_size)), dim=-1)
         grid_emb = self.grid_embedder(grid_features)
-        g2m_emb = self.g2m_embedder(self.g2m_features)
-        m2g_emb = self.m2g_embedder(self.m2g_features)
+        # static edge embeddings, expanded over the batch (base_graph_model.py:125-152)
+        g2m_emb = self.embed_static(self.g2m_embedder, self.g2m_features, batch_size)
+        m2g_emb = self.embed_static(self.m2g_embedder, self.m2g_features, batch_size)
         mesh_emb = self.embedd_mesh_nodes()
 
-        mesh_rep = self.g2m_gnn(grid_emb, self.expand_to_batch(mesh_emb, batch_size),
-                                self.expand_to_batch(g2m_emb, batch_size))
+        mesh_rep = self.g2m_gnn(grid_emb, self.expand_to_batch(mesh_emb, batch_size), g2m_emb)
         grid_rep = ops.mlp_forward(self.encoding_grid_mlp, grid_emb, residual=True)
         mesh_rep = self.process_step(mesh_rep)
-        grid_rep = self.m2g_gnn(mesh_rep, grid_rep, self.expand_to_batch(m2g_emb, batch_size))
+        grid_rep = self.m2g_gnn(mesh_rep, grid_rep, m2g_emb)
         return self.output_map(grid_rep)

@@ -27,7 +27,6 @@ class GraphLAM(BaseGraphModel):
 
     def process_step(self, mesh_rep):
         """graph_lam.py:73-91: embed m2m edges, run the processor layers."""
-        m2m_emb = self.m2m_embedder(self.m2m_features)
-        mesh_rep, _ = self.processor(
-            mesh_rep, self.expand_to_batch(m2m_emb, mesh_rep.shape[0]))
+        m2m_emb = self.embed_static(self.m2m_embedder, self.m2m_features, mesh_rep.shape[0])
+        mesh_rep, _ = self.processor(mesh_rep, m2m_emb)
         return mesh_rep

@@ -340,11 +340,14 @@ def rowmlp_fwd_raw(srcs, W, batch, rows, residual, tiles, precision, want_res=Fa
 
 def rowmlp_bwd_raw(srcs, W, batch, rows, residual, tiles, precision, g0, need_src,
                    g1=None, g1_idx=None, g1_scale=None, aligned=None, g0_idx=None,
-                   d_src_idx=None, reduce_src=-1, reduce_into=None, sink_params=None):
+                   d_src_idx=None, reduce_src=-1, reduce_into=None, sink_params=None,
+                   g0_sum=False):
     """Returns (list of per-row source grads or None, d_params (n_chunks, P)).
     aligned / g0_idx / d_src_idx / reduce_src: fused-aggregation path; the
     gradient rows of source `reduce_src` are segment-summed and ADDED into the
-    existing tensor `reduce_into` ([batch, n_seg, width])."""
+    existing tensor `reduce_into` ([batch, n_seg, width]).
+    g0_sum: g0 is (n, rows, d_out) for a batch-1 descriptor and dOut is its sum over n (the
+    backward of an expand()); summed inside the fused kernel's loads where that exists."""
     lib = L.load()
     dev = srcs[0][0].device
     bd = L.RowMlpBwd()
@@ -380,6 +383,13 @@ def rowmlp_bwd_raw(srcs, W, batch, rows, residual, tiles, precision, g0, need_sr
             d_srcs.append(g)
         else:
             d_srcs.append(None)
+    if g0_sum and g0 is not None and g0.shape[0] > 1:
+        assert batch == 1 and g1 is None and not residual
+        bd.g0_sum_count, bd.g0_sum_stride = g0.shape[0], g0.stride(0)
+        if lib.nlam_rowmlp_bwd_stages(ctypes.byref(bd)) != 2 or W.d_out != 64:
+            bd.g0_sum_count, bd.g0_sum_stride = 0, 0  # no fused kernel here: sum first
+            g0 = g0.sum(0, keepdim=True)
+            bd.g0 = g0.data_ptr()
     sink = _grad_sink(sink_params) if (W.n_chunks == 1 and sink_params is not None) else None
     if sink is not None:
         d_params = None  # gradients are accumulated in place; autograd gets None
@@ -413,7 +423,7 @@ def rowmlp_bwd_raw(srcs, W, batch, rows, residual, tiles, precision, g0, need_sr
         w_bytes = 4 * W.n_chunks * W.param_floats()
         rows_all = batch * rows
         # output-gradient rows read: dense g0 rows + the DISTINCT gathered g1 rows
-        dout_bytes = (rows_all * 4 * W.d_out if g0 is not None else 0) \
+        dout_bytes = (4 * g0.numel() if g0 is not None else 0) \
             + (4 * g1.numel() if g1 is not None else 0)
         # source-gradient rows written: one row per (batch, row) and source, except the
         # segment-reduced source (read-modify-write of its [batch, n_seg, width] target)
@@ -575,6 +585,41 @@ def mlp_forward_cat(module, xs):
         raise ValueError(f"mlp_forward_cat: widths {[x.shape[-1] for x in xs3]} != {W.k}")
     meta = {"precision": get_precision(), "params": W.t}
     return _RowMLPCatFn.apply(meta, *W.t, *xs3)
+
+
+class _RowMLPExpandFn(torch.autograd.Function):
+    """MLP(x).expand(B, -1, -1) for batch-less x (static graph features): the backward takes
+    the (B, rows, d_out) gradient as it is and sums its batch slices inside the kernel's
+    loads, instead of autograd's expand-backward writing and re-reading a summed copy."""
+
+    @staticmethod
+    def forward(ctx, meta, w1, b1, w2, b2, ln_g, ln_b, x):
+        W = Weights(w1, b1, w2, b2, ln_g, ln_b, 1)
+        x3 = _rows3d(x, "mlp input")
+        out = rowmlp_fwd_raw([(x3, None)], W, 1, x3.shape[1], False, None, meta["precision"])
+        ctx.meta = meta
+        ctx.save_for_backward(w1, b1, w2, b2, ln_g, ln_b, x3)
+        return out.expand(meta["batch"], -1, -1)
+
+    @staticmethod
+    def backward(ctx, gout):
+        w1, b1, w2, b2, ln_g, ln_b, x3 = ctx.saved_tensors
+        meta = ctx.meta
+        W = Weights(w1, b1, w2, b2, ln_g, ln_b, 1)
+        d_srcs, d_params = rowmlp_bwd_raw(
+            [(x3, None)], W, 1, x3.shape[1], False, None, meta["precision"], gout,
+            [ctx.needs_input_grad[7]], sink_params=meta.get("params"), g0_sum=True)
+        return (None, *W.split_grads(d_params), d_srcs[0])
+
+
+def mlp_forward_expand(module, x, batch):
+    """`module(x).unsqueeze(0).expand(batch, -1, -1)` for x (rows, K) -- the reference's
+    `expand_to_batch(embedder(static_features), B)` (base_graph_model.py:125-152)."""
+    W = weights_of(module)
+    if x.dim() != 2 or W.n_chunks != 1:
+        raise ValueError("mlp_forward_expand: (rows, K) input, one weight set")
+    meta = {"precision": get_precision(), "params": W.t, "batch": int(batch)}
+    return _RowMLPExpandFn.apply(meta, *W.t, x.unsqueeze(0))
 
 
 def mlp_forward(module, x, residual=False):
