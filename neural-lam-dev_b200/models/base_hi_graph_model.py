@@ -43,7 +43,7 @@ class BaseHiGraphModel(BaseGraphModel):
         batch_size = mesh_rep.shape[0]
 
         def embed(embs, feats):
-            return [self.expand_to_batch(e(f), batch_size) for e, f in zip(embs, feats)]
+            return [self.embed_static(e, f, batch_size) for e, f in zip(embs, feats)]
 
         mesh_rep_levels = [mesh_rep] + embed(list(self.mesh_embedders)[1:],
                                              list(self.mesh_static_features)[1:])
