@@ -1,6 +1,8 @@
 // Fused bf16 tcgen05 row-MLP BACKWARD (input gradients + weight gradients in one
-// kernel) for the square 64-wide case (d_hidden = d_out = source widths = 64, one
-// weight set): every InteractionNet edge / node MLP of the d=64 models.
+// kernel) for d_hidden = 64 and one weight set: every InteractionNet edge / node MLP of
+// the d=64 models (all sources 64 wide), the LayerNorm-free output map (d_out < 64,
+// zero-padded) and, as variant FG = false, the embedders (narrow inputs, no source
+// gradients).
 //
 // One persistent CTA per SM, 512 threads = two CONTEXTS of 256 threads.  Each context
 // is an independent pipeline over 128-row tiles (gather z -> GEMM1 -> SiLU -> GEMM2 ->
@@ -13,9 +15,13 @@
 // image ever goes to HBM.  At the end the two contexts' accumulators are added in
 // a fixed order into the CTA's partial slot (deterministic).
 //
-// Shared memory (201 KB): W1 / W2 bf16 operands staged once per SM (32 KB) + per
-// context 80 KB = z tile (48 KB, later the fp32 staging of the dZ rows) | a -> dH
-// tile (16 KB) | dOut (bf16, staged coalesced) -> dY tile (16 KB).
+// Shared memory (221 KB): W1 / W2 bf16 operands staged once per SM (32 KB) + per
+// context 80 KB = z tile (48 KB) | dOut (bf16, staged coalesced) -> dY tile (16 KB) |
+// a -> dH tile (16 KB) -- the first four blocks double as two fp32 staging buffers of
+// the dZ rows -- + 10 KB of double-buffered index tables (rows to gather / scatter,
+// segment boundaries; fetched one tile ahead).  Tiles are dealt SM-major.  Programmatic
+// dependent launch: prologue (and, when the inputs are known to be old, the first tile's
+// gather + GEMM 1) run before griddepcontrol.wait.
 // TMEM (512 columns, 256 per context): H (64) | Y (64), recycled as dA and the
 // double-buffered dZ | dW1^T rows 0..127 (64, M=128) | 64 columns shared by two M=64
 // accumulators -- an M=64 UMMA writes row i to lane 32*(i/16) + i%16, so dW1^T rows
