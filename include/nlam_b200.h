@@ -6,10 +6,13 @@
  * top of PyG/ATen); every entry point below replaces a piece
  * of Python in /root/reference and cites it.  All pointers are DEVICE
  * pointers unless said otherwise; sizes are element counts; `stream` is a
- * cudaStream_t passed as void*.  No function allocates, synchronises or keeps
- * mutable global state (re-entrant; CUDA-graph capturable); workspaces are
- * caller-provided.  Every function returns 0 on success; otherwise
- * nlam_last_error() (thread-local) describes the failure.
+ * cudaStream_t passed as void*.  No compute function allocates device memory or
+ * synchronises (re-entrant; CUDA-graph capturable); workspaces are caller-provided.
+ * Process-wide state is limited to three things, all mutex/atomic protected: the
+ * tuning switches of nlam_set_option, a per-(kernel, device) cache of shared-memory
+ * opt-ins, and the per-(device, stream) queues of DEFERRED parameter-gradient
+ * reductions (stage_mask bit 8; see nlam_rowmlp_bwd_flush).  Every function returns 0
+ * on success; otherwise nlam_last_error() (thread-local) describes the failure.
  *
  * Row-MLP: out[b,r,:] = [residual +] LN( W2 * SiLU( W1 * concat_s src_s[b, idx_s[r], :] + b1 ) + b2 )
  * which covers, with different gather descriptors,
@@ -225,12 +228,16 @@ size_t nlam_rowmlp_param_floats(const nlam_rowmlp* desc); /* per chunk */
 int nlam_rowmlp_bwd_stages(const nlam_rowmlp_bwd* desc);
 int nlam_rowmlp_bwd_run(const nlam_rowmlp_bwd* desc, void* stream);
 /* Deferred parameter-gradient reductions.  A run with stage_mask bit 3 (value 8) set
- * does not launch its own partial reduction but queues it (process-wide, thread
- * safe); nlam_rowmlp_bwd_flush runs every queued reduction in ONE launch on `stream`
- * (which must be ordered after the runs).  The caller keeps the runs' workspaces and
- * d_params alive until the flush.  nlam_rowmlp_bwd_pending = queued reductions. */
+ * does not launch its own partial reduction but queues it on the queue of (current
+ * device, `stream`) (thread safe); nlam_rowmlp_bwd_flush runs every reduction queued
+ * for (current device, `stream`) in ONE launch on that stream.  The caller keeps the
+ * runs' workspaces and d_params alive until the flush.  nlam_rowmlp_bwd_pending =
+ * queued reductions over all queues; nlam_rowmlp_bwd_discard drops the queue of
+ * (current device, `stream`) without running it (a backward pass that failed half-way
+ * must not leave pointers to freed workspaces behind). */
 int nlam_rowmlp_bwd_flush(void* stream);
 int nlam_rowmlp_bwd_pending(void);
+int nlam_rowmlp_bwd_discard(void* stream);
 int nlam_segsum_run(const nlam_segsum* desc, void* stream);
 int64_t nlam_state_step_partials(int64_t rows);
 int nlam_state_step_fwd(const nlam_state_step* desc, void* stream);

@@ -3,6 +3,9 @@
 #include <stdlib.h>
 
 #include <atomic>
+#include <map>
+#include <mutex>
+#include <utility>
 #include <string.h>
 
 #include "common.cuh"
@@ -29,6 +32,23 @@ int option_dgrad_mc() { return g_dgrad_mc.load(); }
 int option_bwd_fused() { return g_bwd_fused.load(); }
 int option_pdl() { return g_pdl.load(); }
 void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+// largest opt-in so far per (kernel, device)
+static std::mutex g_smem_mutex;
+static std::map<std::pair<const void*, int>, int> g_smem_set;
+cudaError_t ensure_dyn_smem(const void* kern, int bytes) {
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  std::lock_guard<std::mutex> lk(g_smem_mutex);
+  int& have = g_smem_set[{kern, dev}];
+  if (bytes > have) {
+    e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    if (e != cudaSuccess) return e;
+    have = bytes;
+  }
+  return cudaSuccess;
+}
 }  // namespace nlam
 
 using namespace nlam;
@@ -91,3 +111,6 @@ extern "C" int nlam_rowmlp_bwd_flush(void* stream) {
   return reduce_params_flush((cudaStream_t)stream);
 }
 extern "C" int nlam_rowmlp_bwd_pending(void) { return reduce_params_pending(); }
+extern "C" int nlam_rowmlp_bwd_discard(void* stream) {
+  return reduce_params_discard((cudaStream_t)stream);
+}

@@ -10,6 +10,9 @@ namespace nlam {
 
 void set_error(const char* fmt, ...);
 void count_launch(int n = 1);
+// Opt a kernel in for `bytes` of dynamic shared memory on the CURRENT device (cached per
+// kernel and device: a process may drive several GPUs).
+cudaError_t ensure_dyn_smem(const void* kern, int bytes);
 int option_fwd_mc();    // -1 auto, 0 off, 1 force
 int option_dgrad_mc();
 int option_bwd_fused();
@@ -103,5 +106,6 @@ size_t tc_rowmlp_bwd_workspace(const nlam_rowmlp& d);
 bool tc_rowmlp_bwd_is_fused(const nlam_rowmlp_bwd& d);
 int reduce_params_flush(cudaStream_t st);  // rowmlp_simt.cu: deferred partial reductions
 int reduce_params_pending();
+int reduce_params_discard(cudaStream_t st);  // drop queued jobs (a backward pass failed half-way)
 
 }  // namespace nlam

@@ -18,7 +18,9 @@
 #include <math.h>
 
 #include <algorithm>
+#include <map>
 #include <mutex>
+#include <utility>
 #include <vector>
 
 #include "rowmlp_common.cuh"
@@ -679,11 +681,20 @@ __global__ void __launch_bounds__(256) reduce_params_batch_kernel(const __grid_c
 // accumulates into an output already queued (weights used several times in a step,
 // e.g. an unrolled rollout) goes to the next wave, so the order of accumulation is
 // that of the immediate mode
+// One queue per (device, stream): a flush on one stream never runs (or drops) reductions
+// whose producers were enqueued on another stream or GPU.
+typedef std::vector<std::vector<RParams>> RWaves;
 static std::mutex g_rq_mutex;
-static std::vector<std::vector<RParams>> g_rq;
+static std::map<std::pair<int, cudaStream_t>, RWaves> g_rqs;
+static std::pair<int, cudaStream_t> rq_key(cudaStream_t st) {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  return {dev, st};
+}
 static int queue_or_launch_reduce(const RParams& rp, bool defer, cudaStream_t st) {
   if (defer) {
     std::lock_guard<std::mutex> lk(g_rq_mutex);
+    RWaves& g_rq = g_rqs[rq_key(st)];
     size_t wave = 0;
     for (size_t w = 0; w < g_rq.size(); ++w)
       for (const RParams& q : g_rq[w])
@@ -699,10 +710,13 @@ static int queue_or_launch_reduce(const RParams& rp, bool defer, cudaStream_t st
   return 0;
 }
 int reduce_params_flush(cudaStream_t st) {
-  std::vector<std::vector<RParams>> waves;
+  RWaves waves;
   {
     std::lock_guard<std::mutex> lk(g_rq_mutex);
-    waves.swap(g_rq);
+    auto it = g_rqs.find(rq_key(st));
+    if (it == g_rqs.end()) return 0;
+    waves.swap(it->second);
+    g_rqs.erase(it);
   }
   for (const std::vector<RParams>& jobs : waves)
   for (size_t i = 0; i < jobs.size(); i += RB_MAX) {
@@ -725,8 +739,14 @@ int reduce_params_flush(cudaStream_t st) {
 int reduce_params_pending() {
   std::lock_guard<std::mutex> lk(g_rq_mutex);
   size_t n = 0;
-  for (const auto& w : g_rq) n += w.size();
+  for (const auto& kv : g_rqs)
+    for (const auto& w : kv.second) n += w.size();
   return (int)n;
+}
+int reduce_params_discard(cudaStream_t st) {
+  std::lock_guard<std::mutex> lk(g_rq_mutex);
+  g_rqs.erase(rq_key(st));
+  return 0;
 }
 
 int launch_reduce_params(const float* partial, int splits, int n_chunks, int p_total, float* out,
@@ -745,12 +765,7 @@ int launch_reduce_params(const float* partial, int splits, int n_chunks, int p_t
 template <int DP>
 static int launch_fwd(const KParams& p, cudaStream_t st) {
   using C = Cfg<DP>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    NLAM_CUDA(cudaFuncSetAttribute(rowmlp_fwd_kernel<DP>,
-                                   cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM));
-    attr_set = true;
-  }
+  NLAM_CUDA(ensure_dyn_smem((const void*)rowmlp_fwd_kernel<DP>, (int)C::SMEM));
   dim3 grid(n_tiles_of(p.d), p.d.batch);
   rowmlp_fwd_kernel<DP><<<grid, NT, C::SMEM, st>>>(p);
   NLAM_CUDA(cudaGetLastError());
@@ -815,12 +830,7 @@ template <int DP>
 static int launch_bwd(const KParams& p, const WParams& wp, const RParams& rp, int mask,
                       cudaStream_t st) {
   using C = Cfg<DP>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    NLAM_CUDA(cudaFuncSetAttribute(rowmlp_bwd_kernel<DP>,
-                                   cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM));
-    attr_set = true;
-  }
+  NLAM_CUDA(ensure_dyn_smem((const void*)rowmlp_bwd_kernel<DP>, (int)C::SMEM));
   if (mask & 1) {
     dim3 grid(n_tiles_of(p.d), p.d.batch);
     rowmlp_bwd_kernel<DP><<<grid, NT, C::SMEM, st>>>(p);

@@ -372,12 +372,8 @@ int tc_rowmlp_fwd(const nlam_rowmlp& d, cudaStream_t st) {
   int grid = 148 * per_sm;
   if (grid > g.total_tiles) grid = g.total_tiles;
   const int fn = tc::fast_n(p);
-  auto launch = [&](auto kern, int& max_set) -> int {
-    if ((int)g.smem_bytes > max_set) {
-      NLAM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     (int)g.smem_bytes));
-      max_set = (int)g.smem_bytes;
-    }
+  auto launch = [&](auto kern, int&) -> int {
+    NLAM_CUDA(ensure_dyn_smem((const void*)kern, (int)g.smem_bytes));
     NLAM_CUDA(launch_k(kern, grid, tc::NT, g.smem_bytes, st, p, g));
     return 0;
   };

@@ -977,11 +977,8 @@ int tc_rowmlp_bwd(const nlam_rowmlp_bwd& bd, cudaStream_t st) {
                                                                     g.vec_len - ws.partial), st));
   const int fn = tc::fast_n(p);
   const int gd = ws.d_slots, gw = ws.w_slots;
-  auto launch = [&](auto kern, int& max_set, int grid, uint32_t smem) -> int {
-    if ((int)smem > max_set) {
-      NLAM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      max_set = (int)smem;
-    }
+  auto launch = [&](auto kern, int&, int grid, uint32_t smem) -> int {
+    NLAM_CUDA(ensure_dyn_smem((const void*)kern, (int)smem));
     kern<<<grid, tc::NT, smem, st>>>(p, g);
     NLAM_CUDA(cudaGetLastError());
     count_launch();

@@ -790,14 +790,8 @@ int tc_bwd_fused_grid(const tc::BGeo& g) {
 }
 
 int tc_rowmlp_bwd_fused(const KParams& p, const tc::BGeo& g, cudaStream_t st) {
-  static bool attr = false;
-  if (!attr) {
-    NLAM_CUDA(cudaFuncSetAttribute(tc::rowmlp_tc_bwd_fused_kernel<true>,
-                                   cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::FU_SMEM));
-    NLAM_CUDA(cudaFuncSetAttribute(tc::rowmlp_tc_bwd_fused_kernel<false>,
-                                   cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::FU_SMEM));
-    attr = true;
-  }
+  NLAM_CUDA(ensure_dyn_smem((const void*)tc::rowmlp_tc_bwd_fused_kernel<true>, (int)tc::FU_SMEM));
+  NLAM_CUDA(ensure_dyn_smem((const void*)tc::rowmlp_tc_bwd_fused_kernel<false>, (int)tc::FU_SMEM));
   if (tc_bwd_fused_kind(p) == 2)
     NLAM_CUDA(launch_k(tc::rowmlp_tc_bwd_fused_kernel<true>, tc_bwd_fused_grid(g), tc::FU_NT,
                        tc::FU_SMEM, st, p, g));

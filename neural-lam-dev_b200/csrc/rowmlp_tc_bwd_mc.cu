@@ -515,12 +515,7 @@ int tc_dgrad_mc_grid(const tc::BGeo& g) {
 }
 
 int tc_rowmlp_dgrad_mc(const KParams& p, const tc::BGeo& g, cudaStream_t st) {
-  static bool attr = false;
-  if (!attr) {
-    NLAM_CUDA(cudaFuncSetAttribute(tc::rowmlp_tc_dgrad_mc_kernel,
-                                   cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::DM_SMEM));
-    attr = true;
-  }
+  NLAM_CUDA(ensure_dyn_smem((const void*)tc::rowmlp_tc_dgrad_mc_kernel, (int)tc::DM_SMEM));
   tc::rowmlp_tc_dgrad_mc_kernel<<<tc_dgrad_mc_grid(g), tc::DM_NT, tc::DM_SMEM, st>>>(p, g);
   NLAM_CUDA(cudaGetLastError());
   count_launch();

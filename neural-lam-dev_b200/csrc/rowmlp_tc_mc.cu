@@ -297,12 +297,7 @@ bool tc_fwd_mc_supported(const KParams& p) {
 }
 
 int tc_rowmlp_fwd_mc(const KParams& p, const tc::Geo& g, cudaStream_t st) {
-  static bool attr = false;
-  if (!attr) {
-    NLAM_CUDA(cudaFuncSetAttribute(tc::rowmlp_tc_fwd_mc_kernel,
-                                   cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::MC_SMEM));
-    attr = true;
-  }
+  NLAM_CUDA(ensure_dyn_smem((const void*)tc::rowmlp_tc_fwd_mc_kernel, (int)tc::MC_SMEM));
   int grid = (g.total_tiles + tc::MC_WG - 1) / tc::MC_WG;
   if (grid > 148) grid = 148;
   NLAM_CUDA(launch_k(tc::rowmlp_tc_fwd_mc_kernel, grid, tc::MC_NT, tc::MC_SMEM, st, p, g));

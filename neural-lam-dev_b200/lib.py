@@ -133,6 +133,7 @@ SYMBOLS = {
     "nlam_rowmlp_bwd_run": (ctypes.c_int, [ctypes.POINTER(RowMlpBwd), ctypes.c_void_p]),
     "nlam_rowmlp_bwd_flush": (ctypes.c_int, [ctypes.c_void_p]),
     "nlam_rowmlp_bwd_pending": (ctypes.c_int, []),
+    "nlam_rowmlp_bwd_discard": (ctypes.c_int, [ctypes.c_void_p]),
     "nlam_segsum_run": (ctypes.c_int, [ctypes.POINTER(SegSum), ctypes.c_void_p]),
     "nlam_state_step_partials": (ctypes.c_int64, [ctypes.c_int64]),
     "nlam_state_step_fwd": (ctypes.c_int, [ctypes.POINTER(StateStep), ctypes.c_void_p]),

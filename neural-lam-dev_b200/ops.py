@@ -54,6 +54,21 @@ def set_deferred_param_reduce(enabled):
 _deferred_keep = []  # workspaces / gradient buffers of queued reductions
 
 
+def scoped_trainer_flags(sink, defer):
+    """Set (grad_sink, defer_reduce) and return the previous pair (train.py scopes both to
+    its own forward/backward).  Does not flush: the caller does."""
+    prev = (_state.get("grad_sink", False), _state.get("defer_reduce", False))
+    _state["grad_sink"], _state["defer_reduce"] = bool(sink), bool(defer)
+    return prev
+
+
+def discard_param_grads():
+    """Drop the queued reductions of the current stream without running them (error path)."""
+    if torch.cuda.is_available():
+        L.load().nlam_rowmlp_bwd_discard(_stream())
+    _deferred_keep.clear()
+
+
 def flush_param_grads():
     """Run every queued parameter-gradient reduction (one kernel) on the current stream."""
     lib = L.load()

@@ -66,21 +66,32 @@ class FlatGradBuckets:
         self.overlap = overlap and world_size > 1 and self.n_early > 0 and dev.type == "cuda"
         self._pending = 0
         self._early_started = False
+        self._enc_pending = 0  # encoder outputs (one per AR step) whose gradient is still to come
         self._early_params = [p for _, p in early]
         self._early_work = None
         self.side = torch.cuda.Stream(device=dev) if self.overlap else None
-        if self.overlap:
-            for p in self._early_params:
-                p.register_post_accumulate_grad_hook(self._hook)
 
     def zero(self):
         self.flat.zero_()
         self._pending = len(self._early_params)
         self._early_work = None
         self._early_started = False
+        self._enc_pending = 0
+
+    def expect_encoder_output(self):
+        """Forward pass: one more encoder output (AR step) downstream of which the early
+        bucket's parameters are used."""
+        self._enc_pending += 1
 
     def early_ready(self, grad=None):
-        """All gradients of the early bucket are enqueued on the compute stream."""
+        """Backward hook of ONE encoder output.  An unrolled rollout has one per AR step
+        and backward visits them last step first, each followed by more decoder /
+        processor gradient contributions of the earlier steps: the early bucket is only
+        final -- and may only be handed to NCCL -- when the FIRST step's encoder-output
+        gradient has arrived, i.e. when every registered hook has fired."""
+        self._enc_pending -= 1
+        if self._enc_pending > 0:
+            return grad
         if self.flat.is_cuda and torch.cuda.is_current_stream_capturing():
             return grad
         if self.overlap and self._early_work is None and not self._early_started:
@@ -88,12 +99,6 @@ class FlatGradBuckets:
             ops.flush_param_grads()  # the early bucket's gradients must be final
             self._launch_early()
         return grad
-
-    def _hook(self, _param):
-        self._pending -= 1
-        if self._pending == 0 and not self._early_started:
-            self._early_started = True
-            self._launch_early()
 
     def _launch_early(self):
         if True:
@@ -153,27 +158,41 @@ class DataParallelTrainer:
         self.buckets = FlatGradBuckets(list(model.named_parameters()), world_size,
                                        EARLY_PREFIXES, overlap)
         self.optimizer = model.configure_optimizers()
+        # During THIS trainer's forward/backward (and only then, see _forward_backward)
         # weight gradients go straight into the flat buffer (no per-parameter
-        # accumulation kernels); autograd then never "sees" them, so the early
-        # all-reduce is triggered by the backward of the encoder output instead
-        ops.set_param_grad_sink(True)
-        # ... and their per-MLP partial reductions are queued and run by one launch
-        # (ops.flush_param_grads) after backward / before the early all-reduce
-        ops.set_deferred_param_reduce(True)
+        # accumulation kernels; autograd never "sees" them, so the early all-reduce is
+        # triggered by the backward of the encoder output instead) and their per-MLP
+        # partial reductions are queued and run by one launch (ops.flush_param_grads)
+        # after backward / before the early all-reduce.
         if self.buckets.overlap and hasattr(model, "g2m_gnn"):
             model.g2m_gnn.register_forward_hook(self._encoder_output_hook)
 
     def _encoder_output_hook(self, _module, _inputs, output):
         # fires in backward once everything downstream of the g2m encoder (decoder,
         # processor) has been differentiated, i.e. its kernels are enqueued
-        if torch.is_tensor(output) and output.requires_grad:
+        if torch.is_tensor(output) and output.requires_grad and self._in_step:
+            self.buckets.expect_encoder_output()
             output.register_hook(self.buckets.early_ready)
+
+    _in_step = False
 
     def _forward_backward(self, batch):
         self.buckets.zero()
-        loss = self.model.training_step(batch)
-        loss.backward()
-        ops.flush_param_grads()  # queued parameter-gradient reductions: one launch
+        # the gradient sink / deferred reduction are process-wide switches of ops: scope
+        # them to this call so that plain `loss.backward(); optimizer.step()` elsewhere in
+        # the process (another model, the eval helpers) keeps its complete .grad
+        prev = ops.scoped_trainer_flags(True, True)
+        self._in_step = True
+        try:
+            loss = self.model.training_step(batch)
+            loss.backward()
+            ops.flush_param_grads()  # queued parameter-gradient reductions: one launch
+        except BaseException:
+            ops.discard_param_grads()  # never leave pointers to dead workspaces queued
+            raise
+        finally:
+            self._in_step = False
+            ops.scoped_trainer_flags(*prev)
         return loss.detach()
 
     def _eager_step(self, batch):

@@ -81,3 +81,27 @@ def test_flat_buckets_layout():
         assert p.grad.data_ptr() >= fb.flat.data_ptr()  # still views of the flat buffer
     fb.zero()
     assert all(float(p.grad.abs().sum()) == 0 for p in lin.parameters())
+
+
+def test_early_bucket_waits_for_every_ar_step():
+    """An unrolled rollout registers one encoder-output hook per AR step; backward visits
+    them last step first, and the decoder / processor gradients of the earlier steps are
+    written AFTER the later steps' hooks fire.  The early all-reduce may only start with
+    the last hook (= first AR step)."""
+    from neural_lam_b200 import train
+    lin = torch.nn.Linear(3, 2)
+    fb = train.FlatGradBuckets([("processor.w", lin.weight), ("enc.b", lin.bias)], 1, ("processor",))
+    launched = []
+    fb.overlap = True  # the collective itself is replaced below (needs CUDA + NCCL)
+    fb._launch_early = lambda: launched.append(fb._enc_pending)
+    fb.zero()
+    for _ in range(3):  # forward of a 3-step rollout
+        fb.expect_encoder_output()
+    for step in range(3):  # backward
+        fb.early_ready(None)
+        assert len(launched) == (1 if step == 2 else 0)
+    assert launched == [0]
+    fb.zero()
+    fb.expect_encoder_output()
+    fb.early_ready(None)
+    assert len(launched) == 2

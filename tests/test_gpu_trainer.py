@@ -37,16 +37,17 @@ def test_grad_sink_equals_autograd(dev):
     loss.backward()
     want = {n: p.grad.clone() for n, p in model.named_parameters()}
     model2, _ = _model(dev)
-    trainer = train.DataParallelTrainer(model2)  # enables the sink + deferred reductions
+    trainer = train.DataParallelTrainer(model2)  # flat gradient buffer
     trainer.buckets.zero()
+    prev = ops.scoped_trainer_flags(True, True)  # what the trainer does around its backward
+    assert prev == (False, False)  # constructing a trainer leaves the process-wide flags alone
     loss2 = model2.training_step(batch)
     loss2.backward()
     from neural_lam_b200 import lib
     assert lib.load().nlam_rowmlp_bwd_pending() > 0  # queued, not yet reduced
     ops.flush_param_grads()
     assert lib.load().nlam_rowmlp_bwd_pending() == 0
-    ops.set_param_grad_sink(False)
-    ops.set_deferred_param_reduce(False)
+    ops.scoped_trainer_flags(*prev)
     assert torch.equal(loss, loss2)
     for n, p in model2.named_parameters():
         torch.testing.assert_close(p.grad, want[n], rtol=1e-6, atol=1e-7, msg=n)
@@ -63,9 +64,46 @@ def test_trainer_paths_agree(dev, graph):
     la = [ta.step(batch).item() for _ in range(3)]
     host = tuple(t.cpu().pin_memory() for t in batch)
     lb = tb.fit_from_host([host] * 3)
-    ops.set_param_grad_sink(False)
-    ops.set_deferred_param_reduce(False)
     assert la == pytest.approx(lb, rel=1e-5)
     assert la[2] < la[0]  # it trains
     for p, q in zip(model_a.parameters(), model_b.parameters()):
         torch.testing.assert_close(p, q, rtol=1e-5, atol=1e-7)
+
+
+def test_trainer_leaves_plain_autograd_intact(dev):
+    """A trainer step must not leave the gradient sink / deferred reductions switched on:
+    plain `loss.backward()` afterwards yields complete gradients with nothing queued."""
+    from neural_lam_b200 import lib, ops, train
+    model, batch = _model(dev)
+    trainer = train.DataParallelTrainer(model)
+    trainer.step(batch)
+    assert (ops._state.get("grad_sink", False), ops._state.get("defer_reduce", False)) == (False, False)
+    other, _ = _model(dev)
+    ref, _ = _model(dev)
+    for m in (other, ref):
+        m.training_step(batch).backward()
+    assert lib.load().nlam_rowmlp_bwd_pending() == 0
+    for (n, p), q in zip(other.named_parameters(), ref.parameters()):
+        assert p.grad is not None and torch.equal(p.grad, q.grad), n
+
+
+def test_failed_backward_leaves_no_queued_reductions(dev):
+    from neural_lam_b200 import lib, ops, train
+    model, batch = _model(dev)
+    trainer = train.DataParallelTrainer(model)
+
+    class Boom(RuntimeError):
+        pass
+
+    def raise_boom(_grad):
+        raise Boom("backward interrupted")
+
+    # fails once the decoder / processor backward has already queued its reductions
+    handle = model.g2m_gnn.register_forward_hook(
+        lambda _m, _i, out: out.register_hook(raise_boom) and None)
+    with pytest.raises(Boom):
+        trainer.step(batch)
+    handle.remove()
+    assert lib.load().nlam_rowmlp_bwd_pending() == 0
+    assert (ops._state.get("grad_sink", False), ops._state.get("defer_reduce", False)) == (False, False)
+    trainer.step(batch)  # and the trainer still works afterwards
