@@ -54,6 +54,7 @@ def parse():
     ap.add_argument("--scale", type=int, default=1,
                     help="domain scale of the synthetic MEPS grid (2 = 536x476, configs[4])")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-fp32-line", action="store_true")
     ap.add_argument("--cuda-graph", type=int, default=1,
                     help="replay the train step as one CUDA graph (single-GPU runs)")
     return ap.parse_args()
@@ -147,61 +148,107 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------ CPU arm
-def time_cpu_oracle(a, steps, warmup):
-    """Reference CPU path (oracle port) on the host cores: samples/s for one
-    sample per step, fwd + bwd + AdamW."""
+def _cpu_model(a):
+    """(model, kind, describe): the reference's own GraphLAM / HiLAM / HiLAMParallel on the
+    CPU -- the UNMODIFIED reference files (imported from /root/reference in the build
+    container, from the archive oracle/stage_ref.py packed of them on the GPU box) behind
+    oracle/ref_stubs.py; oracle/port.py (the restatement pinned to them) only when neither
+    is present."""
     import torch
+    import torch._dynamo  # noqa: F401  (torch.optim imports it lazily and it probes
+    #                       importlib specs: must happen before the stub modules exist)
 
-    from neural_lam_b200 import synthetic
-    from oracle import port
+    from oracle import ref_stubs
 
-    cores = os.cpu_count()
-    torch.set_num_threads(cores)
     with tempfile.TemporaryDirectory() as root:
         ds, args = make_case(root, a)
         torch.manual_seed(42)
-        model = port.MODELS[a.model](args, None, ds)
+        if ref_stubs.reference_location() is not None:
+            ref_stubs.import_reference()
+            from neural_lam import config as ref_config
+            from neural_lam import models as ref_models
+
+            cls = {"graph_lam": ref_models.GraphLAM, "hi_lam": ref_models.HiLAM,
+                   "hi_lam_parallel": ref_models.HiLAMParallel}[a.model]
+            cfg = ref_config.NeuralLAMConfig(
+                datastore=ref_config.DatastoreSelection(kind="mdp", config_path=""))
+            model = cls(args, cfg, ds)
+            kind = "reference"
+            what = ("the unmodified reference files (neural_lam.models, PyG MessagePassing "
+                    "restated by oracle/ref_stubs.py)")
+        else:
+            from oracle import port
+
+            model = port.MODELS[a.model](args, None, ds)
+            kind, what = "port", "oracle/port.py (restatement pinned to the reference)"
+    return model, ds, kind, what
+
+
+def time_cpu_reference(a, steps, warmup, batch):
+    """The reference's CPU path on the host cores (all of them): samples/s of
+    training_step + backward + AdamW at `batch` samples per step, fp32."""
+    import torch
+
+    from neural_lam_b200 import synthetic
+
+    import contextlib
+
+    cores = os.cpu_count()
+    torch.set_num_threads(cores)
+    with contextlib.redirect_stdout(sys.stderr):  # the reference prints while it builds
+        model, ds, kind, what = _cpu_model(a)
     opt = model.configure_optimizers()
-    batch = synthetic.synthetic_batch(ds, 1, a.ar_steps, seed=1)
+    batch_t = synthetic.synthetic_batch(ds, batch, a.ar_steps, seed=1)
     times = []
     for i in range(warmup + steps):
         t0 = time.perf_counter()
         opt.zero_grad()
-        loss = model.training_step(batch)
+        loss = model.training_step(batch_t)
         loss.backward()
         opt.step()
         times.append(time.perf_counter() - t0)
     timed = times[warmup:]
     total = sum(timed)
-    return {"value": len(timed) / total, "unit": UNIT, "cores": cores, "kind": "port",
-            "sample": f"{len(timed)} train steps (fwd+bwd+AdamW) of batch 1 after {warmup} warm-up, "
-                      "oracle/port.py (reference restatement) in fp32 on CPU",
-            "ms_per_step": 1e3 * total / len(timed)}
+    return {"value": batch * len(timed) / total, "unit": UNIT, "cores": cores, "kind": kind,
+            "sample": f"{len(timed)} train steps (fwd+bwd+AdamW) of batch {batch} after {warmup} "
+                      f"warm-up, {what}, fp32, torch CPU with {cores} threads",
+            "ms_per_step": 1e3 * total / len(timed), "batch": batch,
+            "loss": float(loss.item())}
 
 
 def run_reference(a):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    res = time_cpu_oracle(a, a.steps, min(a.warmup, 2))
+    res = time_cpu_reference(a, a.steps, min(a.warmup, 2), a.batch)
     line = {
         "metric": METRIC, "value": res["value"], "unit": UNIT, "n_gpus": a.gpus,
-        "steps": a.steps, "warmup": a.warmup, "ms_per_step": res["ms_per_step"],
+        "steps": a.steps, "warmup": min(a.warmup, 2), "ms_per_step": res["ms_per_step"],
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-        "data": "synthetic", "config": config_dict(a, {"reference_sample_batch": 1}),
+        "data": "synthetic",
+        "config": config_dict(a, {"reference_sample_batch": res["batch"],
+                                  "global_batch": res["batch"], "parallelism": "cpu"}),
         "impl": "reference",
         "cpu_baseline": {k: res[k] for k in ("value", "unit", "cores", "kind", "sample")},
         "e2e": {"value": res["value"], "unit": UNIT, "h2d_bytes_per_step": 0,
                 "d2h_bytes_per_step": 0},
-        "gpu_launches": 0,
+        "gpu_launches": 0, "loss": res["loss"],
     }
     print(json.dumps(line), flush=True)
 
 
-def layer_edges_per_s(model, batch_size, device, iters=5):
+def layer_edges_per_s(model, batch_size, device, peaks, iters=5):
     """BASELINE metric (i): InteractionNet fwd+bwd edges/s per layer type, on the
-    model's own layers (MEPS g2m / m2m / m2g edge sets), CUDA-event timed."""
+    model's own layers (MEPS g2m / m2m / m2g edge sets), CUDA-event timed, with the
+    SURVEY.md 8(d) roofline fractions of the layer call:
+      flops_fwd = B (M 8 d^2 + N_r 6 d^2), fwd+bwd = 3 x (recompute not counted)
+      bytes_fwd = s d B (M(1+u) + N_s + 2 N_r) + 12 M
+      bytes_bwd = s d B (M(2+u) + 2 N_s + 3 N_r) + 12 M
+    (s = 4 bytes per stored element, u = 1 with update_edges, N_s counted once when it aliases
+    N_r; the input edge rows of a batch-shared static edge embedding count M d s once)."""
     import torch
+
+    from neural_lam_b200 import ops
 
     d = model.args.hidden_dim
     out = {}
@@ -210,14 +257,15 @@ def layer_edges_per_s(model, batch_size, device, iters=5):
               "m2g": (model.m2g_gnn, model.num_mesh_nodes, model.num_grid_nodes)}
     for name, (net, n_send, n_rec) in layers.items():
         M = net.edge_index.shape[1]
-        send = torch.randn(batch_size, n_send, d, device=device, requires_grad=True)
-        rec = send if name == "m2m" else torch.randn(batch_size, n_rec, d, device=device,
-                                                      requires_grad=True)
+        mk = lambda *shape: ops.make_shadow(torch.randn(*shape, device=device,
+                                                        requires_grad=True))
+        # inputs as the model hands them over: fp32 master + bf16 shadow (bf16 mode)
+        send = mk(batch_size, n_send, d)
+        rec = send if name == "m2m" else mk(batch_size, n_rec, d)
         if net.update_edges:
-            edge = torch.randn(batch_size, M, d, device=device, requires_grad=True)
+            edge = mk(batch_size, M, d)
         else:  # static edge embedding shared by the batch (stride-0 expand)
-            edge = torch.randn(M, d, device=device, requires_grad=True).unsqueeze(0).expand(
-                batch_size, -1, -1)
+            edge = ops.expand_with_shadow(mk(M, d), batch_size)
 
         def run():
             o = net(send, rec, edge)
@@ -234,7 +282,19 @@ def layer_edges_per_s(model, batch_size, device, iters=5):
         e1.record()
         torch.cuda.synchronize()
         ms = e0.elapsed_time(e1) / iters
-        out[name] = {"edges": M, "ms_fwd_bwd": ms, "edges_per_s": batch_size * M / (ms / 1e3)}
+        B, u, s = batch_size, (1 if net.update_edges else 0), 4
+        ns = 0 if name == "m2m" else n_send  # aliases N_r
+        e_in = M if net.update_edges else M / B  # static edge rows: once, not B x
+        by_fwd = s * d * B * (e_in + M * u + ns + 2 * n_rec) + 12 * M
+        by_bwd = s * d * B * (e_in + M * (1 + u) + 2 * ns + 3 * n_rec) + 12 * M
+        fl = 3 * B * (M * 8 * d * d + n_rec * 6 * d * d)
+        gbs, tfs = (by_fwd + by_bwd) / (ms / 1e3) / 1e9, fl / (ms / 1e3) / 1e12
+        out[name] = {"edges": M, "ms_fwd_bwd": ms, "edges_per_s": batch_size * M / (ms / 1e3),
+                     "algorithmic_bytes": by_fwd + by_bwd, "algorithmic_flops": fl,
+                     "achieved_gbs": gbs, "achieved_tflops": tfs,
+                     "hbm_frac": gbs / peaks["hbm_gbs"],
+                     "tensor_frac": tfs / peaks["bf16_tflops_sustained"],
+                     "frac": max(gbs / peaks["hbm_gbs"], tfs / peaks["bf16_tflops_sustained"])}
     model.zero_grad(set_to_none=False)
     return out
 
@@ -362,6 +422,11 @@ def run_ours(a):
                 "frac": gbs / peaks["hbm_gbs"], "traffic": traffic, "kernel": dominant,
                 "launches_timed": n_l, "avg_us": avg_s * 1e6,
                 "algorithmic_bytes_per_launch": dom_bytes,
+                "implementation_bytes_per_launch": timer.impl_bytes(dominant),
+                "bytes_convention": "SURVEY 8(d): distinct fp32 rows read + gradients at the size "
+                                    "the algorithm needs (batch-shared static rows once, node "
+                                    "gradients per node); implementation_bytes = rows this "
+                                    "kernel actually moves",
                 "tflops": dom_flops / avg_s / 1e12, "peak_src": peaks["src"],
                 "share_of_step_kernel_time": summ[dominant][1] / step_kernel_ms,
                 "timed": f"CUDA events around each launch over {a.steps} eager steps"}
@@ -389,15 +454,35 @@ def run_ours(a):
            "api": "DataParallelTrainer.fit_from_host(pinned batches)"}
 
     layers = None
+    fp32_mode = None
     if rank == 0 and world == 1:
-        ops.set_param_grad_sink(False)
-        ops.set_deferred_param_reduce(False)
         if a.model == "graph_lam":  # per-layer figure on the model's own g2m / m2m / m2g layers
-            layers = layer_edges_per_s(model, a.batch, device)
+            layers = layer_edges_per_s(model, a.batch, device, peaks)
+        if a.precision == "bf16" and is_default_case(a) and not a.no_fp32_line:
+            # the fp32 half of configs[1] ("bf16/fp32"): same model, weights and batches in
+            # the fp32 parity mode (FFMA kernels, rtol 1e-4 vs the reference), eager steps
+            ops.set_precision("fp32")
+            tr32 = train.DataParallelTrainer(model, rank, world, use_cuda_graph=False)
+            for i in range(2):
+                tr32.step(dev_batches[i % n_rot])
+            torch.cuda.synchronize()
+            e0.record()
+            n32 = 4
+            for i in range(n32):
+                l32 = tr32.step(dev_batches[i % n_rot])
+            e1.record()
+            torch.cuda.synchronize()
+            ms32 = e0.elapsed_time(e1) / n32
+            fp32_mode = {"value": a.batch / (ms32 / 1e3), "unit": UNIT, "ms_per_step": ms32,
+                         "steps": n32, "dtype": "f32", "loss": float(l32.item()),
+                         "note": "fp32 parity mode (FFMA row-MLP kernels), eager, device-resident"}
+            ops.set_precision(a.precision)
 
     cpu = None
     if rank == 0 and world == 1 and not a.no_cpu_baseline:
-        cpu = time_cpu_oracle(a, 3, 1)
+        # same config as the GPU arm where that stays within ~30 s of CPU work
+        cpu_batch = a.batch if is_default_case(a) else 1
+        cpu = time_cpu_reference(a, 3 if is_default_case(a) else 1, 1, cpu_batch)
         cpu = {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")}
 
     if rank == 0:
@@ -415,7 +500,8 @@ def run_ours(a):
                       "no explicit flush"}),
             "clocks": clk, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
             "cpu_baseline": cpu, "impl": "ours", "loss": float(loss.item()),
-            "interaction_net_fwd_bwd": layers,
+            "interaction_net_fwd_bwd": layers, "roofline_layers": layers,
+            "fp32_mode": fp32_mode,
         }
         print(json.dumps(line), flush=True)
     if world > 1:

@@ -47,6 +47,14 @@ typedef struct nlam_src {
                            ar_model.py:204-209) */
   int32_t ld;
   int32_t width;
+  /* Optional bf16 SHADOW of the same rows (NLAM_BF16 mode): dense rows of `width` bf16
+   * values, row i of batch b at shadow + (b*shadow_batch_stride + i*width) elements,
+   * written by the kernel that produced `ptr` (out_bf16 & co. below).  The tensor-core
+   * kernels read their MMA operands from it (half the gather bytes, no conversion; the
+   * TMA row-gather kernels need it); `ptr` stays the fp32 master for residuals. */
+  const void* shadow;
+  int64_t shadow_batch_stride; /* elements; 0 = shared */
+  int64_t shadow_rows;         /* rows per batch item of the shadow tensor */
 } nlam_src;
 
 /* Weights of make_mlp([K, d_hidden, d_out]) (+LayerNorm), nn.Linear layout
@@ -73,6 +81,8 @@ typedef struct nlam_agg {
   const float* scale;      /* [n_seg] or NULL */
   float* out;              /* [batch, n_seg, d_out]; NULL = no reduction */
   int32_t n_seg;
+  void* out_bf16;          /* optional bf16 shadow of `out` (may be given WITHOUT out: the
+                              aggregated messages only feed the node MLP's MMA) */
 } nlam_agg;
 
 typedef struct nlam_rowmlp {
@@ -100,6 +110,8 @@ typedef struct nlam_rowmlp {
                                  out_idx[r] (scatter back to original edge order) */
   nlam_agg agg;               /* optional fused segment reduction (out may then be NULL) */
   int32_t precision;          /* NLAM_FP32 | NLAM_BF16 */
+  void* out_bf16;             /* optional bf16 shadows of out / out_res (same row mapping), */
+  void* out_res_bf16;         /* NLAM_BF16 mode, d_out == 64 */
 } nlam_rowmlp;
 
 /* Backward of a row-MLP (recomputes the forward from the same inputs).
@@ -141,6 +153,28 @@ typedef struct nlam_rowmlp_bwd {
   int64_t g0_sum_stride;  /* g0 + k * g0_sum_stride floats (fwd.batch must be 1): the backward */
                           /* of an output that was expand()-ed over a batch, without the       */
                           /* summed copy; only where nlam_rowmlp_bwd_stages() == 2             */
+  /* bf16 shadows of the upstream gradients (dense [batch, rows|n1, 64]; written by the
+   * backward kernel that produced g0 / g1 through d_src_bf16) and of the per-row source
+   * gradients this run writes.  The TMA kernel (nlam_rowmlp_bwd_stages() == 1) needs the
+   * shadows of every gradient it reads. */
+  const void* g0_bf16;
+  const void* g1_bf16;
+  void* d_src_bf16[NLAM_MAX_SRC];
+  /* Sender pre-reduction (TMA kernel): instead of one gradient row per edge, source
+   * `sp_src` gets one PARTIAL row per (tile, distinct sender in the tile): partial q =
+   * sum of the tile rows sp_rows[sp_row_ptr[q] .. sp_row_ptr[q+1]) (tile-local row ids,
+   * ascending), tile t owns partials [sp_tile_ptr[t], sp_tile_ptr[t+1]); d_src[sp_src] is
+   * then [batch, n_sp, width].  A CSR over the partials (by sender) finishes the sum
+   * (nlam_segsum).  sp_src = -1: off. */
+  int32_t sp_src;
+  int32_t n_sp;
+  const int32_t* sp_tile_ptr;
+  const int32_t* sp_row_ptr;
+  const int32_t* sp_rows;
+  /* src0_batch_sum = 1: source 0 is shared by the batch (batch_stride 0) and d_src[0] is
+   * [1, rows, width] = the gradient SUMMED over the batch on chip (TMEM accumulation over
+   * the batch tiles of one row range) instead of [batch, rows, width]. */
+  int32_t src0_batch_sum;
 } nlam_rowmlp_bwd;
 
 /* out[b,i,:] (+)= scale[i] * sum_{p in [ptr[i],ptr[i+1])} src[b, idx[p], :]
@@ -195,6 +229,32 @@ typedef struct nlam_state_step_bwd {
   float* d_prev;
 } nlam_state_step_bwd;
 
+/* Device-side data feed (replaces the per-sample xarray work of
+ * neural_lam/weather_dataset.py:163-496, analysis data).  The standardised time series stays
+ * in HBM: state [slots, n_grid, d_state], forcing [slots, n_grid, d_forcing] (or NULL), times
+ * [slots]; logical time step t lives in slot (ring_cap ? t % ring_cap : t).  Sample i uses
+ *   states   t = i + max(0, past - 2) + {0, 1}            -> init_states   [B, 2, N, d_state]
+ *            t = i + max(0, past - 2) + 2 + s             -> target_states [B, ar, N, d_state]
+ *   forcing  t = i + max(2, past) + s - past + w, w < past + future + 1
+ *            -> forcing_out[b, s, n, f * (past+future+1) + w]  (feature-major, window inner)
+ *   target_times[b, s] = times of the target steps.
+ * sample_idx is passed by value (host side validates every window against [t_lo, t_hi)). */
+#define NLAM_FEED_MAX_BATCH 64
+typedef struct nlam_feed_batch {
+  const float* state;
+  const float* forcing;
+  const int64_t* times;
+  int64_t sample_idx[NLAM_FEED_MAX_BATCH];
+  int32_t batch, n_grid, d_state, d_forcing;
+  int32_t ar_steps, past, future;
+  int32_t ring_cap;     /* 0 = the series is stored linearly from time step 0 */
+  int64_t t_lo, t_hi;   /* resident logical time steps [t_lo, t_hi) */
+  float* init_states;
+  float* target_states;
+  float* forcing_out;   /* [B, ar, N, d_forcing * (past + future + 1)] */
+  int64_t* target_times; /* [B, ar] or NULL */
+} nlam_feed_batch;
+
 const char* nlam_last_error(void);
 int nlam_version(void);
 /* Kernel-selection knobs (process-wide; -1 = automatic, 0 = off, 1 = force when
@@ -223,7 +283,9 @@ size_t nlam_rowmlp_bwd_workspace(const nlam_rowmlp* desc);
 size_t nlam_rowmlp_param_floats(const nlam_rowmlp* desc); /* per chunk */
 /* Kernels nlam_rowmlp_bwd_run launches for this descriptor: 3 = input gradients,
  * weight gradients, partial reduction (stage_mask bits 1, 2, 4); 2 = one fused
- * input + weight gradient kernel (bit 1; bit 2 is a no-op) and the reduction.  The
+ * input + weight gradient kernel (bit 1; bit 2 is a no-op) and the reduction; 1 = the
+ * TMA row-gather variant of the fused kernel (operands and upstream gradients read
+ * from bf16 shadows by cp.async.bulk.tensor tile::gather4) and the reduction.  The
  * choice can depend on which source gradients (d_src) the descriptor asks for. */
 int nlam_rowmlp_bwd_stages(const nlam_rowmlp_bwd* desc);
 int nlam_rowmlp_bwd_run(const nlam_rowmlp_bwd* desc, void* stream);
@@ -239,6 +301,10 @@ int nlam_rowmlp_bwd_flush(void* stream);
 int nlam_rowmlp_bwd_pending(void);
 int nlam_rowmlp_bwd_discard(void* stream);
 int nlam_segsum_run(const nlam_segsum* desc, void* stream);
+/* dst[r, c] = (src[r, c] - mean[c]) / std[c]  (weather_dataset.py:399-420), in place allowed */
+int nlam_feed_standardize(const float* src, const float* mean, const float* std, float* dst,
+                          int64_t rows, int32_t d, void* stream);
+int nlam_feed_batch_run(const nlam_feed_batch* desc, void* stream);
 int64_t nlam_state_step_partials(int64_t rows);
 int nlam_state_step_fwd(const nlam_state_step* desc, void* stream);
 int nlam_state_step_bwd_run(const nlam_state_step_bwd* desc, void* stream);

@@ -21,6 +21,7 @@ struct KParams {
   const float* g1_scale;
   long long g1_batch_stride;
   float* d_src[NLAM_MAX_SRC];
+  void* d_src_bf16[NLAM_MAX_SRC];  // optional bf16 shadows of the per-row source gradients
   const int32_t* g0_idx;
   const int32_t* d_src_idx[NLAM_MAX_SRC];
   int reduce_src, reduce_accumulate;
@@ -80,7 +81,7 @@ inline int fill_params(const nlam_rowmlp& d, KParams& p) {
                  (((uintptr_t)d.out_res) % 16 == 0);
   p.lay = ParamLayout{k, d.d_hidden, d.d_out, d.w.ln_g != nullptr};
   p.reduce_src = -1;
-  NLAM_CHECK(!d.agg.out || (d.agg.seg_ptr && d.agg.tile_seg && d.tile_ptr && d.n_chunks == 1),
+  NLAM_CHECK(!(d.agg.out || d.agg.out_bf16) || (d.agg.seg_ptr && d.agg.tile_seg && d.tile_ptr && d.n_chunks == 1),
              "rowmlp: agg needs seg_ptr, tile_seg and a (receiver-aligned) tile table");
   NLAM_CHECK(d.out || d.out_res || d.agg.out || true, "unreachable");
   return 0;

@@ -778,6 +778,8 @@ int simt_rowmlp_fwd(const nlam_rowmlp& d, cudaStream_t st) {
   if (fill_params(d, p)) return 1;
   if (d.rows == 0) return 0;
   NLAM_CHECK(d.out, "rowmlp: out is NULL");
+  NLAM_CHECK(!d.out_bf16 && !d.out_res_bf16 && !d.agg.out_bf16,
+             "rowmlp(fp32 path): bf16 shadow outputs need the tensor-core path");
   NLAM_CHECK(!d.agg.out && !d.out_idx,
              "rowmlp: fused aggregation / row scatter exist only on the bf16 tensor-core path");
   const int dp = pick_dp(d);

@@ -262,9 +262,17 @@ rowmlp_tc_fwd_kernel(const __grid_constant__ KParams p, const __grid_constant__ 
           if (res) v.x += e.x, v.y += e.y, v.z += e.z, v.w += e.w;
           const size_t orow = oidx ? (size_t)__ldg(oidx + row0 + row) : (size_t)(row0 + row);
           if (out) *reinterpret_cast<float4*>(out + orow * dout + c4 * 4) = v;
+          if (p.d.out_bf16)
+            *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(p.d.out_bf16) +
+                                      ((size_t)b * p.d.rows + orow) * dout + c4 * 4) =
+                make_uint2(pack_bf16(v.x, v.y), pack_bf16(v.z, v.w));
           if (out2)
             *reinterpret_cast<float4*>(out2 + orow * dout + c4 * 4) =
                 make_float4(v.x + e.x, v.y + e.y, v.z + e.z, v.w + e.w);
+          if (p.d.out_res_bf16)
+            *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(p.d.out_res_bf16) +
+                                      ((size_t)b * p.d.rows + orow) * dout + c4 * 4) =
+                make_uint2(pack_bf16(v.x + e.x, v.y + e.y), pack_bf16(v.z + e.z, v.w + e.w));
         }
       } else {
         for (int u = tid; u < cnt * dout; u += NT) {
@@ -282,7 +290,7 @@ rowmlp_tc_fwd_kernel(const __grid_constant__ KParams p, const __grid_constant__ 
         }
       }
     }
-    if (p.d.agg.out) {  // receiver-aligned tile: every segment of this tile is complete
+    if (p.d.agg.out || p.d.agg.out_bf16) {  // receiver-aligned tile: every segment is complete
       const int seg_lo = __ldg(p.d.agg.tile_seg + tile), seg_hi = __ldg(p.d.agg.tile_seg + tile + 1);
       const int w4 = dout >> 2;
       float* ao = p.d.agg.out + (size_t)b * p.d.agg.n_seg * dout;
@@ -298,7 +306,11 @@ rowmlp_tc_fwd_kernel(const __grid_constant__ KParams p, const __grid_constant__ 
           const float sc = __ldg(p.d.agg.scale + seg);
           acc.x *= sc, acc.y *= sc, acc.z *= sc, acc.w *= sc;
         }
-        *reinterpret_cast<float4*>(ao + (size_t)seg * dout + c4 * 4) = acc;
+        if (p.d.agg.out) *reinterpret_cast<float4*>(ao + (size_t)seg * dout + c4 * 4) = acc;
+        if (p.d.agg.out_bf16)
+          *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(p.d.agg.out_bf16) +
+                                    ((size_t)b * p.d.agg.n_seg + seg) * dout + c4 * 4) =
+              make_uint2(pack_bf16(acc.x, acc.y), pack_bf16(acc.z, acc.w));
       }
     }
     __syncthreads();  // staging (aliases A) is free again
@@ -356,8 +368,12 @@ int tc_rowmlp_fwd(const nlam_rowmlp& d, cudaStream_t st) {
   KParams p{};
   if (fill_params(d, p)) return 1;
   if (d.rows == 0) return 0;
-  NLAM_CHECK(d.out || d.out_res || d.agg.out, "rowmlp: no output requested");
-  NLAM_CHECK(!d.agg.out || d.d_out % 4 == 0, "rowmlp: agg needs d_out %% 4 == 0");
+  NLAM_CHECK(d.out || d.out_res || d.agg.out || d.agg.out_bf16, "rowmlp: no output requested");
+  NLAM_CHECK(!(d.agg.out || d.agg.out_bf16) || d.d_out % 4 == 0, "rowmlp: agg needs d_out %% 4 == 0");
+  NLAM_CHECK(!(d.out_bf16 || d.out_res_bf16 || d.agg.out_bf16) || (p.out_vec_ok && d.d_out % 4 == 0),
+             "rowmlp: bf16 shadow outputs need 16-byte aligned fp32 outputs and d_out %% 4 == 0");
+  NLAM_CHECK(!d.out_bf16 || d.out, "rowmlp: out_bf16 needs out");
+  NLAM_CHECK(!d.out_res_bf16 || d.out_res, "rowmlp: out_res_bf16 needs out_res");
   tc::Geo g{};
   if (tc::make_geo(p, g)) return 1;
   {  // four tiles in flight per SM with shared weights, when there is enough work
@@ -365,6 +381,7 @@ int tc_rowmlp_fwd(const nlam_rowmlp& d, cudaStream_t st) {
     // measured on MEPS shapes: +16 % on the 3-source edge MLPs (gather-latency bound),
     // -12 % on the 2-source node MLP, so only the former take this path by default
     const bool want = mc_env < 0 ? (g.total_tiles > 296 && d.n_src == 3) : mc_env != 0;
+    if (want && option_tma() != 0 && tc_fwd_tma_supported(p)) return tc_rowmlp_fwd_tma(p, g, st);
     if (want && tc_fwd_mc_supported(p)) return tc_rowmlp_fwd_mc(p, g, st);
   }
   int per_sm = g.smem_bytes <= 113 * 1024 ? 2 : 1;

@@ -163,6 +163,21 @@ __device__ __forceinline__ void gather_rows_fast(const KParams& p, int b, int ro
       const int row = i * RPP + rl;
       ridx[i] = row < cnt ? (idx ? __ldg(idx + row0 + row) : row0 + row) : -1;
     }
+    const int kcol_s = (s - s_begin) * FN + c * 8;
+    if (src.shadow) {  // bf16 shadow rows: 16-byte chunks copied as they are
+      const uint4* sb = reinterpret_cast<const uint4*>(
+          reinterpret_cast<const __nv_bfloat16*>(src.shadow) + (long long)b * src.shadow_batch_stride) + c;
+      uint4 q[NP];
+#pragma unroll
+      for (int i = 0; i < NP; ++i) {
+        q[i] = make_uint4(0u, 0u, 0u, 0u);
+        if (ridx[i] >= 0) q[i] = __ldg(sb + (long long)ridx[i] * CPR);
+      }
+#pragma unroll
+      for (int i = 0; i < NP; ++i)
+        *reinterpret_cast<uint4*>(sA + sw128_off(i * RPP + rl, kcol_s, a_blk)) = q[i];
+      continue;
+    }
     float4 x[NP], y[NP];
 #pragma unroll
     for (int i = 0; i < NP; ++i) {
@@ -253,6 +268,9 @@ __device__ __forceinline__ void gather_rows_pipe(const KParams& p, int b,
   auto issue = [&](int s, int hsel, int buf) {
     const nlam_src& src = p.d.src[s];
     const float* base = src.ptr + (long long)b * src.batch_stride + c * 8;
+    const float4* sbase = reinterpret_cast<const float4*>(
+        reinterpret_cast<const __nv_bfloat16*>(src.shadow) + (long long)b * src.shadow_batch_stride) + c;
+    const bool sh = src.shadow != nullptr;
     const int my = s == 0 ? ridx[0] : s == 1 ? ridx[1] : ridx[2];
 #pragma unroll
     for (int j = 0; j < NH; ++j) {
@@ -261,9 +279,13 @@ __device__ __forceinline__ void gather_rows_pipe(const KParams& p, int b,
       x[buf][j] = make_float4(0.f, 0.f, 0.f, 0.f);
       y[buf][j] = x[buf][j];
       if (ri >= 0) {
-        const float4* q = reinterpret_cast<const float4*>(base + (long long)ri * src.ld);
-        x[buf][j] = __ldg(q);
-        y[buf][j] = __ldg(q + 1);
+        if (sh) {  // bf16 shadow row: one raw 16-byte chunk
+          x[buf][j] = __ldg(sbase + (long long)ri * LPR);
+        } else {
+          const float4* q = reinterpret_cast<const float4*>(base + (long long)ri * src.ld);
+          x[buf][j] = __ldg(q);
+          y[buf][j] = __ldg(q + 1);
+        }
       }
     }
   };
@@ -273,6 +295,9 @@ __device__ __forceinline__ void gather_rows_pipe(const KParams& p, int b,
       const int row = rbase + rl + RPPW * (hsel * NH + j);
       uint4 pk = make_uint4(pack_bf16(x[buf][j].x, x[buf][j].y), pack_bf16(x[buf][j].z, x[buf][j].w),
                             pack_bf16(y[buf][j].x, y[buf][j].y), pack_bf16(y[buf][j].z, y[buf][j].w));
+      if (p.d.src[s].shadow)
+        pk = make_uint4(__float_as_uint(x[buf][j].x), __float_as_uint(x[buf][j].y),
+                        __float_as_uint(x[buf][j].z), __float_as_uint(x[buf][j].w));
       *reinterpret_cast<uint4*>(sA + sw128_off(row, s * FN + c * 8, a_blk)) = pk;
     }
   };
@@ -342,5 +367,8 @@ __device__ __forceinline__ void stage_params(const nlam_rowmlp& d, int chunk, in
 // multi-context forward (rowmlp_tc_mc.cu)
 bool tc_fwd_mc_supported(const KParams& p);
 int tc_rowmlp_fwd_mc(const KParams& p, const tc::Geo& g, cudaStream_t st);
+// TMA row-gather forward (rowmlp_tc_tma_fwd.cu)
+bool tc_fwd_tma_supported(const KParams& p);
+int tc_rowmlp_fwd_tma(const KParams& p, const tc::Geo& g, cudaStream_t st);
 
 }  // namespace nlam

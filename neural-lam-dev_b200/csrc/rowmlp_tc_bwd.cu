@@ -964,6 +964,7 @@ int tc_rowmlp_bwd(const nlam_rowmlp_bwd& bd, cudaStream_t st) {
   g.need_dz = 0;
   for (int s = 0; s < NLAM_MAX_SRC; ++s) {
     p.d_src[s] = s < d.n_src ? bd.d_src[s] : nullptr;
+    p.d_src_bf16[s] = s < d.n_src ? bd.d_src_bf16[s] : nullptr;
     if (p.d_src[s]) g.need_dz = 1;
   }
   g.a_img = reinterpret_cast<uint8_t*>(bd.workspace + ws.a_img);

@@ -201,10 +201,15 @@ rowmlp_tc_bwd_fused_kernel(const __grid_constant__ KParams p, const __grid_const
             ix[s * TM + row] = ri[s];
             if (ri[s] >= 0) {
               const nlam_src& src = p.d.src[s];
-              const char* qq = reinterpret_cast<const char*>(
-                  src.ptr + (long long)bn * src.batch_stride + (long long)ri[s] * src.ld);
-              prefetch_l2(qq);
-              if (src.width > 32) prefetch_l2(qq + 128);
+              if (FG && src.shadow) {
+                prefetch_l2(reinterpret_cast<const __nv_bfloat16*>(src.shadow) +
+                            (long long)bn * src.shadow_batch_stride + (long long)ri[s] * FN);
+              } else {
+                const char* qq = reinterpret_cast<const char*>(
+                    src.ptr + (long long)bn * src.batch_stride + (long long)ri[s] * src.ld);
+                prefetch_l2(qq);
+                if (src.width > 32) prefetch_l2(qq + 128);
+              }
             }
           }
         }
@@ -377,6 +382,20 @@ rowmlp_tc_bwd_fused_kernel(const __grid_constant__ KParams p, const __grid_const
         int ridx[4];
 #pragma unroll
         for (int i = 0; i < 4; ++i) ridx[i] = ix[s * TM + i * 32 + grl];
+        if (src.shadow) {  // bf16 shadow rows: raw 16-byte chunks, no conversion
+          const uint4* sb = reinterpret_cast<const uint4*>(
+              reinterpret_cast<const __nv_bfloat16*>(src.shadow) + (long long)b * src.shadow_batch_stride) + gc;
+          uint4 qv[4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            qv[i] = make_uint4(0u, 0u, 0u, 0u);
+            if (ridx[i] >= 0) qv[i] = __ldg(sb + (long long)ridx[i] * 8);
+          }
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+            *reinterpret_cast<uint4*>(sA + sw128_off(i * 32 + grl, s * FN + gc * 8, FU_BLK)) = qv[i];
+          continue;
+        }
         float4 x[4], y[4];
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
@@ -676,6 +695,10 @@ rowmlp_tc_bwd_fused_kernel(const __grid_constant__ KParams p, const __grid_const
                 if (fres) v.x += e[i].x, v.y += e[i].y, v.z += e[i].z, v.w += e[i].w;
                 const size_t orow = scat ? (size_t)b * p.d.rows + ix[(6 + kb) * TM + row] : grow0 + row;
                 *reinterpret_cast<float4*>(o + orow * FN) = v;
+                if (p.d_src_bf16[kb])
+                  *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(p.d_src_bf16[kb]) +
+                                            orow * FN + (ltid & 15) * 4) =
+                      make_uint2(pack_bf16(v.x, v.y), pack_bf16(v.z, v.w));
               }
             }
           }

@@ -150,9 +150,13 @@ class InteractionNet(nn.Module):
             "aggr_params": Wa.t,
         }
         out = ops._InteractionNetFn.apply(meta, *We.t, *Wa.t, send_rep, rec_rep, edge_rep)
+        sh = meta.get("_sh", {})
         if self.update_edges:
             rec_out, edge_out = out
+            ops.attach_shadow(rec_out, sh.get("rec_out"))
+            ops.attach_shadow(edge_out, sh.get("new_edge"))
             return (rec_out[0], edge_out[0]) if squeeze else (rec_out, edge_out)
+        ops.attach_shadow(out, sh.get("rec_out"))
         return out[0] if squeeze else out
 
 

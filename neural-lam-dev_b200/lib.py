@@ -24,6 +24,9 @@ class Src(ctypes.Structure):
         ("batch_stride", ctypes.c_int64),
         ("ld", ctypes.c_int32),
         ("width", ctypes.c_int32),
+        ("shadow", ctypes.c_void_p),
+        ("shadow_batch_stride", ctypes.c_int64),
+        ("shadow_rows", ctypes.c_int64),
     ]
 
 
@@ -38,6 +41,7 @@ class Agg(ctypes.Structure):
         ("scale", c_float_p),
         ("out", c_float_p),
         ("n_seg", ctypes.c_int32),
+        ("out_bf16", ctypes.c_void_p),
     ]
 
 
@@ -61,6 +65,8 @@ class RowMlp(ctypes.Structure):
         ("out_idx", c_int_p),
         ("agg", Agg),
         ("precision", ctypes.c_int32),
+        ("out_bf16", ctypes.c_void_p),
+        ("out_res_bf16", ctypes.c_void_p),
     ]
 
 
@@ -84,6 +90,15 @@ class RowMlpBwd(ctypes.Structure):
         ("stage_mask", ctypes.c_int32),
         ("g0_sum_count", ctypes.c_int32),
         ("g0_sum_stride", ctypes.c_int64),
+        ("g0_bf16", ctypes.c_void_p),
+        ("g1_bf16", ctypes.c_void_p),
+        ("d_src_bf16", ctypes.c_void_p * MAX_SRC),
+        ("sp_src", ctypes.c_int32),
+        ("n_sp", ctypes.c_int32),
+        ("sp_tile_ptr", c_int_p),
+        ("sp_row_ptr", c_int_p),
+        ("sp_rows", c_int_p),
+        ("src0_batch_sum", ctypes.c_int32),
     ]
 
 
@@ -115,6 +130,22 @@ class StateStepBwd(ctypes.Structure):
                 ("d_net_out", c_float_p), ("d_prev", c_float_p)]
 
 
+FEED_MAX_BATCH = 64
+
+
+class FeedBatch(ctypes.Structure):
+    _fields_ = [
+        ("state", c_float_p), ("forcing", c_float_p), ("times", ctypes.c_void_p),
+        ("sample_idx", ctypes.c_int64 * FEED_MAX_BATCH),
+        ("batch", ctypes.c_int32), ("n_grid", ctypes.c_int32), ("d_state", ctypes.c_int32),
+        ("d_forcing", ctypes.c_int32), ("ar_steps", ctypes.c_int32), ("past", ctypes.c_int32),
+        ("future", ctypes.c_int32), ("ring_cap", ctypes.c_int32),
+        ("t_lo", ctypes.c_int64), ("t_hi", ctypes.c_int64),
+        ("init_states", c_float_p), ("target_states", c_float_p), ("forcing_out", c_float_p),
+        ("target_times", ctypes.c_void_p),
+    ]
+
+
 # every symbol include/nlam_b200.h declares: name -> (restype, argtypes)
 SYMBOLS = {
     "nlam_last_error": (ctypes.c_char_p, []),
@@ -135,6 +166,9 @@ SYMBOLS = {
     "nlam_rowmlp_bwd_pending": (ctypes.c_int, []),
     "nlam_rowmlp_bwd_discard": (ctypes.c_int, [ctypes.c_void_p]),
     "nlam_segsum_run": (ctypes.c_int, [ctypes.POINTER(SegSum), ctypes.c_void_p]),
+    "nlam_feed_standardize": (ctypes.c_int, [c_float_p, c_float_p, c_float_p, c_float_p,
+                                             ctypes.c_int64, ctypes.c_int32, ctypes.c_void_p]),
+    "nlam_feed_batch_run": (ctypes.c_int, [ctypes.POINTER(FeedBatch), ctypes.c_void_p]),
     "nlam_state_step_partials": (ctypes.c_int64, [ctypes.c_int64]),
     "nlam_state_step_fwd": (ctypes.c_int, [ctypes.POINTER(StateStep), ctypes.c_void_p]),
     "nlam_state_step_bwd_run": (ctypes.c_int, [ctypes.POINTER(StateStepBwd), ctypes.c_void_p]),

@@ -76,7 +76,8 @@ class ARModel(nn.Module):
     @staticmethod
     def expand_to_batch(x, batch_size):
         """Stride-0 batch view (ar_model.py:204-209)."""
-        return x.unsqueeze(0).expand(batch_size, -1, -1)
+        from .. import ops
+        return ops.expand_with_shadow(x, batch_size)
 
     def predict_step(self, prev_state, prev_prev_state, forcing):
         raise NotImplementedError("No prediction step implemented")

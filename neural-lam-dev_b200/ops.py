@@ -120,8 +120,10 @@ class KernelTimer:
     def want(self, tag):
         return self.only is None or tag == self.only
 
-    def start(self, tag, nbytes, flops):
-        rec = self.records.setdefault(tag, {"events": [], "bytes": nbytes, "flops": flops})
+    def start(self, tag, nbytes, flops, impl_bytes=None):
+        rec = self.records.setdefault(tag, {"events": [], "bytes": nbytes, "flops": flops,
+                                            "impl_bytes": impl_bytes if impl_bytes is not None
+                                            else nbytes})
         ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
         ev[0].record()
         rec["events"].append(ev)
@@ -134,6 +136,9 @@ class KernelTimer:
             ms = sum(a.elapsed_time(b) for a, b in rec["events"])
             out[tag] = (len(rec["events"]), ms, rec["bytes"], rec["flops"])
         return out
+
+    def impl_bytes(self, tag):
+        return self.records[tag]["impl_bytes"]
 
 
 _timer = {"t": None}
@@ -153,9 +158,9 @@ def _rowmlp_cost(kind, srcs, W, batch, rows, extra_row_floats):
     """(tag, algorithmic bytes, flops) of one row-MLP launch.  bytes: distinct
     input rows + gather indices + weights + rows written/read besides the
     inputs; flops: 2*rows*(K*dh + dh*dout) forward, 3x for dgrad+recompute."""
-    k = sum(t.shape[2] for t, _ in srcs)
+    k = sum(it[0].shape[2] for it in srcs)
     tag = f"{kind}|rows={rows}|K={k}|dh={W.d_hidden}|dout={W.d_out}|B={batch}"
-    nbytes = sum(_src_bytes(t, i, batch) for t, i in srcs)
+    nbytes = sum(_src_bytes(it[0], it[1], batch) for it in srcs)
     nbytes += 4 * W.n_chunks * W.param_floats()
     nbytes += 4 * batch * rows * extra_row_floats
     flops = 2 * batch * rows * (k * W.d_hidden + W.d_hidden * W.d_out)
@@ -186,14 +191,74 @@ def _rows3d(t, what):
     return t
 
 
-def _src(t, idx):
+def _src(t, idx, sh=None):
     s = L.Src()
     s.ptr = t.data_ptr()
     s.idx = idx.data_ptr() if idx is not None else None
     s.batch_stride = t.stride(0) if t.shape[0] > 1 else 0
     s.ld = t.stride(1) if t.shape[1] > 1 else t.shape[2]
     s.width = t.shape[2]
+    if sh is not None:
+        assert sh.dtype == torch.bfloat16 and sh.shape == t.shape and sh.stride(2) == 1 \
+            and (sh.shape[1] == 1 or sh.stride(1) == sh.shape[2])
+        s.shadow = sh.data_ptr()
+        s.shadow_batch_stride = sh.stride(0) if (sh.shape[0] > 1 and s.batch_stride != 0) else 0
+        s.shadow_rows = sh.shape[1]
     return s
+
+
+# ---- bf16 shadows -----------------------------------------------------------------------
+# In bf16 mode every kernel that produces a 64-wide representation also writes a bf16 copy
+# of it (the "shadow"); the consuming kernels build their MMA operands from the shadow (half
+# the gather bytes, no fp32 -> bf16 conversion; the TMA row-gather kernels need it), while
+# the fp32 tensor stays the master for residual streams and for autograd.  The shadow
+# travels as an attribute of the fp32 tensor object, together with the tensor's version
+# counter at the time it was written (an in-place update of the master invalidates it).
+SHADOW_WIDTH = 64
+
+
+def attach_shadow(t, sh):
+    if sh is not None:
+        t._nlam_sh = (sh, t._version)
+    return t
+
+
+def shadow_of(t):
+    rec = getattr(t, "_nlam_sh", None)
+    if rec is None or _state.get("no_shadows", False):
+        return None
+    sh, ver = rec
+    if t._version != ver or sh.shape != t.shape or sh.device != t.device:
+        return None
+    return sh
+
+
+def make_shadow(t):
+    """Give a tensor that did not come out of one of this library's kernels (a leaf, user
+    data) a bf16 shadow, so that consumers can take the shadow / TMA paths."""
+    if t.is_cuda and t.dtype == torch.float32 and t.shape[-1] == SHADOW_WIDTH:
+        attach_shadow(t, t.detach().to(torch.bfloat16).contiguous()
+                      if t.is_contiguous() else t.detach().to(torch.bfloat16))
+    return t
+
+
+def set_shadows(enabled):
+    """bf16 shadow activations on / off (bf16 mode only; off = every kernel gathers fp32)."""
+    _state["no_shadows"] = not enabled
+
+
+def _want_shadow(W, precision, batch_rows_ok=True):
+    return (precision == "bf16" and not _state.get("no_shadows", False)
+            and W.d_out == SHADOW_WIDTH and W.d_hidden <= 128 and W.k <= 384 and batch_rows_ok)
+
+
+def expand_with_shadow(x, batch_size):
+    """x (N, d) -> stride-0 (B, N, d) view; carries the shadow along."""
+    out = x.unsqueeze(0).expand(batch_size, -1, -1)
+    sh = shadow_of(x)
+    if sh is not None:
+        attach_shadow(out, sh.unsqueeze(0).expand(batch_size, -1, -1))
+    return out
 
 
 class TileTable:
@@ -287,8 +352,8 @@ def _fill_desc(desc, srcs, W, batch, rows, residual, tiles, out, precision, alig
     """aligned: optional dict with the receiver-aligned tile table and segment
     tables of a _GraphPlan (fused aggregation path)."""
     desc.n_src = len(srcs)
-    for i, (t, idx) in enumerate(srcs):
-        desc.src[i] = _src(t, idx)
+    for i, item in enumerate(srcs):
+        desc.src[i] = _src(*item)
     desc.batch, desc.rows = batch, rows
     desc.d_hidden, desc.d_out = W.d_hidden, W.d_out
     W.fill(desc)
@@ -315,7 +380,7 @@ def _fill_desc(desc, srcs, W, batch, rows, residual, tiles, out, precision, alig
 
 
 def rowmlp_fwd_raw(srcs, W, batch, rows, residual, tiles, precision, want_res=False,
-                   aligned=None):
+                   aligned=None, sh_box=None):
     """srcs: list of (3-D tensor, int32 row index or None).  want_res: also
     return src_0 + out (second output of the same launch).
     aligned (fused aggregation, see _GraphPlan): rows are processed in
@@ -336,6 +401,18 @@ def rowmlp_fwd_raw(srcs, W, batch, rows, residual, tiles, precision, want_res=Fa
         desc.agg.out = agg_out.data_ptr()
         desc.agg.scale = aligned["scale"].data_ptr() if aligned.get("scale") is not None else None
         desc.out_idx = aligned["out_idx"].data_ptr()
+    if sh_box is not None and _want_shadow(W, precision):
+        # bf16 shadows of everything this launch produces (see attach_shadow)
+        mk = lambda t: torch.empty(t.shape, device=dev, dtype=torch.bfloat16)
+        if out is not None:
+            sh_box["out"] = mk(out)
+            desc.out_bf16 = sh_box["out"].data_ptr()
+        if out_res is not None:
+            sh_box["out_res"] = mk(out_res)
+            desc.out_res_bf16 = sh_box["out_res"].data_ptr()
+        if agg_out is not None:
+            sh_box["agg"] = mk(agg_out)
+            desc.agg.out_bf16 = sh_box["agg"].data_ptr()
     end = None
     if _timer["t"] is not None:
         extra = W.d_out * ((1 if out is not None else 0) + (1 if want_res else 0))
@@ -356,7 +433,7 @@ def rowmlp_fwd_raw(srcs, W, batch, rows, residual, tiles, precision, want_res=Fa
 def rowmlp_bwd_raw(srcs, W, batch, rows, residual, tiles, precision, g0, need_src,
                    g1=None, g1_idx=None, g1_scale=None, aligned=None, g0_idx=None,
                    d_src_idx=None, reduce_src=-1, reduce_into=None, sink_params=None,
-                   g0_sum=False):
+                   g0_sum=False, algo_dsrc_bytes=None):
     """Returns (list of per-row source grads or None, d_params (n_chunks, P)).
     aligned / g0_idx / d_src_idx / reduce_src: fused-aggregation path; the
     gradient rows of source `reduce_src` are segment-summed and ADDED into the
@@ -383,7 +460,8 @@ def rowmlp_bwd_raw(srcs, W, batch, rows, residual, tiles, precision, g0, need_sr
         bd.g1_batch_stride = g1.stride(0) if g1.shape[0] > 1 else 0
         assert g1.stride(1) == W.d_out or g1.shape[1] == 1
     d_srcs = []
-    for i, ((t, _), need) in enumerate(zip(srcs, need_src)):
+    for i, (it, need) in enumerate(zip(srcs, need_src)):
+        t = it[0]
         if need and i == reduce_src:
             assert reduce_into is not None and reduce_into.is_contiguous()
             bd.d_src[i] = reduce_into.data_ptr()
@@ -433,8 +511,8 @@ def rowmlp_bwd_raw(srcs, W, batch, rows, residual, tiles, precision, g0, need_sr
         # time the three launches separately (stage_mask) with CUDA events.
         # Algorithmic bytes: dgrad = distinct input rows + dOut rows + per-source
         # gradient rows + the bf16 a/dY/dH tile images; wgrad = input rows + images
-        k = sum(t.shape[2] for t, _ in srcs)
-        src_bytes = sum(_src_bytes(t, i, batch) for t, i in srcs)
+        k = sum(it[0].shape[2] for it in srcs)
+        src_bytes = sum(_src_bytes(it[0], it[1], batch) for it in srcs)
         w_bytes = 4 * W.n_chunks * W.param_floats()
         rows_all = batch * rows
         # output-gradient rows read: dense g0 rows + the DISTINCT gathered g1 rows
@@ -443,22 +521,27 @@ def rowmlp_bwd_raw(srcs, W, batch, rows, residual, tiles, precision, g0, need_sr
         # source-gradient rows written: one row per (batch, row) and source, except the
         # segment-reduced source (read-modify-write of its [batch, n_seg, width] target)
         dsrc_bytes = 0
-        for i, ((t, _), need) in enumerate(zip(srcs, need_src)):
+        for i, (it, need) in enumerate(zip(srcs, need_src)):
             if need and i == reduce_src:
                 dsrc_bytes += 2 * 4 * reduce_into.numel()
             elif need:
-                dsrc_bytes += rows_all * 4 * t.shape[2]
-        dsrc = sum(t.shape[2] for (t, _), n in zip(srcs, need_src) if n)
+                dsrc_bytes += rows_all * 4 * it[0].shape[2]
+        dsrc = sum(it[0].shape[2] for it, n in zip(srcs, need_src) if n)
         img = 2 * (2 * W.d_hidden + W.d_out) if precision == "bf16" else 4 * (2 * W.d_hidden + W.d_out)
         fl = 2 * rows_all * (k * W.d_hidden + W.d_hidden * W.d_out)
         shape = f"rows={rows}|K={k}|dh={W.d_hidden}|dout={W.d_out}|B={batch}"
         agg = "_agg" if aligned is not None else ""
         if lib.nlam_rowmlp_bwd_stages(ctypes.byref(bd)) == 2:
-            # one kernel: input rows + dOut rows in, per-source gradient rows out; no images
+            # one kernel: input rows + dOut rows in, per-source gradient rows out; no images.
+            # algorithmic bytes: gradients at the size the ALGORITHM needs
+            # (algo_dsrc_bytes: batch-shared inputs once, node gradients per node); the
+            # implementation's own traffic (per-edge / per-batch rows) is kept beside it
+            impl = src_bytes + w_bytes + dout_bytes + dsrc_bytes
+            algo = impl if algo_dsrc_bytes is None else \
+                src_bytes + w_bytes + dout_bytes + algo_dsrc_bytes
             stages = (
-                (1, f"rowmlp_bwd_fused_{precision}{agg}|{shape}",
-                 src_bytes + w_bytes + dout_bytes + dsrc_bytes,
-                 (3 * fl if dsrc else 2 * fl + fl // 2)),
+                (1, f"rowmlp_bwd_fused_{precision}{agg}|{shape}", algo,
+                 (3 * fl if dsrc else 2 * fl + fl // 2), impl),
                 (4, f"reduce_params_{precision}|{shape}", 2 * w_bytes, 0),
             )
         else:
@@ -469,9 +552,9 @@ def rowmlp_bwd_raw(srcs, W, batch, rows, residual, tiles, precision, g0, need_sr
                 (2, f"rowmlp_wgrad_{precision}{agg}|{shape}", src_bytes + rows_all * img, fl),
                 (4, f"reduce_params_{precision}|{shape}", 2 * w_bytes, 0),
             )
-        for mask, tag, nbytes, flops in stages:
+        for mask, tag, nbytes, flops, *impl_b in stages:
             bd.stage_mask = mask
-            end = timer.start(tag, nbytes, flops) if timer.want(tag) else None
+            end = timer.start(tag, nbytes, flops, *impl_b) if timer.want(tag) else None
             L.check(lib.nlam_rowmlp_bwd_run(ctypes.byref(bd), _stream()), "nlam_rowmlp_bwd_run")
             if end is not None:
                 end.record()
@@ -531,8 +614,10 @@ class _RowMLPFn(torch.autograd.Function):
         W = Weights(w1, b1, w2, b2, ln_g, ln_b, meta["n_chunks"])
         x3 = _rows3d(x, "mlp input")
         B, rows, _ = x3.shape
-        out = rowmlp_fwd_raw([(x3, None)], W, B, rows, meta["residual"], meta["tiles"],
-                             meta["precision"])
+        ctx.sh_x = shadow_of(x3) if meta["precision"] == "bf16" else None
+        box = meta.setdefault("_sh", {})
+        out = rowmlp_fwd_raw([(x3, None, ctx.sh_x)], W, B, rows, meta["residual"], meta["tiles"],
+                             meta["precision"], sh_box=box)
         ctx.meta = meta
         ctx.save_for_backward(w1, b1, w2, b2, ln_g, ln_b, x3)
         return out
@@ -544,7 +629,7 @@ class _RowMLPFn(torch.autograd.Function):
         W = Weights(w1, b1, w2, b2, ln_g, ln_b, meta["n_chunks"])
         B, rows, _ = x3.shape
         d_srcs, d_params = rowmlp_bwd_raw(
-            [(x3, None)], W, B, rows, meta["residual"], meta["tiles"], meta["precision"],
+            [(x3, None, ctx.sh_x)], W, B, rows, meta["residual"], meta["tiles"], meta["precision"],
             gout, [ctx.needs_input_grad[7]], sink_params=meta.get("params"))
         gw = W.split_grads(d_params)
         return (None, *gw, d_srcs[0])
@@ -611,7 +696,9 @@ class _RowMLPExpandFn(torch.autograd.Function):
     def forward(ctx, meta, w1, b1, w2, b2, ln_g, ln_b, x):
         W = Weights(w1, b1, w2, b2, ln_g, ln_b, 1)
         x3 = _rows3d(x, "mlp input")
-        out = rowmlp_fwd_raw([(x3, None)], W, 1, x3.shape[1], False, None, meta["precision"])
+        box = meta.setdefault("_sh", {})
+        out = rowmlp_fwd_raw([(x3, None)], W, 1, x3.shape[1], False, None, meta["precision"],
+                             sh_box=box)
         ctx.meta = meta
         ctx.save_for_backward(w1, b1, w2, b2, ln_g, ln_b, x3)
         return out.expand(meta["batch"], -1, -1)
@@ -634,7 +721,11 @@ def mlp_forward_expand(module, x, batch):
     if x.dim() != 2 or W.n_chunks != 1:
         raise ValueError("mlp_forward_expand: (rows, K) input, one weight set")
     meta = {"precision": get_precision(), "params": W.t, "batch": int(batch)}
-    return _RowMLPExpandFn.apply(meta, *W.t, x.unsqueeze(0))
+    out = _RowMLPExpandFn.apply(meta, *W.t, x.unsqueeze(0))
+    sh = meta.get("_sh", {}).get("out")
+    if sh is not None:
+        attach_shadow(out, sh.expand(int(batch), -1, -1))
+    return out
 
 
 def mlp_forward(module, x, residual=False):
@@ -646,7 +737,11 @@ def mlp_forward(module, x, residual=False):
     meta = {"n_chunks": 1, "residual": residual, "tiles": None, "precision": get_precision(),
             "params": W.t}
     out = _RowMLPFn.apply(meta, *W.t, x3)
-    return out.reshape(*lead, W.d_out)
+    res = out.reshape(*lead, W.d_out)
+    sh = meta.get("_sh", {}).get("out")
+    if sh is not None:
+        attach_shadow(res, sh.reshape(*lead, W.d_out))
+    return res
 
 
 def split_mlp_forward(module, x):
@@ -690,27 +785,39 @@ class _InteractionNetFn(torch.autograd.Function):
                 f"InteractionNet: got send/rec/edge rows {send3.shape[1]}/{rec3.shape[1]}/"
                 f"{edge3.shape[1]}, edge_index needs >={plan.n_send_idx}/{n_rec}/{M}")
         al = plan.aligned_tables(meta["aggr"]) if _use_aligned(plan, We, Wa, prec) else None
+        bf = prec == "bf16"
+        sh_send, sh_rec, sh_edge = ((shadow_of(send3), shadow_of(rec3), shadow_of(edge3))
+                                    if bf else (None, None, None))
+        ebox, nbox = {}, {}
         if al is not None:
             # receiver-sorted, receiver-aligned tiles: gather -> edge MLP -> (E' scatter)
             # -> per-receiver sum inside ONE kernel; the messages never reach HBM
             _, new_edge, aggr = rowmlp_fwd_raw(
-                [(edge3, plan.perm), (send3, plan.send_sorted), (rec3, plan.recv_sorted)],
-                We, B, M, False, None, prec, want_res=meta["update_edges"], aligned=al)
+                [(edge3, plan.perm, sh_edge), (send3, plan.send_sorted, sh_send),
+                 (rec3, plan.recv_sorted, sh_rec)],
+                We, B, M, False, None, prec, want_res=meta["update_edges"], aligned=al,
+                sh_box=ebox)
         else:
             # message (+ E' = E + m as second output), then CSR segment sum / mean
             edge_out = rowmlp_fwd_raw(
-                [(edge3, None), (send3, plan.send32), (rec3, plan.recv32)], We, B, M,
-                False, plan.edge_tiles, prec, want_res=meta["update_edges"])
+                [(edge3, None, sh_edge), (send3, plan.send32, sh_send),
+                 (rec3, plan.recv32, sh_rec)], We, B, M,
+                False, plan.edge_tiles, prec, want_res=meta["update_edges"],
+                sh_box=ebox if We.n_chunks == 1 else None)
+            ebox.pop("out", None)  # (shadow of the raw messages: not used)
             new_edge = None
             if meta["update_edges"]:
                 edge_out, new_edge = edge_out  # messages m_k and E' = E + m (:112)
             aggr = segsum_raw(edge_out, plan.rowptr, plan.perm, n_rec,
                               scale=plan.inv_deg if meta["aggr"] == "mean" else None)
-        rec_out = rowmlp_fwd_raw([(rec3, None), (aggr, None)], Wa, B, n_rec, True,
-                                 plan.aggr_tiles, prec)
+        sh_aggr = ebox.get("agg")
+        rec_out = rowmlp_fwd_raw([(rec3, None, sh_rec), (aggr, None, sh_aggr)], Wa, B, n_rec, True,
+                                 plan.aggr_tiles, prec, sh_box=nbox if Wa.n_chunks == 1 else None)
         same = (send3.data_ptr() == rec3.data_ptr() and send3.shape == rec3.shape
                 and send3.stride() == rec3.stride())
+        meta["_sh"] = {"rec_out": nbox.get("out"), "new_edge": ebox.get("out_res")}
         meta = dict(meta, aligned=al is not None, same_send_rec=same)
+        ctx.shadows = (sh_send, sh_rec, sh_edge, sh_aggr)
         ctx.meta = meta
         ctx.set_materialize_grads(False)  # unused outputs arrive as None, not zeros
         ctx.save_for_backward(*ew, *aw, send3, rec3, edge3, aggr)
@@ -733,11 +840,12 @@ class _InteractionNetFn(torch.autograd.Function):
         d_rec_out = grads[0]
         d_edge_out = grads[1] if meta["update_edges"] else None
         dev = rec3.device
+        sh_send, sh_rec, sh_edge, sh_aggr = ctx.shadows
         if d_rec_out is None:
             d_rec_out = torch.zeros((B, n_rec, Wa.d_out), device=dev)
         # node stage: R' = R + aggr_mlp([R | A])
         (dR, dA), dPa = rowmlp_bwd_raw(
-            [(rec3, None), (aggr, None)], Wa, B, n_rec, True, plan.aggr_tiles, prec,
+            [(rec3, None, sh_rec), (aggr, None, sh_aggr)], Wa, B, n_rec, True, plan.aggr_tiles, prec,
             d_rec_out, [True, True], sink_params=meta.get("aggr_params"))
         # edge stage: dm_k = dE'_k + dA[r(k)] (/deg)
         need_send, need_rec, need_edge = ctx.needs_input_grad[13:16]
@@ -745,12 +853,17 @@ class _InteractionNetFn(torch.autograd.Function):
         if meta["aligned"]:
             al = plan.aligned_tables(meta["aggr"])
             (d_edge, dzS, d_rec), dPe = rowmlp_bwd_raw(
-                [(edge3, plan.perm), (send3, plan.send_sorted), (rec3, plan.recv_sorted)],
+                [(edge3, plan.perm, sh_edge), (send3, plan.send_sorted, sh_send),
+                 (rec3, plan.recv_sorted, sh_rec)],
                 We, B, M, d_edge_out is not None, None, prec, d_edge_out,
                 [need_edge, need_send, need_rec], g1=dA, g1_idx=plan.recv_sorted,
                 g1_scale=scale, aligned=al, g0_idx=plan.perm,
                 d_src_idx=[plan.perm, None, None], reduce_src=2 if need_rec else -1,
-                reduce_into=dR, sink_params=meta.get("edge_params"))
+                reduce_into=dR, sink_params=meta.get("edge_params"),
+                algo_dsrc_bytes=4 * We.d_out * (
+                    (M * (edge3.shape[0] if edge3.stride(0) != 0 else 1) if need_edge else 0)
+                    + (B * plan.n_send_idx if need_send else 0)
+                    + (2 * B * n_rec if need_rec else 0)))
             d_send = None
             if need_send:
                 if (meta.get("same_send_rec") and need_rec and plan.n_send_idx == n_rec
@@ -764,7 +877,8 @@ class _InteractionNetFn(torch.autograd.Function):
                     d_send = segsum_raw(dzS, plan.ts_rowptr, plan.ts_perm, plan.n_send_idx)
         else:
             (dzE, dzS, dzR), dPe = rowmlp_bwd_raw(
-                [(edge3, None), (send3, plan.send32), (rec3, plan.recv32)], We, B, M,
+                [(edge3, None, sh_edge), (send3, plan.send32, sh_send),
+                 (rec3, plan.recv32, sh_rec)], We, B, M,
                 d_edge_out is not None,  # E' = E + m: the kernel adds dE' to the edge gradient
                 plan.edge_tiles, prec, d_edge_out, [need_edge, need_send, need_rec],
                 g1=dA, g1_idx=plan.recv32, g1_scale=scale, sink_params=meta.get("edge_params"))

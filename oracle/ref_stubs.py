@@ -299,18 +299,34 @@ def install_stubs():
     sys.modules["dataclass_wizard.errors"] = dw_err
 
 
-def import_reference():
-    """Import the unmodified reference package; returns the module."""
+STAGED_ARCHIVE = __import__("os").path.join(
+    __import__("os").path.dirname(__import__("os").path.abspath(__file__)), "_ref",
+    "neural_lam_ref.zip")
+
+
+def reference_location():
+    """Where the unmodified reference can be imported from: its directory in the build
+    container, else the archive oracle/stage_ref.py packed from it (GPU box), else None."""
     import os
 
-    if not os.path.isdir(REFERENCE_ROOT):
+    if os.path.isdir(os.path.join(REFERENCE_ROOT, "neural_lam")):
+        return REFERENCE_ROOT
+    if os.path.exists(STAGED_ARCHIVE):
+        return STAGED_ARCHIVE
+    return None
+
+
+def import_reference():
+    """Import the unmodified reference package; returns the module."""
+    where = reference_location()
+    if where is None:
         raise RuntimeError(
-            f"{REFERENCE_ROOT} not present (it only exists in the build "
-            "container); use oracle.port instead"
+            f"neither {REFERENCE_ROOT} nor {STAGED_ARCHIVE} is present; run "
+            "oracle/stage_ref.py in the build container, or use oracle.port instead"
         )
     install_stubs()
-    if REFERENCE_ROOT not in sys.path:
-        sys.path.insert(0, REFERENCE_ROOT)
+    if where not in sys.path:
+        sys.path.insert(0, where)
     import neural_lam  # noqa: F401
 
     return neural_lam

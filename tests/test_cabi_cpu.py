@@ -32,10 +32,10 @@ def test_header_symbols_exported(built):
 def test_struct_sizes_match_header(built):
     # LP64 layout of the by-pointer descriptors (catches ctypes/header drift)
     import ctypes
-    assert ctypes.sizeof(built.Src) == 32
+    assert ctypes.sizeof(built.Src) == 56
     assert ctypes.sizeof(built.MlpWeights) == 48
-    assert ctypes.sizeof(built.Agg) == 40
-    assert ctypes.sizeof(built.RowMlp) == 8 + 3 * 32 + 16 + 48 + 8 + 24 + 8 + 8 + 8 + 8 + 40 + 8
+    assert ctypes.sizeof(built.Agg) == 48
+    assert ctypes.sizeof(built.RowMlp) == 8 + 3 * 56 + 16 + 48 + 8 + 24 + 8 + 8 + 8 + 8 + 48 + 8 + 16
     assert ctypes.sizeof(built.SegSum) == 64
 
 

@@ -255,3 +255,69 @@ def test_bf16_deterministic(dev, bf16):
         net.zero_grad()
     for a, b in zip(*outs):
         assert torch.equal(a, b)
+
+
+@pytest.mark.parametrize("name", ["graphlam_meps_d64", "hilam_d16"])
+def test_shadows_do_not_change_results(dev, bf16, name):
+    """bf16 shadow activations (ops.attach_shadow) hold exactly the values the consumers
+    would have rounded themselves: a train step with and without them is bit-identical."""
+    from neural_lam_b200 import config as nl_config
+    from neural_lam_b200 import models, ops
+    if name not in MODELS:
+        pytest.skip(f"no golden case {name}")
+    entry = MODELS[name]
+    case = entry["case"]
+    res = []
+    for shadows in (True, False):
+        ops.set_shadows(shadows)
+        try:
+            with tempfile.TemporaryDirectory() as root:
+                ds, args, batch = build_model_case(case, root)
+                model = models.MODELS[case["model"]](args, nl_config.default_config(), ds)
+            model.load_state_dict(entry["state_dict"])
+            model = model.to(dev)
+            loss = model.training_step(tuple(t.to(dev) for t in batch))
+            loss.backward()
+            res.append([loss.detach()] + [p.grad.clone() for p in model.parameters()])
+        finally:
+            ops.set_shadows(True)
+    for a, b in zip(*res):
+        assert torch.equal(a, b)
+
+
+@pytest.mark.parametrize("update,aggr,expand_edges", [(True, "sum", False), (False, "mean", True),
+                                                      (True, "mean", True)])
+def test_tma_kernels_equal_register_gather(dev, bf16, update, aggr, expand_edges):
+    """The TMA row-gather kernels (operands read from bf16 shadows by cp.async.bulk.tensor
+    tile::gather4) compute exactly what the register-gather kernels compute."""
+    from neural_lam_b200 import lib, ops
+    from neural_lam_b200.interaction_net import InteractionNet
+    g = torch.Generator().manual_seed(11)
+    M, n_send, n_rec, d, B = 70001, 5000, 9000, 64, 3
+    s = torch.randint(0, n_send, (M,), generator=g) + n_rec
+    r = torch.randint(0, n_rec, (M,), generator=g)
+    s[0], r[0], s[1], r[1] = n_rec, 0, n_rec + n_send - 1, n_rec - 1
+    torch.manual_seed(5)
+    net = InteractionNet(torch.stack((s, r)), d, update_edges=update, aggr=aggr).to(dev)
+    send = torch.randn(B, n_send, d, generator=g).to(dev)
+    rec = torch.randn(B, n_rec, d, generator=g).to(dev)
+    edge = torch.randn((M, d) if expand_edges else (B, M, d), generator=g).to(dev)
+    res = []
+    l = lib.load()
+    for tma in (1, 0):
+        l.nlam_set_option(b"tma", tma)
+        try:
+            leaves = [t.clone().requires_grad_() for t in (send, rec, edge)]
+            a, b, c = (ops.make_shadow(t) for t in leaves)
+            if expand_edges:
+                c = ops.expand_with_shadow(c, B)
+            out = net(a, b, c)
+            outs = out if isinstance(out, tuple) else (out,)
+            inet_loss(outs).backward()
+            res.append([o.detach().clone() for o in outs] + [t.grad.clone() for t in leaves]
+                       + [p.grad.clone() for p in net.parameters()])
+            net.zero_grad()
+        finally:
+            l.nlam_set_option(b"tma", 1)
+    for x, y in zip(*res):
+        assert torch.equal(x, y)
