@@ -113,6 +113,10 @@ class InteractionNet(nn.Module):
         else:
             self.aggr_mlp = SplitMLPs(
                 [utils.make_mlp(aggr_mlp_recipe) for _ in aggr_chunk_sizes], aggr_chunk_sizes)
+        if hidden_layers < 1:
+            raise NotImplementedError("InteractionNet: hidden_layers must be >= 1 (the fused "
+                                      "kernels compute Linear -> SiLU -> Linear blocks)")
+        self.hidden_layers = hidden_layers
         self.update_edges = update_edges
         self._edge_chunk_sizes = list(edge_chunk_sizes) if edge_chunk_sizes is not None else None
         self._aggr_chunk_sizes = list(aggr_chunk_sizes) if aggr_chunk_sizes is not None else None
@@ -137,6 +141,12 @@ class InteractionNet(nn.Module):
         squeeze = rec_rep.dim() == 2
         if squeeze:
             send_rep, rec_rep, edge_rep = (t.unsqueeze(0) for t in (send_rep, rec_rep, edge_rep))
+        if self.hidden_layers != 1:  # deeper MLPs: chained launches (ops.interaction_net_deep)
+            out = ops.interaction_net_deep(self._get_plan(), self.edge_mlp, self.aggr_mlp, send_rep,
+                                           rec_rep, edge_rep, self.aggr, self.update_edges)
+            if self.update_edges:
+                return (out[0][0], out[1][0]) if squeeze else out
+            return out[0] if squeeze else out
         We = ops.weights_of(self.edge_mlp)
         Wa = ops.weights_of(self.aggr_mlp)
         meta = {

@@ -60,7 +60,8 @@ class BaseGraphModel(ARModel):
     def embed_static(self, embedder, features, batch_size):
         """`expand_to_batch(embedder(features), B)`; on the GPU as one autograd node whose
         backward sums the batch slices of the incoming gradient inside the kernel."""
-        if features.is_cuda and features.dim() == 2 and isinstance(embedder, utils.FusedMLP):
+        if (features.is_cuda and features.dim() == 2 and isinstance(embedder, utils.FusedMLP)
+                and self.args.hidden_layers == 1):
             return ops.mlp_forward_expand(embedder, features, batch_size)
         return self.expand_to_batch(embedder(features), batch_size)
 

@@ -331,6 +331,62 @@ def _mlp_layers(mlp):
     return layers[0], layers[2], ln
 
 
+def _linears_of(mlp):
+    """(list of nn.Linear, LayerNorm | None) of a make_mlp Sequential with any number of hidden
+    layers: Linear, (SiLU, Linear)*, [LayerNorm]  (utils.py:191-214)."""
+    layers = list(mlp)
+    ln = layers.pop() if layers and isinstance(layers[-1], nn.LayerNorm) else None
+    lin = layers[0::2]
+    ok = (len(layers) % 2 == 1 and all(isinstance(m, nn.Linear) for m in lin)
+          and all(isinstance(m, nn.SiLU) for m in layers[1::2]))
+    if not ok or len(lin) < 2:
+        raise NotImplementedError(
+            "fused MLP kernels cover make_mlp blueprints with at least one hidden layer "
+            "(Linear, (SiLU, Linear)+[, LayerNorm]); got " + repr(mlp))
+    return lin, ln
+
+
+_identity_cache = {}
+
+
+def _identity(d, device):
+    key = (d, str(device))
+    if key not in _identity_cache:
+        _identity_cache[key] = (torch.eye(d, device=device), torch.zeros(d, device=device))
+    return _identity_cache[key]
+
+
+def blocks_of(module):
+    """Kernel-sized pieces of a make_mlp Sequential / SplitMLPs with h >= 1 hidden layers
+    (`--hidden_layers`, train_model.py:94): every launch of the fused kernel computes
+    [LN](W_b . SiLU(W_a . x + b_a) + b_b).  Block 0 = the first two Linears; every further
+    Linear W_k rides on an identity first layer, [LN](W_k . SiLU(I . y + 0) + b_k) -- exactly
+    the SiLU that precedes it in the blueprint.  LayerNorm belongs to the last block.  With
+    one hidden layer (every BASELINE config) this is the single block of weights_of()."""
+    mlps = getattr(module, "mlps", None)
+    per_chunk = [_linears_of(m) for m in mlps] if mlps is not None else [_linears_of(module)]
+    n_lin = len(per_chunk[0][0])
+    if any(len(lin) != n_lin for lin, _ in per_chunk):
+        raise NotImplementedError("SplitMLPs chunks with different depths")
+    C = len(per_chunk)
+    st = (lambda ts: torch.stack(list(ts))) if mlps is not None else (lambda ts: list(ts)[0])
+    blocks = []
+    for k in range(1, n_lin):
+        last = k == n_lin - 1
+        ln_g = st(ln.weight for _, ln in per_chunk) if (last and per_chunk[0][1] is not None) else None
+        ln_b = st(ln.bias for _, ln in per_chunk) if (last and per_chunk[0][1] is not None) else None
+        w2, b2 = st(lin[k].weight for lin, _ in per_chunk), st(lin[k].bias for lin, _ in per_chunk)
+        if k == 1:
+            w1, b1 = st(lin[0].weight for lin, _ in per_chunk), st(lin[0].bias for lin, _ in per_chunk)
+        else:
+            d = per_chunk[0][0][k].in_features
+            eye, zero = _identity(d, w2.device)
+            w1 = eye.expand(C, d, d).contiguous() if mlps is not None else eye
+            b1 = zero.expand(C, d).contiguous() if mlps is not None else zero
+        blocks.append(Weights(w1, b1, w2, b2, ln_g, ln_b, C if mlps is not None else 1))
+    return blocks
+
+
 def weights_of(module):
     """Weights of a make_mlp Sequential or a SplitMLPs."""
     mlps = getattr(module, "mlps", None)
@@ -731,29 +787,41 @@ def mlp_forward_expand(module, x, batch):
 def mlp_forward(module, x, residual=False):
     """Fused forward of a make_mlp module on x (..., K); `residual=True`
     returns x + MLP(x) (base_graph_model.py:143-145)."""
-    W = weights_of(module)
+    blocks = blocks_of(module)
     lead = x.shape[:-1]
     x3 = x.reshape(1, -1, x.shape[-1]) if x.dim() != 3 else x
-    meta = {"n_chunks": 1, "residual": residual, "tiles": None, "precision": get_precision(),
-            "params": W.t}
-    out = _RowMLPFn.apply(meta, *W.t, x3)
+    out = _run_blocks(blocks, x3, residual, None)
+    W = blocks[-1]
     res = out.reshape(*lead, W.d_out)
-    sh = meta.get("_sh", {}).get("out")
+    sh = shadow_of(out)
     if sh is not None:
         attach_shadow(res, sh.reshape(*lead, W.d_out))
     return res
 
 
+def _run_blocks(blocks, x3, residual, tiles):
+    """Chain of fused-kernel launches (one per block of blocks_of) on direct rows."""
+    y = x3
+    for i, W in enumerate(blocks):
+        meta = {"n_chunks": W.n_chunks, "residual": residual and len(blocks) == 1, "tiles": tiles,
+                "precision": get_precision(),
+                "params": W.t if (W.n_chunks == 1 and i == 0) else None}
+        out = _RowMLPFn.apply(meta, *W.t, y)
+        attach_shadow(out, meta.get("_sh", {}).get("out"))
+        y = out
+    if residual and len(blocks) > 1:
+        y = x3 + y
+    return y
+
+
 def split_mlp_forward(module, x):
     """SplitMLPs.forward (interaction_net.py:151-163) as one kernel launch."""
-    W = weights_of(module)
+    blocks = blocks_of(module)
     lead = x.shape[:-1]
     x3 = x.reshape(1, *x.shape[-2:]) if x.dim() == 2 else x.reshape(-1, *x.shape[-2:])
     tiles = module._tile_table(x.device)
-    meta = {"n_chunks": W.n_chunks, "residual": False, "tiles": tiles,
-            "precision": get_precision()}
-    out = _RowMLPFn.apply(meta, *W.t, x3)
-    return out.reshape(*lead, W.d_out)
+    out = _run_blocks(blocks, x3, False, tiles)
+    return out.reshape(*lead, blocks[-1].d_out)
 
 
 def _use_aligned(plan, We, Wa, precision):
@@ -900,6 +968,102 @@ class _InteractionNetFn(torch.autograd.Function):
 
         return (None, *We.split_grads(dPe), *Wa.split_grads(dPa), fit(d_send, send3),
                 fit(d_rec, rec3), fit(d_edge, edge3))
+
+
+class _GatherMLPFn(torch.autograd.Function):
+    """out = [LN](W2 . SiLU(W1 . [x0[idx0] | x1[idx1] | ...] + b1) + b2): the first block of a
+    deeper edge / node MLP (`hidden_layers` > 1), sources gathered by row index (None =
+    direct rows).  Backward: per-row source gradients, summed per node through the CSR of
+    that index (deterministic)."""
+
+    @staticmethod
+    def forward(ctx, meta, w1, b1, w2, b2, ln_g, ln_b, *xs):
+        W = Weights(w1, b1, w2, b2, ln_g, ln_b, meta["n_chunks"])
+        xs3 = [_rows3d(x, "gather-mlp input") for x in xs]
+        B = max(x.shape[0] for x in xs3)
+        srcs = [(x, idx) for x, idx in zip(xs3, meta["idxs"])]
+        out = rowmlp_fwd_raw(srcs, W, B, meta["rows"], False, meta["tiles"], meta["precision"])
+        ctx.meta, ctx.n_x = meta, len(xs3)
+        ctx.save_for_backward(w1, b1, w2, b2, ln_g, ln_b, *xs3)
+        return out
+
+    @staticmethod
+    def backward(ctx, gout):
+        saved = ctx.saved_tensors
+        w1, b1, w2, b2, ln_g, ln_b = saved[:6]
+        xs3 = list(saved[6:])
+        meta = ctx.meta
+        W = Weights(w1, b1, w2, b2, ln_g, ln_b, meta["n_chunks"])
+        B = max(x.shape[0] for x in xs3)
+        need = [bool(n) for n in ctx.needs_input_grad[7:7 + ctx.n_x]]
+        srcs = [(x, idx) for x, idx in zip(xs3, meta["idxs"])]
+        d_rows, d_params = rowmlp_bwd_raw(srcs, W, B, meta["rows"], False, meta["tiles"],
+                                          meta["precision"], gout, need)
+        grads = []
+        for g, x, csr in zip(d_rows, xs3, meta["csrs"]):
+            if g is not None and csr is not None:  # gathered source: sum the rows per node
+                rowptr, perm, n_idx = csr
+                g = segsum_raw(g, rowptr, perm, n_idx)
+                if x.shape[1] > n_idx:  # trailing nodes no edge refers to
+                    g = torch.cat((g, g.new_zeros((g.shape[0], x.shape[1] - n_idx, g.shape[2]))), 1)
+            if g is not None and x.shape[0] == 1 and g.shape[0] > 1:
+                g = g.sum(0, keepdim=True)
+            grads.append(g)
+        return (None, *W.split_grads(d_params), *grads)
+
+
+class _SegSumFn(torch.autograd.Function):
+    """A[b, i] = scale[i] * sum_{k: recv(k) = i} m[b, k]  (interaction_net.py:124-131) as its
+    own autograd node (deep path); backward = the gather dm[b, k] = scale * dA[b, recv(k)],
+    run through the same segment-sum kernel with one-element segments."""
+
+    @staticmethod
+    def forward(ctx, plan, mean, m):
+        m3 = _rows3d(m, "messages")
+        ctx.plan, ctx.mean = plan, mean
+        return segsum_raw(m3, plan.rowptr, plan.perm, plan.num_rec,
+                          scale=plan.inv_deg if mean else None)
+
+    @staticmethod
+    def backward(ctx, dA):
+        plan = ctx.plan
+        if not hasattr(plan, "_unit_ptr"):
+            plan._unit_ptr = torch.arange(plan.n_edges + 1, device=dA.device, dtype=torch.int32)
+            plan._edge_scale = plan.inv_deg[plan.recv32.long()].contiguous()
+        dm = segsum_raw(dA.contiguous(), plan._unit_ptr, plan.recv32, plan.n_edges,
+                        scale=plan._edge_scale if ctx.mean else None)
+        return None, None, dm
+
+
+def interaction_net_deep(plan, edge_mlp, aggr_mlp, send, rec, edge, aggr, update_edges):
+    """InteractionNet.forward (interaction_net.py:86-131) for `hidden_layers` > 1: the first
+    block of the edge MLP gathers its three inputs, the remaining blocks run on the M edge
+    rows, then segment sum, then the node MLP the same way.  (One hidden layer -- every
+    BASELINE config -- takes the fully fused _InteractionNetFn instead.)"""
+    e_blocks, a_blocks = blocks_of(edge_mlp), blocks_of(aggr_mlp)
+    prec = get_precision()
+    send3, rec3, edge3 = (_rows3d(send, "send_rep"), _rows3d(rec, "rec_rep"),
+                          _rows3d(edge, "edge_rep"))
+    M, n_rec = plan.n_edges, plan.num_rec
+    if rec3.shape[1] != n_rec or edge3.shape[1] != M or send3.shape[1] < plan.n_send_idx:
+        raise RuntimeError("InteractionNet: input rows do not match edge_index")
+    W0 = e_blocks[0]
+    meta = {"n_chunks": W0.n_chunks, "tiles": plan.edge_tiles, "precision": prec, "rows": M,
+            "idxs": [None, plan.send32, plan.recv32],
+            "csrs": [None, (plan.t_rowptr, plan.t_perm, plan.n_send_idx),
+                     (plan.rowptr, plan.perm, n_rec)]}
+    m = _GatherMLPFn.apply(meta, *W0.t, edge3, send3, rec3)
+    m = _run_blocks(e_blocks[1:], m, False, plan.edge_tiles)
+    A = _SegSumFn.apply(plan, aggr == "mean", m)
+    W0 = a_blocks[0]
+    meta = {"n_chunks": W0.n_chunks, "tiles": plan.aggr_tiles, "precision": prec, "rows": n_rec,
+            "idxs": [None, None], "csrs": [None, None]}
+    u = _GatherMLPFn.apply(meta, *W0.t, rec3, A)
+    u = _run_blocks(a_blocks[1:], u, False, plan.aggr_tiles)
+    rec_out = rec3 + u
+    if update_edges:
+        return rec_out, edge3 + m
+    return rec_out
 
 
 class _StateStepFn(torch.autograd.Function):

@@ -120,6 +120,24 @@ def synthetic_batch(datastore, batch_size, ar_steps, num_past_forcing_steps=1,
     return batch
 
 
+def synthetic_series(datastore, n_time, seed=0, pin_memory=False):
+    """Raw (un-standardised) analysis time series of the datastore's shape for the device
+    feed: state (T, N, d_state), forcing (T, N, d_forcing), times (T,) int64 ns, and the
+    standardisation statistics (state_mean, state_std, forcing_mean, forcing_std)."""
+    g = torch.Generator().manual_seed(seed)
+    n = datastore.num_grid_points
+    d_s = datastore.get_num_data_vars("state")
+    d_f = datastore.get_num_data_vars("forcing")
+    stats = (torch.randn(d_s, generator=g), torch.rand(d_s, generator=g) + 0.5,
+             torch.randn(d_f, generator=g), torch.rand(d_f, generator=g) + 0.5)
+    state = torch.randn(n_time, n, d_s, generator=g) * stats[1] + stats[0]
+    forcing = torch.randn(n_time, n, d_f, generator=g) * stats[3] + stats[2]
+    times = torch.arange(n_time, dtype=torch.int64) * (3 * 3600 * 10 ** 9)
+    if pin_memory:
+        state, forcing, times = state.pin_memory(), forcing.pin_memory(), times.pin_memory()
+    return state, forcing, times, stats
+
+
 class ModelArgs:
     """Duck-typed `args` with the reference CLI defaults
     (train_model.py:29-209; tests/test_training.py:71-87)."""

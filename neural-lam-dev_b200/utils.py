@@ -107,6 +107,10 @@ def make_mlp(blueprint, layer_norm=True):
     optional output LayerNorm (utils.py:191-214)."""
     hidden_layers = len(blueprint) - 2
     assert hidden_layers >= 0, "Invalid MLP blueprint"
+    if hidden_layers == 0:  # fail at construction, not at the first forward
+        raise NotImplementedError(
+            "make_mlp: hidden_layers = 0 (a single Linear) has no fused kernel; the kernels "
+            "compute Linear -> SiLU -> Linear blocks (hidden_layers >= 1)")
     layers = []
     for i, (d_in, d_out) in enumerate(zip(blueprint[:-1], blueprint[1:])):
         layers.append(nn.Linear(d_in, d_out))

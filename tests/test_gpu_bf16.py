@@ -1,6 +1,16 @@
 """GPU parity of the bf16 tensor-core (tcgen05) mode: bf16 MMA operands, fp32
 accumulation / storage.  Tolerance stated by BASELINE.json north_star: 2e-2
-(relative to the largest magnitude of the reference tensor)."""
+(relative to the largest magnitude of the reference tensor).
+
+Where a bound wider than 2e-2 is used it is tied to a YARD-STICK: the deviation of the
+reference's own bf16 mode (`--precision bf16-mixed` = autocast) from its fp32 result on
+the same weights and inputs -- tests/golden/bf16_yardstick.pt for the model cases
+(unmodified reference, oracle/make_golden_autocast.py), the oracle port under
+torch.autocast for single layers.  The bound is then max(2e-2, 2 x yard-stick): this
+repo's bf16 mode may not be more than a factor two further from fp32 than the reference's
+own bf16 mode is.  Measured (profiles/parity_bf16_r2.txt): the MEPS-size model meets 2e-2
+on every element of every gradient; whole-gradient L2 errors are 4e-3 .. 9e-3 where the
+reference's autocast run has 4e-2 .. 7e-2."""
 import tempfile
 
 import pytest
@@ -189,13 +199,25 @@ def test_interaction_net_bf16_vs_oracle(dev, bf16, kernel_choice, d, M, n_send, 
         _close(x, y, "output")
     inet_loss(o_ref).backward()
     inet_loss(o).backward()
-    # >= 125 messages per receiver (M / n_rec) make the aggregated activations > 10x
-    # larger than the bf16-rounded inputs they came from: 4e-2 there, 2e-2 otherwise
-    tol = 4e-2 if M // n_rec > 100 else TOL
-    for x, y, n in zip(b, a, ("send", "rec", "edge")):
-        _close(x.grad, y.grad, f"grad {n}", tol=tol)
-    for (n, p), (_, q) in zip(ref.named_parameters(), net.named_parameters()):
-        _close(q.grad, p.grad, f"grad {n}", tol=tol)
+    # yard-stick: the same layer (oracle port) under the reference's bf16 mode (autocast)
+    import copy
+    ref_y = copy.deepcopy(ref)
+    ref_y.zero_grad()
+    a_y = [x.clone().requires_grad_() for x in xs]
+    with torch.autocast("cpu", dtype=torch.bfloat16):
+        o_y = ref_y(*a_y)
+    o_y = o_y if isinstance(o_y, tuple) else (o_y,)
+    inet_loss([t.float() for t in o_y]).backward()
+
+    def bound(y_bf16, y_fp32):
+        yard = ((y_bf16.float() - y_fp32).abs().max() / (y_fp32.abs().max() + 1e-30)).item()
+        return max(TOL, 2 * yard)
+
+    for x, y, z, n in zip(b, a, a_y, ("send", "rec", "edge")):
+        _close(x.grad, y.grad, f"grad {n}", tol=bound(z.grad, y.grad))
+    for (n, p), (_, q), (_, z) in zip(ref.named_parameters(), net.named_parameters(),
+                                      ref_y.named_parameters()):
+        _close(q.grad, p.grad, f"grad {n}", tol=bound(z.grad, p.grad))
 
 
 @pytest.mark.parametrize("name", sorted(MODELS))
@@ -217,23 +239,27 @@ def test_train_step_bf16_vs_reference(dev, bf16, name):
     loss.backward()
     with torch.no_grad():
         pred, _ = model.predict_step(batch[0][:, 1], batch[0][:, 0], batch[2][:, 0])
+    yard = load_golden("bf16_yardstick.pt")["cases"][name]
     if case.get("summary_only"):
+        # MEPS size (BASELINE configs[1]): EVERY element of every parameter gradient within
+        # the stated 2e-2 of that gradient's largest entry (full fp32 reference gradients:
+        # tests/golden/meps_grads.pt)
         _close(pred[:, ::997], entry["pred_slice"], f"{name} pred")
-        for n, p in model.named_parameters():
-            _close(p.grad.norm(), entry["grad_norms"][n], f"{name} |grad {n}|", tol=5e-2)
+        param_grads = load_golden("meps_grads.pt")[name]["param_grads"]
+        per_param_tol = {n: TOL for n in param_grads}
     else:
         _close(pred, entry["pred_step"], f"{name} pred")
-        # whole-gradient relative L2 error <= 5e-2; per parameter 5e-2 for the flat
-        # models.  HiLAM's gradients cross up to 26 stacked bf16 InteractionNets
-        # on graphs of 9..729 nodes and partly cancel, so single small parameter
-        # gradients are only required to stay within 2.5e-1 there.
-        names = [n for n, _ in model.named_parameters()]
-        got = torch.cat([p.grad.reshape(-1) for _, p in model.named_parameters()])
-        want = torch.cat([entry["param_grads"][n].reshape(-1) for n in names])
-        _close_l2(got, want, f"{name} all gradients", tol=5e-2)
-        tol = 2.5e-1 if case["model"].startswith("hi_lam") else 5e-2
-        for n, p in model.named_parameters():
-            _close_l2(p.grad, entry["param_grads"][n], f"{name} grad {n}", tol=tol)
+        # d = 8 / 16 toy models on 9..729-node graphs: gradients partly cancel, and the
+        # reference's own bf16 mode moves single parameter gradients by up to 8e-1 there;
+        # per parameter max(2e-2, 2 x the reference's own deviation)
+        param_grads = entry["param_grads"]
+        per_param_tol = {n: max(TOL, 2 * yard["grad_max"][n]) for n in param_grads}
+    names = [n for n, _ in model.named_parameters()]
+    got = torch.cat([p.grad.reshape(-1) for _, p in model.named_parameters()])
+    want = torch.cat([param_grads[n].reshape(-1) for n in names])
+    _close_l2(got, want, f"{name} all gradients", tol=TOL)  # whole gradient: 2e-2, all models
+    for n, p in model.named_parameters():
+        _close(p.grad, param_grads[n], f"{name} grad {n}", tol=per_param_tol[n])
 
 
 def test_bf16_deterministic(dev, bf16):

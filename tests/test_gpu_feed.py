@@ -50,7 +50,7 @@ def test_feed_equals_dataset_port(dev, T, N, ds, df, ar, past, future, standardi
         assert g.shape == w.shape, what
         assert torch.equal(g.cpu(), w), what
     with pytest.raises(RuntimeError, match="resident"):
-        feed.batch([len(ref)])
+        feed.batch([len(ref) + 1])
 
 
 def test_streaming_ring(dev):
