@@ -220,9 +220,29 @@ __device__ __forceinline__ void prefetch_tile_rows(const float* base, const int3
   }
 }
 
+// device-side twin of fast_gather(): shadows are only read on the square fast path
+__device__ __forceinline__ bool fast_gather_dev(const KParams& p) {
+  const nlam_rowmlp& d = p.d;
+  if (d.d_hidden != d.d_out || (d.d_hidden != 64 && d.d_hidden != 128)) return false;
+  for (int s = 0; s < d.n_src; ++s)
+    if (d.src[s].width != d.d_hidden || !p.vec_ok[s]) return false;
+  return true;
+}
+
 __device__ __forceinline__ void prefetch_sources(const KParams& p, int b, int row0, int cnt) {
   for (int s = 0; s < p.d.n_src; ++s) {
     const nlam_src& src = p.d.src[s];
+    if (src.shadow && fast_gather_dev(p)) {  // the gather will read the bf16 shadow rows
+      const int row = threadIdx.x;
+      if (row < cnt) {
+        const int ridx = src.idx ? __ldg(src.idx + row0 + row) : row0 + row;
+        const char* q = reinterpret_cast<const char*>(
+            reinterpret_cast<const __nv_bfloat16*>(src.shadow) +
+            (long long)b * src.shadow_batch_stride + (long long)ridx * src.width);
+        for (int l = 0; l < (src.width * 2 + 127) >> 7; ++l) prefetch_l2(q + l * 128);
+      }
+      continue;
+    }
     prefetch_tile_rows(src.ptr + (long long)b * src.batch_stride, src.idx, src.ld, src.width,
                        row0, cnt);
   }

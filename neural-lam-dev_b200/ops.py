@@ -214,7 +214,7 @@ def _src(t, idx, sh=None):
 # the fp32 tensor stays the master for residual streams and for autograd.  The shadow
 # travels as an attribute of the fp32 tensor object, together with the tensor's version
 # counter at the time it was written (an in-place update of the master invalidates it).
-SHADOW_WIDTH = 64
+SHADOW_WIDTHS = (64, 128)
 
 
 def attach_shadow(t, sh):
@@ -236,7 +236,7 @@ def shadow_of(t):
 def make_shadow(t):
     """Give a tensor that did not come out of one of this library's kernels (a leaf, user
     data) a bf16 shadow, so that consumers can take the shadow / TMA paths."""
-    if t.is_cuda and t.dtype == torch.float32 and t.shape[-1] == SHADOW_WIDTH:
+    if t.is_cuda and t.dtype == torch.float32 and t.shape[-1] in SHADOW_WIDTHS:
         attach_shadow(t, t.detach().to(torch.bfloat16).contiguous()
                       if t.is_contiguous() else t.detach().to(torch.bfloat16))
     return t
@@ -249,7 +249,7 @@ def set_shadows(enabled):
 
 def _want_shadow(W, precision, batch_rows_ok=True):
     return (precision == "bf16" and not _state.get("no_shadows", False)
-            and W.d_out == SHADOW_WIDTH and W.d_hidden <= 128 and W.k <= 384 and batch_rows_ok)
+            and W.d_out in SHADOW_WIDTHS and W.d_hidden <= 128 and W.k <= 384 and batch_rows_ok)
 
 
 def expand_with_shadow(x, batch_size):

@@ -92,7 +92,8 @@ class FlatGradBuckets:
         self._enc_pending -= 1
         if self._enc_pending > 0:
             return grad
-        if self.flat.is_cuda and torch.cuda.is_current_stream_capturing():
+        if (self.flat.is_cuda and torch.cuda.is_current_stream_capturing()
+                and not self.capture_collectives):
             return grad
         if self.overlap and self._early_work is None and not self._early_started:
             self._early_started = True
@@ -100,12 +101,20 @@ class FlatGradBuckets:
             self._launch_early()
         return grad
 
+    # True while the trainer captures a CUDA graph that contains the collectives: the early
+    # all-reduce then becomes a forked branch of the graph (side stream joined into the
+    # capture) that runs next to the encoder part of backward at every replay
+    capture_collectives = False
+
     def _launch_early(self):
-        if True:
-            # all early gradients are written on the compute stream: reduce them
-            # on the side stream while backward continues
-            self.side.wait_stream(torch.cuda.current_stream())
-            with torch.cuda.stream(self.side):
+        # all early gradients are written on the compute stream: reduce them
+        # on the side stream while backward continues
+        self.side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(self.side):
+            if torch.cuda.is_current_stream_capturing():
+                dist.all_reduce(self.flat[:self.n_early], op=dist.ReduceOp.AVG)
+                self._early_work = "captured"
+            else:
                 self._early_work = dist.all_reduce(
                     self.flat[:self.n_early], op=dist.ReduceOp.AVG, async_op=True)
 
@@ -113,12 +122,14 @@ class FlatGradBuckets:
         """Finish the gradient mean over ranks (call after backward)."""
         if self.world == 1:
             return
-        if self.flat.is_cuda and torch.cuda.is_current_stream_capturing():
-            raise RuntimeError("the gradient all-reduce must stay outside CUDA-graph capture")
+        if (self.flat.is_cuda and torch.cuda.is_current_stream_capturing()
+                and not self.capture_collectives):
+            raise RuntimeError("the gradient all-reduce must stay outside this CUDA-graph capture")
         if self.flat.is_cuda:
             if self._early_work is not None:
                 dist.all_reduce(self.flat[self.n_early:], op=dist.ReduceOp.AVG)
-                self._early_work.wait()
+                if self._early_work != "captured":
+                    self._early_work.wait()
                 torch.cuda.current_stream().wait_stream(self.side)
             else:
                 dist.all_reduce(self.flat, op=dist.ReduceOp.AVG)
@@ -147,6 +158,12 @@ class DataParallelTrainer:
         self.model = model
         self.use_cuda_graph = use_cuda_graph
         self._graph = None
+        self._graph_has_collectives = False
+        # measured on 8 x B200 (bench.py, GraphLAM configs[1]): collectives inside the graph
+        # 3.410 ms/step, outside 3.378 ms/step (2 GPUs: 3.377 vs 3.364) -- NCCL's kernels as
+        # graph nodes plus the fork/join cost more than the ~40 us of all-reduce they hide, so
+        # the default keeps them outside; NLAM_GRAPH_NCCL=1 captures them
+        self.graph_collectives = os.environ.get("NLAM_GRAPH_NCCL", "0") == "1"
         self._static_batch = None
         self._static_loss = None
         self.rank, self.world = rank, world_size
@@ -231,10 +248,25 @@ class DataParallelTrainer:
                             v.copy_(saved_state[id(p)][k])
                         else:
                             v.zero_()
-        # one process: the whole step is one graph.  Several ranks: forward + backward
-        # are the graph; the (single, latency-bound) NCCL all-reduce and AdamW stay
-        # outside it (NCCL inside a captured graph hung on this stack)
+        # One process: the whole step is one graph.  Several ranks, default: forward +
+        # backward are the graph, one all-reduce and AdamW are launched after each replay.
+        # graph_collectives (NLAM_GRAPH_NCCL=1): the whole step is the graph, NCCL
+        # all-reduces included -- the decoder / processor bucket's all-reduce is a forked
+        # branch next to the encoder part of backward, the encoder bucket's follows, AdamW
+        # closes the graph (works with capture_error_mode="thread_local"; not faster, see
+        # __init__).
         self._graph = torch.cuda.CUDAGraph()
+        self._graph_has_collectives = self.world > 1 and self.graph_collectives
+        if self._graph_has_collectives:
+            self.buckets.capture_collectives = True
+            try:
+                # thread_local: the NCCL watchdog thread's event queries must not abort
+                # the capture
+                with torch.cuda.graph(self._graph, capture_error_mode="thread_local"):
+                    self._static_loss = self._eager_step(self._static_batch)
+            finally:
+                self.buckets.capture_collectives = False
+            return
         with torch.cuda.graph(self._graph):
             if self.world == 1:
                 self._static_loss = self._eager_step(self._static_batch)
@@ -243,7 +275,7 @@ class DataParallelTrainer:
 
     def _replay(self):
         self._graph.replay()
-        if self.world > 1:
+        if self.world > 1 and not self._graph_has_collectives:
             self.buckets._early_work = None  # no hook fired: whole buffer in one all-reduce
             self.buckets.reduce()
             self.optimizer.step()

@@ -349,3 +349,36 @@ def test_tma_kernels_equal_register_gather(dev, bf16, update, aggr, expand_edges
             l.nlam_set_option(b"tma", 1)
     for x, y in zip(*res):
         assert torch.equal(x, y)
+
+
+@pytest.mark.parametrize("d", [64, 128])
+def test_shadow_chain_equals_fp32_gather(dev, bf16, d):
+    """Two chained InteractionNets (the second consumes the first one's outputs and their
+    bf16 shadows): bit-identical with and without shadows, d = 64 and d = 128."""
+    from neural_lam_b200 import ops
+    from neural_lam_b200.interaction_net import InteractionNet
+    g = torch.Generator().manual_seed(d)
+    M, n, B = 40000, 3000, 2
+    ei = torch.stack((torch.randint(0, n, (M,), generator=g), torch.randint(0, n, (M,), generator=g)))
+    ei[0, 0], ei[1, 0], ei[0, 1], ei[1, 1] = 0, 0, n - 1, n - 1
+    torch.manual_seed(d)
+    nets = [InteractionNet(ei.clone(), d).to(dev) for _ in range(2)]
+    x0 = torch.randn(B, n, d, generator=g).to(dev)
+    e0 = torch.randn(B, M, d, generator=g).to(dev)
+    res = []
+    for shadows in (True, False):
+        ops.set_shadows(shadows)
+        try:
+            x, e = x0.clone().requires_grad_(), e0.clone().requires_grad_()
+            h, f = nets[0](x, x, e)
+            assert (ops.shadow_of(h) is not None) == shadows
+            h, f = nets[1](h, h, f)
+            (h.square().sum() + f.sum()).backward()
+            res.append([h.detach().clone(), f.detach().clone(), x.grad.clone(), e.grad.clone()]
+                       + [p.grad.clone() for net in nets for p in net.parameters()])
+            for net in nets:
+                net.zero_grad()
+        finally:
+            ops.set_shadows(True)
+    for a, b in zip(*res):
+        assert torch.equal(a, b)
