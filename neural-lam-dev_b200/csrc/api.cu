@@ -27,7 +27,7 @@ static std::atomic<int> g_fwd_mc{env_or("NLAM_FWD_MC", -1)};
 static std::atomic<int> g_dgrad_mc{env_or("NLAM_DGRAD_MC", 0)};
 static std::atomic<int> g_bwd_fused{env_or("NLAM_BWD_FUSED", -1)};
 static std::atomic<int> g_pdl{env_or("NLAM_PDL", 1)};
-static std::atomic<int> g_tma{env_or("NLAM_TMA", 1)};
+static std::atomic<int> g_tma{env_or("NLAM_TMA", 0)};
 int option_tma() { return g_tma.load(); }
 int option_fwd_mc() { return g_fwd_mc.load(); }
 int option_dgrad_mc() { return g_dgrad_mc.load(); }

@@ -28,6 +28,11 @@ struct KParams {
   int g0_nsum;              // > 1: dOut = sum of g0_nsum slices of g0, g0_sum_stride floats apart
   long long g0_sum_stride;
   int inputs_stable;  // fwd.src rows were not written by the kernel just before this one
+  int sp_src, n_sp;         // sender pre-reduction (fused backward): source index or -1
+  const int32_t* sp_tile_ptr;
+  const int32_t* sp_row_ptr;
+  const int32_t* sp_rows;
+  int src0_batch_sum;       // d_src[0] = [1, rows, w] summed over the batch
   float* a_save;
   float* dy_save;
   float* dh_save;
@@ -81,6 +86,7 @@ inline int fill_params(const nlam_rowmlp& d, KParams& p) {
                  (((uintptr_t)d.out_res) % 16 == 0);
   p.lay = ParamLayout{k, d.d_hidden, d.d_out, d.w.ln_g != nullptr};
   p.reduce_src = -1;
+  p.sp_src = -1;
   NLAM_CHECK(!(d.agg.out || d.agg.out_bf16) || (d.agg.seg_ptr && d.agg.tile_seg && d.tile_ptr && d.n_chunks == 1),
              "rowmlp: agg needs seg_ptr, tile_seg and a (receiver-aligned) tile table");
   NLAM_CHECK(d.out || d.out_res || d.agg.out || true, "unreachable");

@@ -883,7 +883,7 @@ static TcBwdWs tc_bwd_ws(const KParams& p, const BGeo& g, bool fused) {
   w.a_img = o, o += fused ? 0 : al((size_t)g.total_tiles * g.kb2 * blk_f);
   w.dy_img = o, o += fused ? 0 : al((size_t)g.total_tiles * g.kbo * blk_f);
   w.dh_img = o, o += fused ? 0 : al((size_t)g.total_tiles * g.kb2 * blk_f);
-  w.d_slots = fused ? tc_bwd_fused_grid(g)
+  w.d_slots = fused ? (p.src0_batch_sum ? tc_bwd_fused_grid_bsum(g) : tc_bwd_fused_grid(g))
               : use_dgrad_mc(p, g) ? tc_dgrad_mc_grid(g)
                                    : grid_for(g.smem_bytes, g.tmem_cols, g.total_tiles);
   w.w_slots = fused ? w.d_slots : wgrad_grid(g);
@@ -935,6 +935,23 @@ int tc_rowmlp_bwd(const nlam_rowmlp_bwd& bd, cudaStream_t st) {
   int want_dz = 0;
   for (int s = 0; s < d.n_src; ++s) want_dz |= bd.d_src[s] != nullptr;
   const bool fused = tc::use_bwd_fused(p, want_dz);
+  // sender pre-reduction / batch-summed source-0 gradient: fused 64-wide kernel only
+  p.sp_src = bd.sp_src >= 0 && bd.sp_tile_ptr ? bd.sp_src : -1;
+  p.n_sp = bd.n_sp, p.sp_tile_ptr = bd.sp_tile_ptr, p.sp_row_ptr = bd.sp_row_ptr, p.sp_rows = bd.sp_rows;
+  p.src0_batch_sum = bd.src0_batch_sum;
+  if (p.sp_src >= 0 || p.src0_batch_sum) {
+    NLAM_CHECK(fused && tc_bwd_fused_kind(p) == 2 && d.tile_ptr && d.agg.tile_seg,
+               "rowmlp_bwd: sp_src / src0_batch_sum need the fused 64-wide kernel on "
+               "receiver-aligned tiles");
+    NLAM_CHECK(p.sp_src < 0 || (p.sp_src == 1 && bd.sp_row_ptr && bd.sp_rows && bd.n_sp > 0 &&
+                                bd.d_src[1] && !bd.d_src_idx[1] && !bd.d_src_idx[2] &&
+                                bd.reduce_src != 1 && !bd.d_src_bf16[1]),
+               "rowmlp_bwd: sp_src must be source 1 with dense, un-scattered partial rows");
+    NLAM_CHECK(!p.src0_batch_sum || (d.src[0].batch_stride == 0 && d.batch > 1 && !bd.g0 &&
+                                     d.residual_src < 0 && bd.d_src[0] && bd.reduce_src != 0 &&
+                                     !bd.d_src_bf16[0]),
+               "rowmlp_bwd: src0_batch_sum needs a batch-shared source 0 without residual");
+  }
   const tc::TcBwdWs ws = tc::tc_bwd_ws(p, g, fused);
   NLAM_CHECK(bd.workspace && bd.workspace_floats >= ws.total,
              "rowmlp_bwd: workspace too small (%zu < %zu floats)", bd.workspace_floats, ws.total);

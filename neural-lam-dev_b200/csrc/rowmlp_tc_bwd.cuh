@@ -105,6 +105,7 @@ int tc_rowmlp_dgrad_mc(const KParams& p, const tc::BGeo& g, cudaStream_t st);
 // fused input + weight gradient kernel (rowmlp_tc_bwd_fused.cu)
 int tc_bwd_fused_kind(const KParams& p);  // 0 no, 1 narrow inputs (no source gradients), 2 yes
 int tc_bwd_fused_grid(const tc::BGeo& g);
+int tc_bwd_fused_grid_bsum(const tc::BGeo& g);  // src0_batch_sum: row tiles are the dealt unit
 int tc_rowmlp_bwd_fused(const KParams& p, const tc::BGeo& g, cudaStream_t st);
 
 }  // namespace nlam

@@ -44,7 +44,9 @@ constexpr uint32_t FU_OFF_W1 = FU_CTX * FU_CTXB;
 constexpr uint32_t FU_OFF_W2 = FU_OFF_W1 + 3u * FU_FN * 128u;
 constexpr uint32_t FU_OFF_PAR = FU_OFF_W2 + FU_FN * 128u;
 constexpr uint32_t FU_OFF_LNX = FU_OFF_PAR + 3u * FU_FN * 4u;          // [ctx][4][TM][2] floats
-constexpr int FU_IXN = 9 * TM + 136;  // int32 per staged-index buffer (see stage_idx)
+constexpr int FU_SPO = 9 * TM + 136;  // sender-partial area: [0] first / [1] last+1 partial of the
+                                      // tile, then the partials' row ranges (<= 129 entries)
+constexpr int FU_IXN = FU_SPO + 136;  // int32 per staged-index buffer (see stage_idx)
 constexpr uint32_t FU_OFF_IDX = FU_OFF_LNX + FU_CTX * 4u * TM * 2u * 4u;  // [ctx][2][FU_IXN]
 constexpr uint32_t FU_OFF_BAR = FU_OFF_IDX + FU_CTX * 2u * FU_IXN * 4u;
 constexpr uint32_t FU_SMEM = FU_OFF_BAR + 256u;
@@ -182,9 +184,24 @@ rowmlp_tc_bwd_fused_kernel(const __grid_constant__ KParams p, const __grid_const
     // The same threads pull the rows themselves into L2.  The gather / dOut loads / stores
     // of the tile then start from an LDS instead of a dependent global load.
     int* sIx = reinterpret_cast<int*>(sm + FU_OFF_IDX) + ctx * (2 * FU_IXN);
-    auto stage_idx = [&](int tn, int* ix) {
+    // Tile enumeration.  Default: tile index t = (row tile) * batch + b, dealt SM-major
+    // (tile t -> SM t mod gridDim, then alternately to that SM's contexts).  Batch-sum mode
+    // (src0_batch_sum: source 0 is shared by the batch and its gradient is wanted summed
+    // over the batch): the UNIT dealt is the row tile, and a context runs its batch items
+    // one after the other, so that it can accumulate the gradient rows of source 0 in place.
+    const bool bsum = p.src0_batch_sum != 0;
+    auto decode = [&](int n, int& tile, int& b) -> bool {
+      if (bsum) {
+        tile = blockIdx.x + gridDim.x * ctx + (n / p.d.batch) * stride;
+        b = n % p.d.batch;
+        return tile < g.tiles_per_batch;
+      }
+      const int t = blockIdx.x + gridDim.x * ctx + n * stride;
+      tile = t / p.d.batch, b = t % p.d.batch;  // batch innermost: shared rows hit L2
+      return t < g.total_tiles;
+    };
+    auto stage_idx = [&](int tile_n, int bn, int* ix) {
       int r0n, cn, chn;
-      const int tile_n = tn / p.d.batch, bn = tn % p.d.batch;
       tile_range<TM>(p.d, tile_n, r0n, cn, chn);
       const int row = ltid & (TM - 1);
       const bool valid = row < cn;
@@ -245,6 +262,15 @@ rowmlp_tc_bwd_fused_kernel(const __grid_constant__ KParams p, const __grid_const
         ix[5 * TM + row] = __float_as_int(sc);
 #pragma unroll
         for (int s = 0; s < NLAM_MAX_SRC; ++s) ix[(6 + s) * TM + row] = orow[s];
+        if (p.sp_src >= 0) {
+          // partials of this tile: their rows are exactly the tile's rows, regrouped by
+          // sender, so the row list starts at the tile's first row
+          const int q_lo = __ldg(p.sp_tile_ptr + tile_n), q_hi = __ldg(p.sp_tile_ptr + tile_n + 1);
+          if (row == 0) ix[FU_SPO] = q_lo, ix[FU_SPO + 1] = q_hi;
+          if (valid) ix[7 * TM + row] = __ldg(p.sp_rows + r0n + row);
+          if (row <= q_hi - q_lo) ix[FU_SPO + 2 + row] = __ldg(p.sp_row_ptr + q_lo + row) - r0n;
+          if (row == 0) ix[FU_SPO + 2 + (q_hi - q_lo)] = __ldg(p.sp_row_ptr + q_hi) - r0n;
+        }
         if (p.reduce_src >= 0) {
           const int nseg = seg_hi - seg_lo;
           if (row == 0) ix[9 * TM] = seg_lo, ix[9 * TM + 1] = seg_hi;
@@ -263,8 +289,8 @@ rowmlp_tc_bwd_fused_kernel(const __grid_constant__ KParams p, const __grid_const
     };
     int pb = 0;
     {
-      const int t_first = blockIdx.x + gridDim.x * ctx;
-      if (t_first < g.total_tiles) stage_idx(t_first, sIx);
+      int tile0, b0;
+      if (decode(0, tile0, b0)) stage_idx(tile0, b0, sIx);
       fu_sync(ctx);
     }
     // Programmatic dependent launch: everything above -- TMEM allocation, weights -> bf16
@@ -283,8 +309,9 @@ rowmlp_tc_bwd_fused_kernel(const __grid_constant__ KParams p, const __grid_const
 
     // SM-major round robin: this SM's tiles are blockIdx.x, + gridDim.x, + 2 gridDim.x, ...
     // (counts differ by at most one ACROSS SMs), dealt alternately to its contexts
-    for (int t = blockIdx.x + gridDim.x * ctx; t < g.total_tiles; t += stride) {
-      const int b = t % p.d.batch, tile = t / p.d.batch;  // batch innermost: shared rows hit L2
+    for (int nt = 0;; ++nt) {
+      int tile, b;
+      if (!decode(nt, tile, b)) break;
       int row0, cnt, chunk;
       tile_range<TM>(p.d, tile, row0, cnt, chunk);
       const size_t grow0 = (size_t)b * p.d.rows + row0;
@@ -438,7 +465,10 @@ rowmlp_tc_bwd_fused_kernel(const __grid_constant__ KParams p, const __grid_const
         dm_load(ltid + 4 * FU_CT, va, vb, gs);
         dm_store(ltid + 4 * FU_CT, va, vb, gs);
       }
-      if (t + stride < g.total_tiles) stage_idx(t + stride, sIx + (pb ^ 1) * FU_IXN);
+      {
+        int tile_n, b_n;
+        if (decode(nt + 1, tile_n, b_n)) stage_idx(tile_n, b_n, sIx + (pb ^ 1) * FU_IXN);
+      }
       mbar_wait(bar_m, ph_m);
       ph_m ^= 1;
       tc_fence_after();
@@ -635,6 +665,7 @@ rowmlp_tc_bwd_fused_kernel(const __grid_constant__ KParams p, const __grid_const
           float* fdst = p.d_src[kb];
           const bool fres = fdst && (kb == p.d.residual_src) && p.g0;
           const bool reduce = fdst && kb == p.reduce_src;
+          const bool partial = fdst && kb == p.sp_src;
           const bool scat = fdst && p.d_src_idx[kb] != nullptr;  // rows staged in ix[6 + kb]
           float4 e[8];
           if (fres) {  // residual rows requested early
@@ -685,6 +716,23 @@ rowmlp_tc_bwd_fused_kernel(const __grid_constant__ KParams p, const __grid_const
               acc.x += old.x, acc.y += old.y, acc.z += old.z, acc.w += old.w;
               *o4 = acc;
             }
+          } else if (partial) {
+            // sender pre-reduction: one row per (tile, distinct sender) instead of one per
+            // edge -- the tile's rows of each sender are summed here (ascending row order),
+            // a CSR over the partial rows finishes the per-sender sum
+            const int q_lo = ix[FU_SPO], q_hi = ix[FU_SPO + 1];
+            const int* rp = ix + FU_SPO + 2 - q_lo;
+            float* po = fdst + (size_t)b * p.n_sp * FN + (ltid & 15) * 4;
+            for (int qi = q_lo + (ltid >> 4); qi < q_hi; qi += 16) {
+              const int j0 = rp[qi], j1 = rp[qi + 1];
+              float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+              for (int j = j0; j < j1; ++j) {
+                const float4 v =
+                    *reinterpret_cast<const float4*>(stgk + stg_idx(ix[7 * TM + j], ltid & 15, FN));
+                acc.x += v.x, acc.y += v.y, acc.z += v.z, acc.w += v.w;
+              }
+              *reinterpret_cast<float4*>(po + (size_t)qi * FN) = acc;
+            }
           } else if (fdst) {
             float* o = fdst + (ltid & 15) * 4;
 #pragma unroll
@@ -693,7 +741,20 @@ rowmlp_tc_bwd_fused_kernel(const __grid_constant__ KParams p, const __grid_const
               if (row < cnt) {
                 float4 v = *reinterpret_cast<const float4*>(stgk + stg_idx(row, ltid & 15, FN));
                 if (fres) v.x += e[i].x, v.y += e[i].y, v.z += e[i].z, v.w += e[i].w;
-                const size_t orow = scat ? (size_t)b * p.d.rows + ix[(6 + kb) * TM + row] : grow0 + row;
+                size_t orow = scat ? (size_t)b * p.d.rows + ix[(6 + kb) * TM + row] : grow0 + row;
+                if (bsum && kb == 0) {
+                  // batch-shared source: ONE gradient row per input row, accumulated over this
+                  // context's consecutive batch items by the thread that wrote it before
+                  orow -= (size_t)b * p.d.rows;
+                  if (b > 0) {
+                    const float4 old = *reinterpret_cast<const float4*>(o + orow * FN);
+                    v.x += old.x, v.y += old.y, v.z += old.z, v.w += old.w;
+                  }
+                  if (p.src0_batch_sum == 2 && b == p.d.batch - 1) {  // batch MEAN wanted
+                    const float sc = 1.0f / (float)p.d.batch;
+                    v.x *= sc, v.y *= sc, v.z *= sc, v.w *= sc;
+                  }
+                }
                 *reinterpret_cast<float4*>(o + orow * FN) = v;
                 if (p.d_src_bf16[kb])
                   *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(p.d_src_bf16[kb]) +
@@ -727,7 +788,8 @@ rowmlp_tc_bwd_fused_kernel(const __grid_constant__ KParams p, const __grid_const
     const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
     const int c0 = cq * 16;
     // a context without tiles (last CTA of a small launch) never wrote its accumulators
-    const bool two = (int)(blockIdx.x + gridDim.x) < g.total_tiles;
+    const bool two = p.src0_batch_sum ? (int)(blockIdx.x + gridDim.x) < g.tiles_per_batch
+                                      : (int)(blockIdx.x + gridDim.x) < g.total_tiles;
     float v[16], w[16];
     tmem_ld16(tmem_base + 128u + lane_addr + (uint32_t)c0, v);
     tmem_ld16(tmem_base + 256u + 128u + lane_addr + (uint32_t)c0, w);
@@ -811,12 +873,19 @@ int tc_bwd_fused_grid(const tc::BGeo& g) {
   int grid = (g.total_tiles + tc::FU_CTX - 1) / tc::FU_CTX;
   return grid > 148 ? 148 : grid;
 }
+// batch-sum mode deals row tiles (not tile x batch items) to the contexts
+int tc_bwd_fused_grid_bsum(const tc::BGeo& g) {
+  int grid = (g.tiles_per_batch + tc::FU_CTX - 1) / tc::FU_CTX;
+  return grid > 148 ? 148 : grid;
+}
 
 int tc_rowmlp_bwd_fused(const KParams& p, const tc::BGeo& g, cudaStream_t st) {
   NLAM_CUDA(ensure_dyn_smem((const void*)tc::rowmlp_tc_bwd_fused_kernel<true>, (int)tc::FU_SMEM));
   NLAM_CUDA(ensure_dyn_smem((const void*)tc::rowmlp_tc_bwd_fused_kernel<false>, (int)tc::FU_SMEM));
+  static_assert(tc::FU_SMEM <= 232448, "fused backward: shared memory");
   if (tc_bwd_fused_kind(p) == 2)
-    NLAM_CUDA(launch_k(tc::rowmlp_tc_bwd_fused_kernel<true>, tc_bwd_fused_grid(g), tc::FU_NT,
+    NLAM_CUDA(launch_k(tc::rowmlp_tc_bwd_fused_kernel<true>,
+                       p.src0_batch_sum ? tc_bwd_fused_grid_bsum(g) : tc_bwd_fused_grid(g), tc::FU_NT,
                        tc::FU_SMEM, st, p, g));
   else
     NLAM_CUDA(launch_k(tc::rowmlp_tc_bwd_fused_kernel<false>, tc_bwd_fused_grid(g), tc::FU_NT,

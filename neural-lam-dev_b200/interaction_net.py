@@ -58,6 +58,37 @@ class _GraphPlan:
         self.a_n_tiles = len(tile_seg) - 1
         # sender CSR over the receiver-sorted positions (backward of the x_j gather)
         self.ts_rowptr, self.ts_perm, _ = ops.csr_build(self.send_sorted, self.n_send_idx, False)
+        self._build_sender_partials(rowptr[tile_seg])
+
+    def _build_sender_partials(self, tile_ptr):
+        """Sender pre-reduction tables of the fused backward (nlam_rowmlp_bwd.sp_*): inside
+        a receiver-aligned tile the edges of one sender are summed on chip, so the kernel
+        writes one PARTIAL gradient row per (tile, distinct sender) instead of one row per
+        edge; a CSR over the partials (by sender, ascending tile order = deterministic)
+        finishes the per-sender sum.  m2g (4 nearest mesh nodes per grid node,
+        create_graph.py:506-519): ~11x fewer rows; m2m: ~2.4x; g2m (every grid node sends to
+        ~1.2 mesh nodes): nothing to gain, tables not built."""
+        self.sp = None
+        M, n_tiles = self.n_edges, self.a_n_tiles
+        send = self.send_sorted.cpu().numpy().astype(np.int64)
+        tile_of_row = np.repeat(np.arange(n_tiles, dtype=np.int64), np.diff(tile_ptr))
+        key = tile_of_row * max(self.n_send_idx, 1) + send
+        order = np.argsort(key, kind="stable")  # rows grouped by (tile, sender), ascending inside
+        ks = key[order]
+        starts = np.flatnonzero(np.r_[True, ks[1:] != ks[:-1]])
+        n_sp = int(starts.shape[0])
+        if n_sp > 0.6 * M:
+            return
+        mk = lambda a: torch.tensor(np.asarray(a, dtype=np.int32), device=self.device)
+        sender = mk(send[order[starts]])
+        rowptr, perm, _ = ops.csr_build(sender, self.n_send_idx, False)
+        self.sp = {
+            "n_sp": n_sp,
+            "tile_ptr": mk(np.searchsorted(tile_of_row[order[starts]], np.arange(n_tiles + 1), "left")),
+            "row_ptr": mk(np.r_[starts, M]),
+            "rows": mk(order - tile_ptr[tile_of_row[order]]),  # tile-local row ids
+            "csr_rowptr": rowptr, "csr_perm": perm,
+        }
 
     def aligned_tables(self, aggr):
         return {"tile_ptr": self.a_tile_ptr, "n_tiles": self.a_n_tiles,

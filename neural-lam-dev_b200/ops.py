@@ -19,7 +19,14 @@ from . import lib as L
 import os as _os
 
 _state = {"precision": "fp32",
-          "disable_aligned": _os.environ.get("NLAM_FUSED_AGG", "1") == "0"}
+          "disable_aligned": _os.environ.get("NLAM_FUSED_AGG", "1") == "0",
+          # on-chip reductions of the fused edge backward (set_backward_reductions):
+          # sender partials: measured -3 % on the m2g layer (1274 -> 1235 us fwd+bwd), on;
+          # batch-summed static edge gradient: measured +29 % (1274 -> 1646 us: the batch
+          # items of a row tile must then run one after the other in ONE context and
+          # read-modify-write their gradient rows), off
+          "no_sender_partials": _os.environ.get("NLAM_SENDER_PARTIALS", "1") == "0",
+          "no_batch_sum": _os.environ.get("NLAM_BATCH_SUM", "0") != "1"}
 _PREC = {"fp32": L.FP32, "bf16": L.BF16}
 
 
@@ -96,6 +103,14 @@ def _grad_sink(params):
     if base.storage_offset() + total > base.untyped_storage().nbytes() // 4:
         return None
     return torch.as_strided(base, (1, total), (total, 1))
+
+
+def set_backward_reductions(sender_partials=True, batch_sum=False):
+    """On-chip reductions of the fused edge backward (A/B switch for tests and benchmarks):
+    per-(tile, sender) partial gradient rows instead of per-edge rows, and the gradient of a
+    batch-shared edge embedding summed over the batch inside the kernel."""
+    _state["no_sender_partials"] = not sender_partials
+    _state["no_batch_sum"] = not batch_sum
 
 
 def set_fused_aggregation(enabled):
@@ -489,7 +504,7 @@ def rowmlp_fwd_raw(srcs, W, batch, rows, residual, tiles, precision, want_res=Fa
 def rowmlp_bwd_raw(srcs, W, batch, rows, residual, tiles, precision, g0, need_src,
                    g1=None, g1_idx=None, g1_scale=None, aligned=None, g0_idx=None,
                    d_src_idx=None, reduce_src=-1, reduce_into=None, sink_params=None,
-                   g0_sum=False, algo_dsrc_bytes=None):
+                   g0_sum=False, algo_dsrc_bytes=None, sp=None, batch_sum0=0, info=None):
     """Returns (list of per-row source grads or None, d_params (n_chunks, P)).
     aligned / g0_idx / d_src_idx / reduce_src: fused-aggregation path; the
     gradient rows of source `reduce_src` are segment-summed and ADDED into the
@@ -504,7 +519,12 @@ def rowmlp_bwd_raw(srcs, W, batch, rows, residual, tiles, precision, g0, need_sr
     if g0_idx is not None:
         bd.g0_idx = g0_idx.data_ptr()
     keep = []
+    g0_copies = 0
     if g0 is not None:
+        if g0_sum and g0.dim() == 3 and g0.shape[0] > 1 and g0.stride(0) == 0:
+            # a stride-0 batch view (the producer already summed / averaged over the batch,
+            # see batch_sum0): read the one slice shape[0] times instead of materialising it
+            g0_copies, g0 = g0.shape[0], g0[0:1]
         g0 = g0.contiguous()
         _check_cuda(g0, "grad_output")
         bd.g0 = g0.data_ptr()
@@ -515,9 +535,37 @@ def rowmlp_bwd_raw(srcs, W, batch, rows, residual, tiles, precision, g0, need_sr
         bd.g1_scale = g1_scale.data_ptr() if g1_scale is not None else None
         bd.g1_batch_stride = g1.stride(0) if g1.shape[0] > 1 else 0
         assert g1.stride(1) == W.d_out or g1.shape[1] == 1
+    # sender pre-reduction / batch-summed gradient of a batch-shared source 0: fused kernel only
+    lib_fused = None
+    if sp is not None or batch_sum0:
+        for i, (it, need) in enumerate(zip(srcs, need_src)):  # probe with plain outputs
+            bd.d_src[i] = 1 if need else None
+        lib_fused = lib.nlam_rowmlp_bwd_stages(ctypes.byref(bd)) == 2
+        for i in range(len(srcs)):
+            bd.d_src[i] = None
+        if not lib_fused:
+            sp, batch_sum0 = None, 0
+    if info is not None:
+        info["sp"], info["batch_sum0"] = sp is not None, batch_sum0
     d_srcs = []
     for i, (it, need) in enumerate(zip(srcs, need_src)):
         t = it[0]
+        if need and sp is not None and i == 1:
+            g = torch.empty((batch, sp["n_sp"], t.shape[2]), device=dev, dtype=torch.float32)
+            bd.d_src[i] = g.data_ptr()
+            bd.sp_src, bd.n_sp = 1, sp["n_sp"]
+            bd.sp_tile_ptr, bd.sp_row_ptr = sp["tile_ptr"].data_ptr(), sp["row_ptr"].data_ptr()
+            bd.sp_rows = sp["rows"].data_ptr()
+            d_srcs.append(g)
+            continue
+        if need and batch_sum0 and i == 0:
+            g = torch.empty((1, rows, t.shape[2]), device=dev, dtype=torch.float32)
+            bd.d_src[i] = g.data_ptr()
+            bd.src0_batch_sum = batch_sum0
+            if d_src_idx is not None and d_src_idx[i] is not None:
+                bd.d_src_idx[i] = d_src_idx[i].data_ptr()
+            d_srcs.append(g)
+            continue
         if need and i == reduce_src:
             assert reduce_into is not None and reduce_into.is_contiguous()
             bd.d_src[i] = reduce_into.data_ptr()
@@ -532,12 +580,15 @@ def rowmlp_bwd_raw(srcs, W, batch, rows, residual, tiles, precision, g0, need_sr
             d_srcs.append(g)
         else:
             d_srcs.append(None)
-    if g0_sum and g0 is not None and g0.shape[0] > 1:
+    if g0_sum and g0 is not None and (g0.shape[0] > 1 or g0_copies > 1):
         assert batch == 1 and g1 is None and not residual
-        bd.g0_sum_count, bd.g0_sum_stride = g0.shape[0], g0.stride(0)
+        if g0_copies > 1:
+            bd.g0_sum_count, bd.g0_sum_stride = g0_copies, 0
+        else:
+            bd.g0_sum_count, bd.g0_sum_stride = g0.shape[0], g0.stride(0)
         if lib.nlam_rowmlp_bwd_stages(ctypes.byref(bd)) != 2 or W.d_out != 64:
             bd.g0_sum_count, bd.g0_sum_stride = 0, 0  # no fused kernel here: sum first
-            g0 = g0.sum(0, keepdim=True)
+            g0 = g0 * float(g0_copies) if g0_copies > 1 else g0.sum(0, keepdim=True)
             bd.g0 = g0.data_ptr()
     sink = _grad_sink(sink_params) if (W.n_chunks == 1 and sink_params is not None) else None
     if sink is not None:
@@ -580,8 +631,8 @@ def rowmlp_bwd_raw(srcs, W, batch, rows, residual, tiles, precision, g0, need_sr
         for i, (it, need) in enumerate(zip(srcs, need_src)):
             if need and i == reduce_src:
                 dsrc_bytes += 2 * 4 * reduce_into.numel()
-            elif need:
-                dsrc_bytes += rows_all * 4 * it[0].shape[2]
+            elif need:  # rows this launch writes (per edge, per (tile, sender), or batch-summed)
+                dsrc_bytes += 4 * d_srcs[i].numel()
         dsrc = sum(it[0].shape[2] for it, n in zip(srcs, need_src) if n)
         img = 2 * (2 * W.d_hidden + W.d_out) if precision == "bf16" else 4 * (2 * W.d_hidden + W.d_out)
         fl = 2 * rows_all * (k * W.d_hidden + W.d_hidden * W.d_out)
@@ -920,6 +971,14 @@ class _InteractionNetFn(torch.autograd.Function):
         scale = plan.inv_deg if meta["aggr"] == "mean" else None
         if meta["aligned"]:
             al = plan.aligned_tables(meta["aggr"])
+            # batch-shared static edge embedding (g2m / m2g / first m2m layer): its gradient is
+            # accumulated over the batch inside the kernel (1 = sum for a batch-1 tensor,
+            # 2 = mean for a stride-0 expanded view, whose autograd gradient is summed again)
+            shared_e = B > 1 and (edge3.shape[0] == 1 or edge3.stride(0) == 0)
+            bs0 = 0
+            if shared_e and need_edge and d_edge_out is None and not _state.get("no_batch_sum"):
+                bs0 = 1 if edge3.shape[0] == 1 else 2
+            binfo = {}
             (d_edge, dzS, d_rec), dPe = rowmlp_bwd_raw(
                 [(edge3, plan.perm, sh_edge), (send3, plan.send_sorted, sh_send),
                  (rec3, plan.recv_sorted, sh_rec)],
@@ -928,21 +987,29 @@ class _InteractionNetFn(torch.autograd.Function):
                 g1_scale=scale, aligned=al, g0_idx=plan.perm,
                 d_src_idx=[plan.perm, None, None], reduce_src=2 if need_rec else -1,
                 reduce_into=dR, sink_params=meta.get("edge_params"),
+                sp=plan.sp if (need_send and not _state.get("no_sender_partials")) else None,
+                batch_sum0=bs0, info=binfo,
                 algo_dsrc_bytes=4 * We.d_out * (
                     (M * (edge3.shape[0] if edge3.stride(0) != 0 else 1) if need_edge else 0)
                     + (B * plan.n_send_idx if need_send else 0)
                     + (2 * B * n_rec if need_rec else 0)))
             d_send = None
+            if binfo.get("batch_sum0") == 2:
+                d_edge = d_edge.expand(B, -1, -1)  # the batch MEAN: autograd's expand-backward
+                #                                    sums the B slices back to the batch sum
             if need_send:
+                # per-sender sum: over the per-edge rows, or over the (tile, sender) partials
+                s_ptr, s_perm = ((plan.sp["csr_rowptr"], plan.sp["csr_perm"]) if binfo.get("sp")
+                                 else (plan.ts_rowptr, plan.ts_perm))
                 if (meta.get("same_send_rec") and need_rec and plan.n_send_idx == n_rec
                         and d_rec is dR and dR.shape[0] == B):
                     # sender and receiver rows are the SAME tensor (m2m layers,
                     # graph_lam.py:51-57): its gradient is d_send + d_rec -- accumulate the
                     # sender part into the receiver gradient instead of returning two
                     # tensors for autograd to add
-                    segsum_raw(dzS, plan.ts_rowptr, plan.ts_perm, n_rec, out=dR, accumulate=True)
+                    segsum_raw(dzS, s_ptr, s_perm, n_rec, out=dR, accumulate=True)
                 else:
-                    d_send = segsum_raw(dzS, plan.ts_rowptr, plan.ts_perm, plan.n_send_idx)
+                    d_send = segsum_raw(dzS, s_ptr, s_perm, plan.n_send_idx)
         else:
             (dzE, dzS, dzR), dPe = rowmlp_bwd_raw(
                 [(edge3, None, sh_edge), (send3, plan.send32, sh_send),
@@ -965,6 +1032,9 @@ class _InteractionNetFn(torch.autograd.Function):
             if g is not None and t.shape[0] == 1 and g.shape[0] > 1:
                 g = g.sum(0, keepdim=True)
             return g
+
+        if meta["aligned"] and binfo.get("batch_sum0") == 1:
+            pass  # d_edge is already the (1, M, d) batch sum
 
         return (None, *We.split_grads(dPe), *Wa.split_grads(dPa), fit(d_send, send3),
                 fit(d_rec, rec3), fit(d_edge, edge3))

@@ -17,9 +17,14 @@ from neural_lam_b200.interaction_net import InteractionNet  # noqa: E402
 
 def main():
     which = sys.argv[1] if len(sys.argv) > 1 else "m2g"
+    red = {"sp": 1, "bs": 1}
     for kv in sys.argv[2:]:
         k, v = kv.split("=")
-        lib.load().nlam_set_option(k.encode(), int(v))
+        if k in red:
+            red[k] = int(v)
+        else:
+            lib.load().nlam_set_option(k.encode(), int(v))
+    ops.set_backward_reductions(bool(red["sp"]), bool(red["bs"]))
     dev = torch.device("cuda:0")
     B, d = 4, 64
     with tempfile.TemporaryDirectory() as root:
