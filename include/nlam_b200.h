@@ -264,7 +264,10 @@ int nlam_version(void);
  * for square 64-wide MLPs.  Environment NLAM_FWD_MC / NLAM_DGRAD_MC /
  * NLAM_BWD_FUSED give the initial values.  "pdl" (default 1, env NLAM_PDL): launch with
  * programmatic dependent launch so that a kernel's prologue overlaps the tail of the
- * previous one (every kernel waits with griddepcontrol.wait before reading its inputs). */
+ * previous one (every kernel waits with griddepcontrol.wait before reading its inputs).
+ * "tma" (default 0, env NLAM_TMA): forward edge kernel whose operands arrive by
+ * cp.async.bulk.tensor tile::gather4 from the bf16 shadows; "bwd_nh" (default 2, env
+ * NLAM_BWD_NH): threads per tile row of the fused backward kernel (2 or 4). */
 int nlam_set_option(const char* name, int value);
 /* Number of kernels this library has launched in this process (monotonic;
  * bench.py reports the delta over its timed region as "gpu_launches"). */

@@ -952,6 +952,8 @@ int tc_rowmlp_bwd(const nlam_rowmlp_bwd& bd, cudaStream_t st) {
                                      !bd.d_src_bf16[0]),
                "rowmlp_bwd: src0_batch_sum needs a batch-shared source 0 without residual");
   }
+  NLAM_CHECK(!fused || (!bd.d_src_idx[1] && !bd.d_src_idx[2]),
+             "rowmlp_bwd: the fused kernel scatters the rows of source 0 only (d_src_idx[1..2])");
   const tc::TcBwdWs ws = tc::tc_bwd_ws(p, g, fused);
   NLAM_CHECK(bd.workspace && bd.workspace_floats >= ws.total,
              "rowmlp_bwd: workspace too small (%zu < %zu floats)", bd.workspace_floats, ws.total);

@@ -35,25 +35,39 @@ namespace nlam {
 namespace tc {
 
 constexpr int FU_CTX = 2;
-constexpr int FU_CT = 256;                     // threads per context
-constexpr int FU_NT = FU_CTX * FU_CT;
 constexpr int FU_FN = 64;
+// NH = threads per tile row (column groups of 64 / NH columns): a context has 128 * NH threads.
+// NH = 2 (default): 2 x 8 warps per SM at <= 128 registers.  NH = 4: 2 x 16 warps at <= 64
+// registers -- every epilogue phase is half as long per thread and twice as many warps could
+// hide its latencies, but the 64-register budget spills and the instruction count grows:
+// measured 7 % slower on the GraphLAM step (nlam_set_option("bwd_nh", 4) to try it).
+template <int NH> struct FuCfg {
+  static constexpr int CT = 128 * NH;            // threads per context
+  static constexpr int NT = FU_CTX * CT;
+  static constexpr int CPT = FU_FN / NH;         // columns per thread
+  static constexpr int CH = CPT / 16;            // 16-column chunks per thread
+};
 constexpr uint32_t FU_BLK = TM * 128u;         // one 64-column bf16 tile block: 16 KB
 constexpr uint32_t FU_CTXB = 5u * FU_BLK;      // z (3) | a/dH | dOut/dY
 constexpr uint32_t FU_OFF_W1 = FU_CTX * FU_CTXB;
 constexpr uint32_t FU_OFF_W2 = FU_OFF_W1 + 3u * FU_FN * 128u;
 constexpr uint32_t FU_OFF_PAR = FU_OFF_W2 + FU_FN * 128u;
-constexpr uint32_t FU_OFF_LNX = FU_OFF_PAR + 3u * FU_FN * 4u;          // [ctx][4][TM][2] floats
-constexpr int FU_SPO = 9 * TM + 136;  // sender-partial area: [0] first / [1] last+1 partial of the
-                                      // tile, then the partials' row ranges (<= 129 entries)
-constexpr int FU_IXN = FU_SPO + 136;  // int32 per staged-index buffer (see stage_idx)
-constexpr uint32_t FU_OFF_IDX = FU_OFF_LNX + FU_CTX * 4u * TM * 2u * 4u;  // [ctx][2][FU_IXN]
-constexpr uint32_t FU_OFF_BAR = FU_OFF_IDX + FU_CTX * 2u * FU_IXN * 4u;
-constexpr uint32_t FU_SMEM = FU_OFF_BAR + 256u;
+constexpr uint32_t FU_OFF_LNX = FU_OFF_PAR + 3u * FU_FN * 4u;          // [ctx][4][TM][NH] floats
+// staged-index buffer (int32, see stage_idx): source rows | g0 row | g1 row | scatter row of the
+// source-0 gradient | tile-local rows of the sender partials | segment area | partial area
+constexpr int IX_G0 = 3 * TM, IX_G1 = 4 * TM, IX_SCAT = 5 * TM, IX_SPR = 6 * TM;
+constexpr int IX_SEG = 7 * TM;        // [0] first / [1] last+1 segment, then <= 129 boundaries
+constexpr int FU_SPO = IX_SEG + 132;  // [0] first / [1] last+1 partial, then <= 129 row ranges
+constexpr int FU_IXN = FU_SPO + 132;
+__host__ __device__ constexpr uint32_t fu_off_idx(int nh) { return FU_OFF_LNX + FU_CTX * 4u * TM * (uint32_t)nh * 4u; }
+__host__ __device__ constexpr uint32_t fu_off_bar(int nh) { return fu_off_idx(nh) + FU_CTX * 2u * FU_IXN * 4u; }
+__host__ __device__ constexpr uint32_t fu_smem(int nh) { return fu_off_bar(nh) + 64u; }
+static_assert(fu_smem(4) <= 232448, "fused backward: shared memory");
 constexpr int FU_NBAR = 3;  // per context: main, dZ0, dZ1
 
+template <int CT>
 __device__ __forceinline__ void fu_sync(int ctx) {
-  asm volatile("bar.sync %0, 256;" ::"r"(ctx + 1) : "memory");
+  asm volatile("bar.sync %0, %1;" ::"r"(ctx + 1), "n"(CT) : "memory");
 }
 __device__ __forceinline__ void unpack8(const uint4& q, float* v) {
   v[0] = __uint_as_float(q.x << 16), v[1] = __uint_as_float(q.x & 0xffff0000u);
@@ -64,15 +78,18 @@ __device__ __forceinline__ void unpack8(const uint4& q, float* v) {
 
 // FG = true : every source is 64 wide and 16-byte aligned (vector gather; source gradients)
 // FG = false: arbitrary source widths with k_total <= 64 (embedders; no source gradients)
-template <bool FG>
-__global__ void __launch_bounds__(FU_NT, 1)
+template <bool FG, int NH>
+__global__ void __launch_bounds__(FuCfg<NH>::NT, 1)
 rowmlp_tc_bwd_fused_kernel(const __grid_constant__ KParams p, const __grid_constant__ BGeo g) {
   extern __shared__ __align__(1024) uint8_t sm[];
   if (smem_u32(sm) & 1023u) __trap();
   constexpr int FN = FU_FN;
+  constexpr int FU_CT = FuCfg<NH>::CT, FU_NT = FuCfg<NH>::NT;
+  constexpr int CPT = FuCfg<NH>::CPT, CH = FuCfg<NH>::CH;
+  constexpr uint32_t FU_OFF_IDX = fu_off_idx(NH), FU_OFF_BAR = fu_off_bar(NH);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int ctx = tid >> 8;
-  const int ltid = tid & 255, lwarp = ltid >> 5;
+  const int ctx = tid / FU_CT;
+  const int ltid = tid % FU_CT, lwarp = ltid >> 5;
   uint8_t* sW1 = sm + FU_OFF_W1;
   uint8_t* sW2 = sm + FU_OFF_W2;
   float* sPar = reinterpret_cast<float*>(sm + FU_OFF_PAR);  // b1 | b2 | gamma
@@ -137,9 +154,9 @@ rowmlp_tc_bwd_fused_kernel(const __grid_constant__ KParams p, const __grid_const
   const int mch = FG ? (n_src + 1) / 2 : 1;  // 128-row chunks of dW1^T
 
   // per-thread column sums
-  float acc_db1[2], acc_db2[2], acc_dg[2];
+  float acc_db1[CH], acc_db2[CH], acc_dg[CH];
 #pragma unroll
-  for (int i = 0; i < 2; ++i) acc_db1[i] = acc_db2[i] = acc_dg[i] = 0.f;
+  for (int i = 0; i < CH; ++i) acc_db1[i] = acc_db2[i] = acc_dg[i] = 0.f;
   // column sums of the dOut rows in fp32, BEFORE they are rounded to bf16 (LayerNorm beta
   // gradient; b2 gradient of an MLP without LayerNorm): this thread's 4 columns
   // (ltid & 15) * 4 .. + 3 of the rows it loads
@@ -152,7 +169,7 @@ rowmlp_tc_bwd_fused_kernel(const __grid_constant__ KParams p, const __grid_const
     uint8_t* sD = sA + 3u * FU_BLK;                        // dOut (bf16) -> dY
     uint8_t* sT = sA + 4u * FU_BLK;                        // a -> dH
     // dZ staging: two fp32 [128][64] buffers = blocks 0-1 and 2-3 (z and dY are dead by then)
-    float* sLnx = reinterpret_cast<float*>(sm + FU_OFF_LNX) + ctx * (4 * TM * 2);
+    float* sLnx = reinterpret_cast<float*>(sm + FU_OFF_LNX) + ctx * (4 * TM * NH);
     uint64_t* cb = &bars[ctx * FU_NBAR];
     uint64_t* bar_m = &cb[0];
     uint64_t* bar_z = &cb[1];
@@ -173,7 +190,9 @@ rowmlp_tc_bwd_fused_kernel(const __grid_constant__ KParams p, const __grid_const
     const float* sB2 = sPar + FN;
     const float* sG = sPar + 2 * FN;
     const int k1steps = FG ? n_src * FN / 16 : FN / 16;
-    const int gc = ltid & 7, grl = ltid >> 3;  // gather: 16-byte bf16 chunk / row of a 32-row pass
+    const int gc = ltid & 7, grl = ltid >> 3;  // gather: 16-byte bf16 chunk / row of a GRP-row pass
+    constexpr int GRP = FU_CT / 8, GNP = TM / GRP;  // rows per gather pass, passes
+    constexpr int ORP = FU_CT / 16, ONP = TM / ORP;  // output phases: rows per pass, passes
 
     // Everything index-like a tile needs is fetched ONE TILE AHEAD, spread over the 256
     // threads, and parked in shared memory:
@@ -205,6 +224,7 @@ rowmlp_tc_bwd_fused_kernel(const __grid_constant__ KParams p, const __grid_const
       tile_range<TM>(p.d, tile_n, r0n, cn, chn);
       const int row = ltid & (TM - 1);
       const bool valid = row < cn;
+      if (ltid >= 2 * TM) return;
       if (ltid < TM) {
         int ri[NLAM_MAX_SRC];
 #pragma unroll
@@ -231,22 +251,16 @@ rowmlp_tc_bwd_fused_kernel(const __grid_constant__ KParams p, const __grid_const
           }
         }
       } else {
-        int g0r = -1, g1r = -1, orow[NLAM_MAX_SRC];
-        float sc = 1.f;
+        int g0r = -1, g1r = -1, orow0 = -1;
         if (valid && p.g0) g0r = p.g0_idx ? __ldg(p.g0_idx + r0n + row) : r0n + row;
         if (valid && p.g1) g1r = __ldg(p.g1_idx + r0n + row);
-#pragma unroll
-        for (int s = 0; s < NLAM_MAX_SRC; ++s) {
-          orow[s] = -1;
-          if (s < n_src && valid && p.d_src[s] && p.d_src_idx[s] && s != p.reduce_src)
-            orow[s] = __ldg(p.d_src_idx[s] + r0n + row);
-        }
+        if (valid && p.d_src[0] && p.d_src_idx[0] && p.reduce_src != 0)
+          orow0 = __ldg(p.d_src_idx[0] + r0n + row);
         int seg_lo = 0, seg_hi = 0;
         if (p.reduce_src >= 0) {
           seg_lo = __ldg(p.d.agg.tile_seg + tile_n);
           seg_hi = __ldg(p.d.agg.tile_seg + tile_n + 1);
         }
-        if (g1r >= 0 && p.g1_scale) sc = __ldg(p.g1_scale + g1r);
         if (g0r >= 0) {
           const float* qq = p.g0 + ((size_t)bn * p.d.rows + g0r) * dout;
           prefetch_l2(qq);
@@ -257,26 +271,24 @@ rowmlp_tc_bwd_fused_kernel(const __grid_constant__ KParams p, const __grid_const
           prefetch_l2(qq);
           prefetch_l2(qq + 32);
         }
-        ix[3 * TM + row] = g0r;
-        ix[4 * TM + row] = g1r;
-        ix[5 * TM + row] = __float_as_int(sc);
-#pragma unroll
-        for (int s = 0; s < NLAM_MAX_SRC; ++s) ix[(6 + s) * TM + row] = orow[s];
+        ix[IX_G0 + row] = g0r;
+        ix[IX_G1 + row] = g1r;
+        ix[IX_SCAT + row] = orow0;
         if (p.sp_src >= 0) {
           // partials of this tile: their rows are exactly the tile's rows, regrouped by
           // sender, so the row list starts at the tile's first row
           const int q_lo = __ldg(p.sp_tile_ptr + tile_n), q_hi = __ldg(p.sp_tile_ptr + tile_n + 1);
           if (row == 0) ix[FU_SPO] = q_lo, ix[FU_SPO + 1] = q_hi;
-          if (valid) ix[7 * TM + row] = __ldg(p.sp_rows + r0n + row);
+          if (valid) ix[IX_SPR + row] = __ldg(p.sp_rows + r0n + row);
           if (row <= q_hi - q_lo) ix[FU_SPO + 2 + row] = __ldg(p.sp_row_ptr + q_lo + row) - r0n;
           if (row == 0) ix[FU_SPO + 2 + (q_hi - q_lo)] = __ldg(p.sp_row_ptr + q_hi) - r0n;
         }
         if (p.reduce_src >= 0) {
           const int nseg = seg_hi - seg_lo;
-          if (row == 0) ix[9 * TM] = seg_lo, ix[9 * TM + 1] = seg_hi;
+          if (row == 0) ix[IX_SEG] = seg_lo, ix[IX_SEG + 1] = seg_hi;
           if (nseg <= TM) {
-            if (row <= nseg) ix[9 * TM + 2 + row] = __ldg(p.d.agg.seg_ptr + seg_lo + row) - r0n;
-            if (row == 0) ix[9 * TM + 2 + nseg] = __ldg(p.d.agg.seg_ptr + seg_hi) - r0n;
+            if (row <= nseg) ix[IX_SEG + 2 + row] = __ldg(p.d.agg.seg_ptr + seg_lo + row) - r0n;
+            if (row == 0) ix[IX_SEG + 2 + nseg] = __ldg(p.d.agg.seg_ptr + seg_hi) - r0n;
             if (row < nseg && p.reduce_accumulate) {  // rows the reduction will read-modify-write
               const float* qq = p.d_src[p.reduce_src] +
                                 ((size_t)bn * p.d.agg.n_seg + seg_lo + row) * FN;
@@ -291,7 +303,7 @@ rowmlp_tc_bwd_fused_kernel(const __grid_constant__ KParams p, const __grid_const
     {
       int tile0, b0;
       if (decode(0, tile0, b0)) stage_idx(tile0, b0, sIx);
-      fu_sync(ctx);
+      fu_sync<FU_CT>(ctx);
     }
     // Programmatic dependent launch: everything above -- TMEM allocation, weights -> bf16
     // operands, the first tile's index tables (static graph data; its L2 prefetches of
@@ -325,8 +337,8 @@ rowmlp_tc_bwd_fused_kernel(const __grid_constant__ KParams p, const __grid_const
         for (int j = 0; j < 4; ++j) {
           const int u = base + j * FU_CT, row = u >> 4, col = (u & 15) * 4;
           g0p[j] = g1p[j] = nullptr;
-          const int g0r = ix[3 * TM + row], g1r = ix[4 * TM + row];
-          gs[j] = __int_as_float(ix[5 * TM + row]);
+          const int g0r = ix[IX_G0 + row], g1r = ix[IX_G1 + row];
+          gs[j] = (g1r >= 0 && p.g1_scale) ? __ldg(p.g1_scale + g1r) : 1.f;
           if (g0r >= 0) g0p[j] = p.g0 + ((size_t)b * p.d.rows + g0r) * dout + col;
           if (g1r >= 0) g1p[j] = p.g1 + (size_t)b * p.g1_batch_stride + (size_t)g1r * dout + col;
         }
@@ -381,7 +393,7 @@ rowmlp_tc_bwd_fused_kernel(const __grid_constant__ KParams p, const __grid_const
       if constexpr (!FG) {
         // narrow sources: unit = 8 concatenated input columns of one row (scalar loads)
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
+        for (int i = 0; i < TM * 8 / FU_CT; ++i) {
           const int u = ltid + i * FU_CT, row = u >> 3, k0 = (u & 7) * 8;
           float v[8];
 #pragma unroll
@@ -406,26 +418,26 @@ rowmlp_tc_bwd_fused_kernel(const __grid_constant__ KParams p, const __grid_const
       for (int s = 0; s < n_src; ++s) {
         const nlam_src& src = p.d.src[s];
         const float* base = src.ptr + (long long)b * src.batch_stride + gc * 8;
-        int ridx[4];
+        int ridx[GNP];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) ridx[i] = ix[s * TM + i * 32 + grl];
+        for (int i = 0; i < GNP; ++i) ridx[i] = ix[s * TM + i * GRP + grl];
         if (src.shadow) {  // bf16 shadow rows: raw 16-byte chunks, no conversion
           const uint4* sb = reinterpret_cast<const uint4*>(
               reinterpret_cast<const __nv_bfloat16*>(src.shadow) + (long long)b * src.shadow_batch_stride) + gc;
-          uint4 qv[4];
+          uint4 qv[GNP];
 #pragma unroll
-          for (int i = 0; i < 4; ++i) {
+          for (int i = 0; i < GNP; ++i) {
             qv[i] = make_uint4(0u, 0u, 0u, 0u);
             if (ridx[i] >= 0) qv[i] = __ldg(sb + (long long)ridx[i] * 8);
           }
 #pragma unroll
-          for (int i = 0; i < 4; ++i)
-            *reinterpret_cast<uint4*>(sA + sw128_off(i * 32 + grl, s * FN + gc * 8, FU_BLK)) = qv[i];
+          for (int i = 0; i < GNP; ++i)
+            *reinterpret_cast<uint4*>(sA + sw128_off(i * GRP + grl, s * FN + gc * 8, FU_BLK)) = qv[i];
           continue;
         }
-        float4 x[4], y[4];
+        float4 x[GNP], y[GNP];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
+        for (int i = 0; i < GNP; ++i) {
           x[i] = make_float4(0.f, 0.f, 0.f, 0.f);
           y[i] = x[i];
           if (ridx[i] >= 0) {
@@ -435,13 +447,13 @@ rowmlp_tc_bwd_fused_kernel(const __grid_constant__ KParams p, const __grid_const
           }
         }
 #pragma unroll
-        for (int i = 0; i < 4; ++i)
-          *reinterpret_cast<uint4*>(sA + sw128_off(i * 32 + grl, s * FN + gc * 8, FU_BLK)) =
+        for (int i = 0; i < GNP; ++i)
+          *reinterpret_cast<uint4*>(sA + sw128_off(i * GRP + grl, s * FN + gc * 8, FU_BLK)) =
               make_uint4(pack_bf16(x[i].x, x[i].y), pack_bf16(x[i].z, x[i].w),
                          pack_bf16(y[i].x, y[i].y), pack_bf16(y[i].z, y[i].w));
       }
       fence_async_smem();
-      fu_sync(ctx);
+      fu_sync<FU_CT>(ctx);
       if (ltid == 0) {
         tc_fence_after();
         const uint32_t a0 = smem_u32(sA), w0 = smem_u32(sW1);
@@ -460,10 +472,11 @@ rowmlp_tc_bwd_fused_kernel(const __grid_constant__ KParams p, const __grid_const
         }
         float4 va[4], vb[4];
         float gs[4];
-        dm_load(ltid, va, vb, gs);
-        dm_store(ltid, va, vb, gs);
-        dm_load(ltid + 4 * FU_CT, va, vb, gs);
-        dm_store(ltid + 4 * FU_CT, va, vb, gs);
+#pragma unroll
+        for (int base = 0; base < TM * 16; base += 4 * FU_CT) {
+          dm_load(ltid + base, va, vb, gs);
+          dm_store(ltid + base, va, vb, gs);
+        }
       }
       {
         int tile_n, b_n;
@@ -475,8 +488,8 @@ rowmlp_tc_bwd_fused_kernel(const __grid_constant__ KParams p, const __grid_const
 
       // ---------------- epilogue 1: a = SiLU(H + b1) -> bf16 tile
 #pragma unroll
-      for (int ci = 0; ci < 2; ++ci) {
-        const int c0 = hf * 32 + ci * 16;
+      for (int ci = 0; ci < CH; ++ci) {
+        const int c0 = hf * CPT + ci * 16;
         float v[16];
         tmem_ld16(tH + lane_addr + (uint32_t)c0, v);
 #pragma unroll
@@ -491,7 +504,7 @@ rowmlp_tc_bwd_fused_kernel(const __grid_constant__ KParams p, const __grid_const
       }
       fence_async_smem();
       tc_fence_before();
-      fu_sync(ctx);
+      fu_sync<FU_CT>(ctx);
 
       // ---------------- GEMM 2: Y = a . W2^T
       if (ltid == 0) {
@@ -508,10 +521,10 @@ rowmlp_tc_bwd_fused_kernel(const __grid_constant__ KParams p, const __grid_const
 
       // ---------------- epilogue 2: LayerNorm backward -> dY (bf16, in place of dOut)
       {
-        float y[32];  // this thread's 32 columns of row r: y -> y_hat
+        float y[CPT];  // this thread's CPT columns of row r: y -> y_hat
 #pragma unroll
-        for (int ci = 0; ci < 2; ++ci) {
-          const int c0 = hf * 32 + ci * 16;
+        for (int ci = 0; ci < CH; ++ci) {
+          const int c0 = hf * CPT + ci * 16;
           float v[16];
           tmem_ld16(tY + lane_addr + (uint32_t)c0, v);
 #pragma unroll
@@ -519,30 +532,39 @@ rowmlp_tc_bwd_fused_kernel(const __grid_constant__ KParams p, const __grid_const
         }
         float rstd = 1.f, m1 = 0.f, m2 = 0.f;
         if (has_ln) {
-          // mean / variance of the 64-wide row from the two 32-column halves with ONE
-          // exchange: each half sends (sum, sum of squared deviations from its own mean),
-          // combined with the pairwise update of Chan et al. (two-pass accuracy)
+          // mean / variance of the 64-wide row from its NH column groups with ONE exchange:
+          // every group sends (sum, sum of squared deviations from its OWN mean); combined
+          // with the parallel-variance update of Chan et al. (two-pass accuracy)
           float s = 0.f;
 #pragma unroll
-          for (int j = 0; j < 32; ++j) s += y[j];
-          const float mh = s * (1.0f / 32);
+          for (int j = 0; j < CPT; ++j) s += y[j];
+          const float mh = s * (1.0f / CPT);
           float qh = 0.f;
 #pragma unroll
-          for (int j = 0; j < 32; ++j) qh += (y[j] - mh) * (y[j] - mh);
-          sLnx[(0 * TM + r) * 2 + hf] = s;
-          sLnx[(1 * TM + r) * 2 + hf] = qh;
-          fu_sync(ctx);
-          const float so = sLnx[(0 * TM + r) * 2 + (hf ^ 1)], qo = sLnx[(1 * TM + r) * 2 + (hf ^ 1)];
-          const float mean = (s + so) * (1.0f / FN);
-          const float dlt = (s - so) * (1.0f / 32);  // difference of the half means
-          const float var = (qh + qo + dlt * dlt * 16.0f) * (1.0f / FN);
-          rstd = rsqrtf(var + LN_EPS);
+          for (int j = 0; j < CPT; ++j) qh += (y[j] - mh) * (y[j] - mh);
+          sLnx[(0 * TM + r) * NH + hf] = s;
+          sLnx[(1 * TM + r) * NH + hf] = qh;
+          fu_sync<FU_CT>(ctx);
+          float sg[NH], stot = 0.f, qtot = 0.f;
 #pragma unroll
-          for (int j = 0; j < 32; ++j) y[j] -= mean;
+          for (int h = 0; h < NH; ++h) {
+            sg[h] = sLnx[(0 * TM + r) * NH + h];
+            stot += sg[h];
+            qtot += sLnx[(1 * TM + r) * NH + h];
+          }
+          const float mean = stot * (1.0f / FN);
+#pragma unroll
+          for (int h = 0; h < NH; ++h) {
+            const float dlt = sg[h] * (1.0f / CPT) - mean;  // group mean - row mean
+            qtot += dlt * dlt * (float)CPT;
+          }
+          rstd = rsqrtf(qtot * (1.0f / FN) + LN_EPS);
+#pragma unroll
+          for (int j = 0; j < CPT; ++j) y[j] -= mean;
           float s1 = 0.f, s2 = 0.f;
 #pragma unroll
-          for (int ci = 0; ci < 2; ++ci) {
-            const int c0 = hf * 32 + ci * 16;
+          for (int ci = 0; ci < CH; ++ci) {
+            const int c0 = hf * CPT + ci * 16;
             float dmv[16], pv[16];
             unpack8(*reinterpret_cast<const uint4*>(sD + sw128_off(r, c0, FU_BLK)), dmv);
             unpack8(*reinterpret_cast<const uint4*>(sD + sw128_off(r, c0 + 8, FU_BLK)), dmv + 8);
@@ -557,15 +579,19 @@ rowmlp_tc_bwd_fused_kernel(const __grid_constant__ KParams p, const __grid_const
             }
             acc_dg[ci] += warp_colsum16(pv, lane);
           }
-          sLnx[(2 * TM + r) * 2 + hf] = s1;
-          sLnx[(3 * TM + r) * 2 + hf] = s2;
-          fu_sync(ctx);
-          m1 = (sLnx[(2 * TM + r) * 2] + sLnx[(2 * TM + r) * 2 + 1]) * (1.0f / FN);
-          m2 = (sLnx[(3 * TM + r) * 2] + sLnx[(3 * TM + r) * 2 + 1]) * (1.0f / FN);
+          sLnx[(2 * TM + r) * NH + hf] = s1;
+          sLnx[(3 * TM + r) * NH + hf] = s2;
+          fu_sync<FU_CT>(ctx);
+#pragma unroll
+          for (int h = 0; h < NH; ++h) {
+            m1 += sLnx[(2 * TM + r) * NH + h];
+            m2 += sLnx[(3 * TM + r) * NH + h];
+          }
+          m1 *= 1.0f / FN, m2 *= 1.0f / FN;
         }
 #pragma unroll
-        for (int ci = 0; ci < 2; ++ci) {
-          const int c0 = hf * 32 + ci * 16;
+        for (int ci = 0; ci < CH; ++ci) {
+          const int c0 = hf * CPT + ci * 16;
           float v[16];
           unpack8(*reinterpret_cast<const uint4*>(sD + sw128_off(r, c0, FU_BLK)), v);
           unpack8(*reinterpret_cast<const uint4*>(sD + sw128_off(r, c0 + 8, FU_BLK)), v + 8);
@@ -588,7 +614,7 @@ rowmlp_tc_bwd_fused_kernel(const __grid_constant__ KParams p, const __grid_const
       }
       fence_async_smem();
       tc_fence_before();
-      fu_sync(ctx);
+      fu_sync<FU_CT>(ctx);
 
       // ---------------- GEMM 3: dA = dY . W2 (into Y's columns), and dW2^T += a^T . dY
       if (ltid == 0) {
@@ -609,8 +635,8 @@ rowmlp_tc_bwd_fused_kernel(const __grid_constant__ KParams p, const __grid_const
 
       // ---------------- epilogue 3: dH = dA * SiLU'(H + b1) -> bf16 tile
 #pragma unroll
-      for (int ci = 0; ci < 2; ++ci) {
-        const int c0 = hf * 32 + ci * 16;
+      for (int ci = 0; ci < CH; ++ci) {
+        const int c0 = hf * CPT + ci * 16;
         float v[16], h[16];
         tmem_ld16(tY + lane_addr + (uint32_t)c0, v);
         tmem_ld16(tH + lane_addr + (uint32_t)c0, h);
@@ -627,7 +653,7 @@ rowmlp_tc_bwd_fused_kernel(const __grid_constant__ KParams p, const __grid_const
       }
       fence_async_smem();
       tc_fence_before();
-      fu_sync(ctx);
+      fu_sync<FU_CT>(ctx);
 
       // ---------------- dW1^T += z^T . dH, then GEMM 4 + epilogue 4: dZ = dH . W1, one
       // source (64 columns) at a time, double-buffered in the recycled H / Y columns
@@ -666,15 +692,15 @@ rowmlp_tc_bwd_fused_kernel(const __grid_constant__ KParams p, const __grid_const
           const bool fres = fdst && (kb == p.d.residual_src) && p.g0;
           const bool reduce = fdst && kb == p.reduce_src;
           const bool partial = fdst && kb == p.sp_src;
-          const bool scat = fdst && p.d_src_idx[kb] != nullptr;  // rows staged in ix[6 + kb]
-          float4 e[8];
+          const bool scat = fdst && kb == 0 && p.d_src_idx[0] != nullptr;  // rows staged in IX_SCAT
+          float4 e[ONP];
           if (fres) {  // residual rows requested early
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              const int row = (ltid >> 4) + 16 * i;
+            for (int i = 0; i < ONP; ++i) {
+              const int row = (ltid >> 4) + ORP * i;
               e[i] = make_float4(0.f, 0.f, 0.f, 0.f);
               if (row < cnt) {
-                const size_t gr = (size_t)b * p.d.rows + ix[3 * TM + row];
+                const size_t gr = (size_t)b * p.d.rows + ix[IX_G0 + row];
                 e[i] = __ldg(reinterpret_cast<const float4*>(p.g0 + gr * FN) + (ltid & 15));
               }
             }
@@ -685,8 +711,8 @@ rowmlp_tc_bwd_fused_kernel(const __grid_constant__ KParams p, const __grid_const
           // double-buffered staging: block kb+1 is written while stragglers still read kb
           float* stgk = stg + (kb & 1) * (TM * FN);
 #pragma unroll
-          for (int ci = 0; ci < 2; ++ci) {
-            const int c0 = hf * 32 + ci * 16;
+          for (int ci = 0; ci < CH; ++ci) {
+            const int c0 = hf * CPT + ci * 16;
             float v[16];
             tmem_ld16(((kb & 1) ? tY : tH) + lane_addr + (uint32_t)c0, v);
 #pragma unroll
@@ -695,14 +721,14 @@ rowmlp_tc_bwd_fused_kernel(const __grid_constant__ KParams p, const __grid_const
                   make_float4(v[j4 * 4], v[j4 * 4 + 1], v[j4 * 4 + 2], v[j4 * 4 + 3]);
           }
           tc_fence_before();
-          fu_sync(ctx);
+          fu_sync<FU_CT>(ctx);
           if (reduce) {
             // receiver-aligned tile: sum the gradient rows of each segment (fixed order)
-            const int seg_lo = ix[9 * TM], seg_hi = ix[9 * TM + 1];
+            const int seg_lo = ix[IX_SEG], seg_hi = ix[IX_SEG + 1];
             const bool staged = seg_hi - seg_lo <= TM;
-            const int* sp = ix + 9 * TM + 2 - seg_lo;
+            const int* sp = ix + IX_SEG + 2 - seg_lo;
             float* ro = fdst + (size_t)b * p.d.agg.n_seg * FN + (ltid & 15) * 4;
-            for (int seg = seg_lo + (ltid >> 4); seg < seg_hi; seg += 16) {
+            for (int seg = seg_lo + (ltid >> 4); seg < seg_hi; seg += ORP) {
               const int r0 = staged ? sp[seg] : __ldg(p.d.agg.seg_ptr + seg) - row0;
               const int r1 = staged ? sp[seg + 1] : __ldg(p.d.agg.seg_ptr + seg + 1) - row0;
               float4* o4 = reinterpret_cast<float4*>(ro + (size_t)seg * FN);
@@ -723,12 +749,12 @@ rowmlp_tc_bwd_fused_kernel(const __grid_constant__ KParams p, const __grid_const
             const int q_lo = ix[FU_SPO], q_hi = ix[FU_SPO + 1];
             const int* rp = ix + FU_SPO + 2 - q_lo;
             float* po = fdst + (size_t)b * p.n_sp * FN + (ltid & 15) * 4;
-            for (int qi = q_lo + (ltid >> 4); qi < q_hi; qi += 16) {
+            for (int qi = q_lo + (ltid >> 4); qi < q_hi; qi += ORP) {
               const int j0 = rp[qi], j1 = rp[qi + 1];
               float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
               for (int j = j0; j < j1; ++j) {
                 const float4 v =
-                    *reinterpret_cast<const float4*>(stgk + stg_idx(ix[7 * TM + j], ltid & 15, FN));
+                    *reinterpret_cast<const float4*>(stgk + stg_idx(ix[IX_SPR + j], ltid & 15, FN));
                 acc.x += v.x, acc.y += v.y, acc.z += v.z, acc.w += v.w;
               }
               *reinterpret_cast<float4*>(po + (size_t)qi * FN) = acc;
@@ -736,12 +762,12 @@ rowmlp_tc_bwd_fused_kernel(const __grid_constant__ KParams p, const __grid_const
           } else if (fdst) {
             float* o = fdst + (ltid & 15) * 4;
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              const int row = (ltid >> 4) + 16 * i;
+            for (int i = 0; i < ONP; ++i) {
+              const int row = (ltid >> 4) + ORP * i;
               if (row < cnt) {
                 float4 v = *reinterpret_cast<const float4*>(stgk + stg_idx(row, ltid & 15, FN));
                 if (fres) v.x += e[i].x, v.y += e[i].y, v.z += e[i].z, v.w += e[i].w;
-                size_t orow = scat ? (size_t)b * p.d.rows + ix[(6 + kb) * TM + row] : grow0 + row;
+                size_t orow = scat ? (size_t)b * p.d.rows + ix[IX_SCAT + row] : grow0 + row;
                 if (bsum && kb == 0) {
                   // batch-shared source: ONE gradient row per input row, accumulated over this
                   // context's consecutive batch items by the thread that wrote it before
@@ -770,7 +796,7 @@ rowmlp_tc_bwd_fused_kernel(const __grid_constant__ KParams p, const __grid_const
       }
       pb ^= 1;
       tc_fence_before();
-      fu_sync(ctx);  // tiles / staging free for the next tile
+      fu_sync<FU_CT>(ctx);  // tiles / staging free for the next tile
     }
   }
 
@@ -780,8 +806,9 @@ rowmlp_tc_bwd_fused_kernel(const __grid_constant__ KParams p, const __grid_const
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  float* sRed = reinterpret_cast<float*>(sm);  // [16 warps][4][32], context 0's dead z tile
-  {
+  float* sRed = reinterpret_cast<float*>(sm);  // [warps][4][32], context 0's dead z tile
+  constexpr int NWARP = FU_NT / 32;
+  if (warp < 16) {
     const ParamLayout lay = p.lay;
     float* dst = g.partial + (size_t)blockIdx.x * g.p_total;
     const int q = warp & 3, cq = warp >> 2, r = q * 32 + lane;  // 16 warps: 4 column quarters
@@ -813,16 +840,18 @@ rowmlp_tc_bwd_fused_kernel(const __grid_constant__ KParams p, const __grid_const
       for (int j = 0; j < 16; ++j)
         if (c0 + j < dout) dst[lay.off_w2() + (size_t)(c0 + j) * FN + h] = two ? v[j] + w[j] : v[j];
     }
+  }
+  {
     if (lane < 16) {
 #pragma unroll
-      for (int i = 0; i < 2; ++i) {
+      for (int i = 0; i < CH; ++i) {
         sRed[(warp * 4 + 0) * 32 + i * 16 + lane] = acc_db1[i];
         sRed[(warp * 4 + 1) * 32 + i * 16 + lane] = acc_db2[i];
         sRed[(warp * 4 + 2) * 32 + i * 16 + lane] = acc_dg[i];
       }
     }
-    // fp32 dOut column sums: [32 row groups (context, ltid >> 4)][64 columns]
-    float* sDm = sRed + 16 * 4 * 32;
+    // fp32 dOut column sums: [row groups (tid >> 4)][64 columns]
+    float* sDm = sRed + NWARP * 4 * 32;
 #pragma unroll
     for (int e = 0; e < 4; ++e) sDm[(tid >> 4) * 64 + (tid & 15) * 4 + e] = acc_dm[e];
   }
@@ -831,17 +860,18 @@ rowmlp_tc_bwd_fused_kernel(const __grid_constant__ KParams p, const __grid_const
   if (tid < 4 * FN) {
     const int which = tid >> 6, col = tid & 63;
     if ((which < 2 || has_ln) && (which == 0 || col < dout)) {
-      const int h = col >> 5, cc = col & 31;
+      const int h = col / CPT, cc = col % CPT;  // column group and column inside it
       float s = 0.f;
       // dLN beta, and db2 without LayerNorm (dY == dOut): the fp32 sums of the dOut rows
       if (which == 3 || (which == 1 && !has_ln)) {
-        const float* sDm = sRed + 16 * 4 * 32;
-        for (int gI = 0; gI < 32; ++gI) s += sDm[gI * 64 + col];
+        const float* sDm = sRed + NWARP * 4 * 32;
+        for (int gI = 0; gI < FU_NT / 16; ++gI) s += sDm[gI * 64 + col];
       } else {
 #pragma unroll
         for (int c = 0; c < FU_CTX; ++c)
 #pragma unroll
-          for (int qq = 0; qq < 4; ++qq) s += sRed[((c * 8 + h * 4 + qq) * 4 + which) * 32 + cc];
+          for (int qq = 0; qq < 4; ++qq)
+            s += sRed[((c * 4 * NH + h * 4 + qq) * 4 + which) * 32 + cc];
       }
       g.vec_partial[(size_t)blockIdx.x * g.vec_len + which * FN + col] = s;
     }
@@ -879,17 +909,27 @@ int tc_bwd_fused_grid_bsum(const tc::BGeo& g) {
   return grid > 148 ? 148 : grid;
 }
 
+template <bool FG, int NH>
+static int launch_fused(const KParams& p, const tc::BGeo& g, int grid, cudaStream_t st) {
+  NLAM_CUDA(ensure_dyn_smem((const void*)tc::rowmlp_tc_bwd_fused_kernel<FG, NH>, (int)tc::fu_smem(NH)));
+  NLAM_CUDA(launch_k(tc::rowmlp_tc_bwd_fused_kernel<FG, NH>, grid, tc::FuCfg<NH>::NT, tc::fu_smem(NH),
+                     st, p, g));
+  return 0;
+}
+
 int tc_rowmlp_bwd_fused(const KParams& p, const tc::BGeo& g, cudaStream_t st) {
-  NLAM_CUDA(ensure_dyn_smem((const void*)tc::rowmlp_tc_bwd_fused_kernel<true>, (int)tc::FU_SMEM));
-  NLAM_CUDA(ensure_dyn_smem((const void*)tc::rowmlp_tc_bwd_fused_kernel<false>, (int)tc::FU_SMEM));
-  static_assert(tc::FU_SMEM <= 232448, "fused backward: shared memory");
-  if (tc_bwd_fused_kind(p) == 2)
-    NLAM_CUDA(launch_k(tc::rowmlp_tc_bwd_fused_kernel<true>,
-                       p.src0_batch_sum ? tc_bwd_fused_grid_bsum(g) : tc_bwd_fused_grid(g), tc::FU_NT,
-                       tc::FU_SMEM, st, p, g));
-  else
-    NLAM_CUDA(launch_k(tc::rowmlp_tc_bwd_fused_kernel<false>, tc_bwd_fused_grid(g), tc::FU_NT,
-                       tc::FU_SMEM, st, p, g));
+  // threads per tile row: 2 (16 warps per SM, 128 registers).  4 (32 warps, 64 registers,
+  // ~0.4 KB of spills) is kept as an option: measured 3.55 vs 3.30 ms per GraphLAM step
+  const bool nh4 = option_bwd_nh() == 4;
+  int rc;
+  if (tc_bwd_fused_kind(p) == 2) {
+    const int grid = p.src0_batch_sum ? tc_bwd_fused_grid_bsum(g) : tc_bwd_fused_grid(g);
+    rc = nh4 ? launch_fused<true, 4>(p, g, grid, st) : launch_fused<true, 2>(p, g, grid, st);
+  } else {
+    const int grid = tc_bwd_fused_grid(g);
+    rc = nh4 ? launch_fused<false, 4>(p, g, grid, st) : launch_fused<false, 2>(p, g, grid, st);
+  }
+  if (rc) return rc;
   NLAM_CUDA(cudaGetLastError());
   count_launch();
   return 0;

@@ -434,3 +434,33 @@ def test_on_chip_backward_reductions(dev, bf16, B, update, expand_edges, same):
         assert torch.equal(a, b)  # deterministic
     for a, b in zip(res[0], res[2]):
         _close(a, b, "on-chip reductions vs per-edge rows", tol=1e-5)
+
+
+def test_fused_backward_four_threads_per_row(dev, bf16):
+    """The NH = 4 instantiation of the fused backward kernel (32 warps per SM) computes what
+    the default NH = 2 one computes (LayerNorm statistics are combined from 4 instead of 2
+    partial sums: 1e-5)."""
+    from neural_lam_b200 import lib, ops
+    from neural_lam_b200.interaction_net import InteractionNet
+    g = torch.Generator().manual_seed(3)
+    M, n, d, B = 30000, 2500, 64, 2
+    ei = torch.stack((torch.randint(0, n, (M,), generator=g), torch.randint(0, n, (M,), generator=g)))
+    ei[0, 0], ei[1, 0], ei[0, 1], ei[1, 1] = 0, 0, n - 1, n - 1
+    torch.manual_seed(3)
+    net = InteractionNet(ei, d).to(dev)
+    x0 = torch.randn(B, n, d, generator=g).to(dev)
+    e0 = torch.randn(B, M, d, generator=g).to(dev)
+    res = []
+    l = lib.load()
+    for nh in (2, 4):
+        l.nlam_set_option(b"bwd_nh", nh)
+        try:
+            x, e = x0.clone().requires_grad_(), e0.clone().requires_grad_()
+            h, f = net(x, x, e)
+            inet_loss((h, f)).backward()
+            res.append([x.grad.clone(), e.grad.clone()] + [p.grad.clone() for p in net.parameters()])
+            net.zero_grad()
+        finally:
+            l.nlam_set_option(b"bwd_nh", 2)
+    for a, b in zip(*res):
+        _close(a, b, "NH=4 vs NH=2", tol=1e-5)

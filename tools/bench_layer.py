@@ -17,7 +17,7 @@ from neural_lam_b200.interaction_net import InteractionNet  # noqa: E402
 
 def main():
     which = sys.argv[1] if len(sys.argv) > 1 else "m2g"
-    red = {"sp": 1, "bs": 1}
+    red = {"sp": 1, "bs": 0}
     for kv in sys.argv[2:]:
         k, v = kv.split("=")
         if k in red:
