@@ -1,7 +1,7 @@
-"""GPU parity at BASELINE.json's full sizes (configs 3-5): the CUDA path (fp32
-mode) against the CPU oracle run in the same process on the same seeded
-inputs; bf16 mode checked on loss/prediction.  One sample per case keeps the
-oracle to seconds."""
+"""GPU parity at BASELINE.json's full sizes (configs 3-5, config 4 with its ar_steps = 3): the CUDA
+path (fp32 mode) against the CPU oracle run in the same process on the same seeded
+inputs; bf16 mode checked on the loss and the whole gradient (2e-2).  One sample per case
+keeps the oracle to seconds (config 5 with 2 of its processor layers)."""
 import tempfile
 
 import pytest
@@ -14,8 +14,8 @@ CASES = {
     "multiscale_d128": dict(model="graph_lam", scale=1, graph=dict(n_max_levels=None, hierarchical=False),
                             args=dict(hidden_dim=128, processor_layers=8, graph="multiscale"), ar=1),
     # config 4: HiLAM hierarchical 4-level mesh, hidden_dim 64, AR rollout
-    "hilam_d64_ar2": dict(model="hi_lam", scale=1, graph=dict(n_max_levels=None, hierarchical=True),
-                          args=dict(hidden_dim=64, processor_layers=4, graph="hierarchical"), ar=2),
+    "hilam_d64_ar3": dict(model="hi_lam", scale=1, graph=dict(n_max_levels=None, hierarchical=True),
+                          args=dict(hidden_dim=64, processor_layers=4, graph="hierarchical"), ar=3),
     # config 5: HiLAMParallel on the 4x domain (536 x 476 grid), hidden_dim 128
     "hilam_parallel_4x_d128": dict(model="hi_lam_parallel", scale=2,
                                    graph=dict(n_max_levels=None, hierarchical=True),
@@ -76,6 +76,7 @@ def test_full_size_train_step_vs_oracle(dev, name):
         assert abs(loss16.item() - loss_ref.item()) <= 2e-2 * abs(loss_ref.item())
         got = torch.cat([q.grad.reshape(-1) for _, q in model.named_parameters()])
         want = torch.cat([p.grad.reshape(-1) for _, p in ref.named_parameters()])
-        assert _rel_l2(got, want) <= 5e-2
+        # whole gradient within the stated 2e-2 (measured 5e-3 .. 9e-3, profiles/parity_bf16_r2.txt)
+        assert _rel_l2(got, want) <= 2e-2, f"bf16 whole-gradient relative L2 {_rel_l2(got, want):.3e}"
     finally:
         ops.set_precision("fp32")
