@@ -29,6 +29,8 @@ static std::atomic<int> g_bwd_fused{env_or("NLAM_BWD_FUSED", -1)};
 static std::atomic<int> g_pdl{env_or("NLAM_PDL", 1)};
 static std::atomic<int> g_tma{env_or("NLAM_TMA", 0)};
 int option_tma() { return g_tma.load(); }
+static std::atomic<int> g_wide128{env_or("NLAM_WIDE128", 1)};
+int option_wide128() { return g_wide128.load(); }
 static std::atomic<int> g_bwd_nh{env_or("NLAM_BWD_NH", 2)};
 int option_bwd_nh() { return g_bwd_nh.load(); }
 int option_fwd_mc() { return g_fwd_mc.load(); }
@@ -64,6 +66,7 @@ extern "C" int nlam_set_option(const char* name, int value) {
   if (name && !strcmp(name, "pdl")) return nlam::g_pdl.store(value), 0;
   if (name && !strcmp(name, "tma")) return nlam::g_tma.store(value), 0;
   if (name && !strcmp(name, "bwd_nh")) return nlam::g_bwd_nh.store(value), 0;
+  if (name && !strcmp(name, "wide128")) return nlam::g_wide128.store(value), 0;
   nlam::set_error("nlam_set_option: unknown option");
   return 1;
 }

@@ -25,10 +25,14 @@ namespace nlam {
 namespace tc {
 
 
-template <int FN, bool FG>
-__global__ void __launch_bounds__(NT, 2)
+// TNT = threads per CTA: 256 (two CTAs per SM at d <= 64), or 512 for d = 128, where shared
+// memory allows one CTA per SM only -- 16 warps instead of 8, and 32 instead of 64 columns of
+// a row per thread (NG = TNT / 128 column groups per row).
+template <int FN, bool FG, int TNT>
+__global__ void __launch_bounds__(TNT, TNT == 256 ? 2 : 1)
 rowmlp_tc_fwd_kernel(const __grid_constant__ KParams p, const __grid_constant__ Geo g) {
   constexpr bool F = FN > 0;  // square fast path: sizes are compile-time constants
+  constexpr int NG = TNT / 128;  // column groups (threads) per tile row
   const int n1 = F ? FN : g.n1, n2 = F ? FN : g.n2, k2 = F ? FN : g.k2;
   extern __shared__ __align__(1024) uint8_t sm[];
   if (smem_u32(sm) & 1023u) __trap();  // SWIZZLE_128B operands need 1024-byte alignment
@@ -61,9 +65,9 @@ rowmlp_tc_fwd_kernel(const __grid_constant__ KParams p, const __grid_constant__ 
   uint32_t ph0 = 0, ph1 = 0;
   int loaded_chunk = -1;
   if (p.d.n_chunks == 1) {  // single weight set: staged while the previous kernel drains
-    stage_weight(p.d.w.w1, dh, p.k_total, n1, g.k1, sW1);
-    stage_weight(p.d.w.w2, dout, dh, n2, k2, sW2);
-    stage_params(p.d, 0, n1, n2, sPar);
+    stage_weight<TNT>(p.d.w.w1, dh, p.k_total, n1, g.k1, sW1);
+    stage_weight<TNT>(p.d.w.w2, dout, dh, n2, k2, sW2);
+    stage_params<TNT>(p.d, 0, n1, n2, sPar);
     loaded_chunk = 0;
   }
   pdl_wait();
@@ -77,9 +81,18 @@ rowmlp_tc_fwd_kernel(const __grid_constant__ KParams p, const __grid_constant__ 
 
   // epilogue ownership: TMEM lane quarter q, row r, column half hf
   const int q = warp & 3, hf = warp >> 2, r = q * 32 + lane;
-  const int cp1 = n1 >= 32 ? n1 / 2 : n1, cp2 = n2 >= 32 ? n2 / 2 : n2;
-  const bool act1 = n1 >= 32 || hf == 0, act2 = n2 >= 32 || hf == 0;
-  const bool split2 = n2 >= 32;
+  // columns per thread: a row is split over the NG column groups when every group gets at
+  // least one 16-column chunk, else group 0 takes the whole row
+  const int cp1 = n1 >= 16 * NG ? n1 / NG : n1, cp2 = n2 >= 16 * NG ? n2 / NG : n2;
+  const bool act1 = n1 >= 16 * NG || hf == 0, act2 = n2 >= 16 * NG || hf == 0;
+  const bool split2 = n2 >= 16 * NG;
+  auto lnx_sum = [&](const float* base) {  // sum of the row's partial values (NG or 1)
+    float s = base[0];
+    if (split2)
+#pragma unroll
+      for (int h = 1; h < NG; ++h) s += base[h];
+    return s;
+  };
   const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
 
   // pipelined gather (64-wide sources): row indices are fetched one tile ahead
@@ -88,7 +101,7 @@ rowmlp_tc_fwd_kernel(const __grid_constant__ KParams p, const __grid_constant__ 
   if (PIPE && (int)blockIdx.x < g.total_tiles) {
     int r0, c0, ch0;
     tile_range<TM>(p.d, blockIdx.x / p.d.batch, r0, c0, ch0);
-    load_row_idx<NT>(p, r0, c0, tid, nidx);
+    load_row_idx<TNT>(p, r0, c0, tid, nidx);
   }
 
   for (int t = blockIdx.x; t < g.total_tiles; t += gridDim.x) {
@@ -97,20 +110,20 @@ rowmlp_tc_fwd_kernel(const __grid_constant__ KParams p, const __grid_constant__ 
     tile_range<TM>(p.d, tile, row0, cnt, chunk);
 
     if (chunk != loaded_chunk) {  // (re)load the weight set of this chunk
-      stage_weight(p.d.w.w1 + (size_t)chunk * dh * p.k_total, dh, p.k_total, n1, g.k1, sW1);
-      stage_weight(p.d.w.w2 + (size_t)chunk * dout * dh, dout, dh, n2, k2, sW2);
-      stage_params(p.d, chunk, n1, n2, sPar);
+      stage_weight<TNT>(p.d.w.w1 + (size_t)chunk * dh * p.k_total, dh, p.k_total, n1, g.k1, sW1);
+      stage_weight<TNT>(p.d.w.w2 + (size_t)chunk * dout * dh, dout, dh, n2, k2, sW2);
+      stage_params<TNT>(p.d, chunk, n1, n2, sPar);
       loaded_chunk = chunk;
     }
 
     // ---------------- gather: fp32 rows -> bf16 A operand
     if (PIPE) {
       const int cidx[NLAM_MAX_SRC] = {nidx[0], nidx[1], nidx[2]};
-      gather_rows_pipe<64, NT>(p, b, cidx, sA, tid);
+      gather_rows_pipe<64, TNT>(p, b, cidx, sA, tid);
     } else if (F && FG) {
-      gather_rows_fast<(F ? FN : 64)>(p, b, row0, cnt, 0, p.d.n_src, sA);
+      gather_rows_fast<(F ? FN : 64), TNT>(p, b, row0, cnt, 0, p.d.n_src, sA);
     } else {
-      gather_rows(p, b, row0, cnt, 0, g.k1, sA);
+      gather_rows<TNT>(p, b, row0, cnt, 0, g.k1, sA);
     }
     {  // next tile: row indices (pipelined gather) and L2 prefetch of its input rows
       const int tn = t + gridDim.x;
@@ -118,7 +131,7 @@ rowmlp_tc_fwd_kernel(const __grid_constant__ KParams p, const __grid_constant__ 
         int r0n, cn, chn;
         tile_range<TM>(p.d, tn / p.d.batch, r0n, cn, chn);
         if (PIPE) {
-          load_row_idx<NT>(p, r0n, cn, tid, nidx);
+          load_row_idx<TNT>(p, r0n, cn, tid, nidx);
           prefetch_rows_of(p, tn % p.d.batch, nidx, (tid & 31) < 16);
         } else {
           prefetch_sources(p, tn % p.d.batch, r0n, cn);
@@ -198,9 +211,9 @@ rowmlp_tc_fwd_kernel(const __grid_constant__ KParams p, const __grid_constant__ 
           for (int j = 0; j < 16; ++j)
             if (F || c0 + j < dout) s += v[j] + sB2[c0 + j];
         }
-      sLnx[(0 * TM + r) * 2 + hf] = s;
+      sLnx[(0 * TM + r) * NG + hf] = s;
       __syncthreads();
-      mean = (sLnx[(0 * TM + r) * 2] + (split2 ? sLnx[(0 * TM + r) * 2 + 1] : 0.f)) / (float)dout;
+      mean = lnx_sum(&sLnx[(0 * TM + r) * NG]) / (float)dout;
       float qq = 0.f;
       if (act2)
         for (int cc = 0; cc < cp2; cc += 16) {
@@ -214,10 +227,9 @@ rowmlp_tc_fwd_kernel(const __grid_constant__ KParams p, const __grid_constant__ 
               qq += dl * dl;
             }
         }
-      sLnx[(1 * TM + r) * 2 + hf] = qq;
+      sLnx[(1 * TM + r) * NG + hf] = qq;
       __syncthreads();
-      const float var =
-          (sLnx[(1 * TM + r) * 2] + (split2 ? sLnx[(1 * TM + r) * 2 + 1] : 0.f)) / (float)dout;
+      const float var = lnx_sum(&sLnx[(1 * TM + r) * NG]) / (float)dout;
       rstd = rsqrtf(var + LN_EPS);
     }
     if (act2)
@@ -250,7 +262,7 @@ rowmlp_tc_fwd_kernel(const __grid_constant__ KParams p, const __grid_constant__ 
       const bool need0 = res || out2;
       if (p.out_vec_ok && (!need0 || p.vec_ok[0])) {
         const int w4 = dout >> 2;
-        for (int u = tid; u < cnt * w4; u += NT) {
+        for (int u = tid; u < cnt * w4; u += TNT) {
           const int row = u / w4, c4 = u % w4;
           float4 v = *reinterpret_cast<const float4*>(stg + (size_t)row * g.stg_ld + c4 * 4);
           float4 e = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -275,7 +287,7 @@ rowmlp_tc_fwd_kernel(const __grid_constant__ KParams p, const __grid_constant__ 
                 make_uint2(pack_bf16(v.x + e.x, v.y + e.y), pack_bf16(v.z + e.z, v.w + e.w));
         }
       } else {
-        for (int u = tid; u < cnt * dout; u += NT) {
+        for (int u = tid; u < cnt * dout; u += TNT) {
           const int row = u / dout, c = u % dout;
           float v = stg[(size_t)row * g.stg_ld + c];
           float e = 0.f;
@@ -294,7 +306,7 @@ rowmlp_tc_fwd_kernel(const __grid_constant__ KParams p, const __grid_constant__ 
       const int seg_lo = __ldg(p.d.agg.tile_seg + tile), seg_hi = __ldg(p.d.agg.tile_seg + tile + 1);
       const int w4 = dout >> 2;
       float* ao = p.d.agg.out + (size_t)b * p.d.agg.n_seg * dout;
-      for (int u = tid; u < (seg_hi - seg_lo) * w4; u += NT) {
+      for (int u = tid; u < (seg_hi - seg_lo) * w4; u += TNT) {
         const int seg = seg_lo + u / w4, c4 = u % w4;
         const int r0 = __ldg(p.d.agg.seg_ptr + seg) - row0, r1 = __ldg(p.d.agg.seg_ptr + seg + 1) - row0;
         float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -345,7 +357,7 @@ int make_geo(const KParams& p, Geo& g) {
   const uint32_t a_bytes = (uint32_t)g.kb1 * TM * 128u;
   const uint32_t a2_bytes = (uint32_t)g.kb2 * TM * 128u;
   const uint32_t stg_bytes = (uint32_t)TM * g.stg_ld * 4u;
-  const uint32_t lnx_bytes = 2u * TM * 2u * 4u;
+  const uint32_t lnx_bytes = 2u * TM * 4u * 4u;  // [2][TM][<= 4 column groups]
   uint32_t r0 = a_bytes > a2_bytes ? a_bytes : a2_bytes;
   if (stg_bytes + lnx_bytes > r0) r0 = stg_bytes + lnx_bytes;
   auto al = [](uint32_t x) { return (x + 1023u) & ~1023u; };
@@ -389,18 +401,21 @@ int tc_rowmlp_fwd(const nlam_rowmlp& d, cudaStream_t st) {
   int grid = 148 * per_sm;
   if (grid > g.total_tiles) grid = g.total_tiles;
   const int fn = tc::fast_n(p);
-  auto launch = [&](auto kern, int&) -> int {
+  auto launch = [&](auto kern, int threads) -> int {
     NLAM_CUDA(ensure_dyn_smem((const void*)kern, (int)g.smem_bytes));
-    NLAM_CUDA(launch_k(kern, grid, tc::NT, g.smem_bytes, st, p, g));
+    NLAM_CUDA(launch_k(kern, grid, threads, g.smem_bytes, st, p, g));
     return 0;
   };
   const bool fg = tc::fast_gather(p);
-  static int ms[5] = {0, 0, 0, 0, 0};
-  int rc = fn == 64    ? (fg ? launch(tc::rowmlp_tc_fwd_kernel<64, true>, ms[1])
-                             : launch(tc::rowmlp_tc_fwd_kernel<64, false>, ms[2]))
-           : fn == 128 ? (fg ? launch(tc::rowmlp_tc_fwd_kernel<128, true>, ms[3])
-                             : launch(tc::rowmlp_tc_fwd_kernel<128, false>, ms[4]))
-                       : launch(tc::rowmlp_tc_fwd_kernel<0, false>, ms[0]);
+  // d = 128: one CTA per SM (shared memory) -> 512 threads (option "wide128" = 0: 256)
+  const bool wide = option_wide128() != 0 && per_sm == 1;
+  int rc = fn == 64    ? (fg ? launch(tc::rowmlp_tc_fwd_kernel<64, true, 256>, 256)
+                             : launch(tc::rowmlp_tc_fwd_kernel<64, false, 256>, 256))
+           : fn == 128 ? (wide ? (fg ? launch(tc::rowmlp_tc_fwd_kernel<128, true, 512>, 512)
+                                     : launch(tc::rowmlp_tc_fwd_kernel<128, false, 512>, 512))
+                               : (fg ? launch(tc::rowmlp_tc_fwd_kernel<128, true, 256>, 256)
+                                     : launch(tc::rowmlp_tc_fwd_kernel<128, false, 256>, 256)))
+                       : launch(tc::rowmlp_tc_fwd_kernel<0, false, 256>, 256);
   if (rc) return rc;
   NLAM_CUDA(cudaGetLastError());
   count_launch();

@@ -38,11 +38,13 @@ __device__ __forceinline__ float silu_fast(float x) {
 }
 
 // W[n][k] fp32 (nn.Linear layout) -> bf16 K-major SW128 blocks of [n_pad rows][64]
+// (TNT = threads of the calling CTA, here and in the helpers below)
+template <int TNT = NT>
 __device__ __forceinline__ void stage_weight(const float* __restrict__ W, int n_real, int k_real, int n_pad,
                              int k_pad, uint8_t* dst) {
   const int nch = k_pad >> 3;
   const uint32_t blk = (uint32_t)n_pad * 128u;
-  for (int u = threadIdx.x; u < n_pad * nch; u += NT) {
+  for (int u = threadIdx.x; u < n_pad * nch; u += TNT) {
     const int n = u / nch, c = u % nch, k0 = c * 8;
     float v[8];
 #pragma unroll
@@ -67,17 +69,18 @@ __device__ __forceinline__ float silu_grad_fast(float x) {
 // GU with all row-index loads, then all 128-bit data loads, issued before any
 // use, so that GU*2 loads per thread are in flight (memory-level parallelism).
 constexpr int GU = 6;
+template <int TNT = NT>
 __device__ __forceinline__ void gather_rows(const KParams& p, int b, int row0, int cnt,
                                             int k_begin, int k_end, uint8_t* sA) {
   const int nch = (k_end - k_begin) >> 3;
   const int total = TM * nch;
   const uint32_t a_blk = TM * 128u;
-  for (int base = threadIdx.x; base < total; base += NT * GU) {
+  for (int base = threadIdx.x; base < total; base += TNT * GU) {
     const float* rp[GU];
     int rowv[GU], k0v[GU], nval[GU];  // nval: 8 = vector path, 0 = zero, <0 = -(scalar count)
 #pragma unroll
     for (int j = 0; j < GU; ++j) {
-      const int u = base + j * NT;
+      const int u = base + j * TNT;
       rp[j] = nullptr;
       nval[j] = 0;
       rowv[j] = 0, k0v[j] = k_begin;
@@ -144,11 +147,11 @@ __device__ __forceinline__ void gather_rows(const KParams& p, int b, int row0, i
 // 16-byte aligned.  Thread (rl, c) handles chunk c of rows rl, rl+RPP, ...: no
 // divisions, all row indices then all 2*NP 128-bit loads issued before use.
 // Source s lands at A-tile columns [(s - s_begin)*FN, ...).
-template <int FN>
+template <int FN, int TNT = NT>
 __device__ __forceinline__ void gather_rows_fast(const KParams& p, int b, int row0, int cnt,
                                                  int s_begin, int s_end, uint8_t* sA) {
   constexpr int CPR = FN / 8;    // 16-byte bf16 chunks per source row
-  constexpr int RPP = NT / CPR;  // rows per pass
+  constexpr int RPP = TNT / CPR;  // rows per pass
   constexpr int NP = TM / RPP;   // passes
   const int c = threadIdx.x % CPR, rl = threadIdx.x / CPR;
   const uint32_t a_blk = TM * 128u;
@@ -363,10 +366,11 @@ inline bool fast_gather(const KParams& p) {
 }
 
 // b1[n1] | b2[n2] | gamma[n2] | beta[n2], zero / identity padded
+template <int TNT = NT>
 __device__ __forceinline__ void stage_params(const nlam_rowmlp& d, int chunk, int n1, int n2,
                                              float* sPar, int n_vec = 3) {
   const int dh = d.d_hidden, dout = d.d_out;
-  for (int i = threadIdx.x; i < n1 + n_vec * n2; i += NT) {
+  for (int i = threadIdx.x; i < n1 + n_vec * n2; i += TNT) {
     float v = 0.f;
     if (i < n1) {
       if (i < dh) v = __ldg(d.w.b1 + (size_t)chunk * dh + i);

@@ -32,10 +32,14 @@ namespace tc {
 
 constexpr int MAXCH = 4;  // 16-column chunks per thread (n <= 128, two column halves)
 
-template <int FN, bool FG>
-__global__ void __launch_bounds__(NT, 2)
+// TNT = threads per CTA (256, or 512 at d = 128 where one CTA fits per SM; see rowmlp_tc.cu)
+template <int FN, bool FG, int TNT>
+__global__ void __launch_bounds__(TNT, TNT == 256 ? 2 : 1)
 rowmlp_tc_dgrad_kernel(const __grid_constant__ KParams p, const __grid_constant__ BGeo g) {
   constexpr bool F = FN > 0;  // square fast path: sizes are compile-time constants
+  constexpr int NG = TNT / 128;   // column groups (threads) per tile row
+  constexpr int ZC = 64 / NG;     // columns of a 64-wide dZ block per thread
+  constexpr int ORP = TNT / 16, ONP = TM / ORP;  // output phases: rows per pass, passes
   const int n1 = F ? FN : g.n1, n2 = F ? FN : g.n2;
   const int k2 = F ? FN : g.k2, ko = F ? FN : g.ko;
   const int kb2 = F ? FN / 64 : g.kb2, kbo = F ? FN / 64 : g.kbo;
@@ -48,7 +52,7 @@ rowmlp_tc_dgrad_kernel(const __grid_constant__ KParams p, const __grid_constant_
   uint8_t* sW2 = sm + g.off_w2;
   float* sPar = reinterpret_cast<float*>(sm + g.off_par);
   float* sLnx = reinterpret_cast<float*>(sm + g.off_lnx);  // [TM][2]
-  float* sRed = reinterpret_cast<float*>(sm + g.off_t);    // [8 warps][4][64], aliases sT
+  float* sRed = reinterpret_cast<float*>(sm + g.off_t);    // [warps][4][64], aliases sT
   uint64_t* bars = reinterpret_cast<uint64_t*>(sm + g.off_bar);  // [0] main, [1],[2] dZ
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3);
 
@@ -78,12 +82,35 @@ rowmlp_tc_dgrad_kernel(const __grid_constant__ KParams p, const __grid_constant_
   const uint32_t idesc4 = make_idesc_bf16(TM, 64, 0, 1);    // B = W1 block viewed MN-major
 
   const int q = warp & 3, hf = warp >> 2, r = q * 32 + lane;
-  const int cp1 = n1 >= 32 ? n1 / 2 : n1, cp2 = n2 >= 32 ? n2 / 2 : n2;
-  const bool act1 = n1 >= 32 || hf == 0, act2 = n2 >= 32 || hf == 0;
-  const bool split2 = n2 >= 32;
+  const int cp1 = n1 >= 16 * NG ? n1 / NG : n1, cp2 = n2 >= 16 * NG ? n2 / NG : n2;
+  const bool act1 = n1 >= 16 * NG || hf == 0, act2 = n2 >= 16 * NG || hf == 0;
+  const bool split2 = n2 >= 16 * NG;
   const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
   const float* sB2 = sPar + n1;
   const float* sG = sB2 + n2;
+  // Sum over the column groups of row r of one per-thread partial value, returned to every
+  // thread of the row; fixed order (deterministic).  The exchange array is [TM][2] floats
+  // (shared memory is full at d = 128): four groups go through it in two steps, pair sums
+  // (0+1), (2+3) first.  Ends with a barrier: the array may be reused right away.
+  auto row_allsum = [&](float v) {
+    float tot;
+    if (NG == 4 && split2) {
+      if (hf & 1) sLnx[r * 2 + (hf >> 1)] = v;
+      __syncthreads();
+      float pair = v;
+      if (!(hf & 1)) pair = v + sLnx[r * 2 + (hf >> 1)];
+      __syncthreads();
+      if (!(hf & 1)) sLnx[r * 2 + (hf >> 1)] = pair;
+      __syncthreads();
+      tot = sLnx[r * 2] + sLnx[r * 2 + 1];
+    } else {
+      sLnx[r * 2 + hf] = v;
+      __syncthreads();
+      tot = sLnx[r * 2] + (split2 ? sLnx[r * 2 + 1] : 0.f);
+    }
+    __syncthreads();
+    return tot;
+  };
 
   // per-CTA column-sum accumulators (lane l owns column c0 + (l & 15) of each chunk)
   float acc_db1[MAXCH], acc_db2[MAXCH], acc_dg[MAXCH], acc_dbt[MAXCH];
@@ -105,7 +132,7 @@ rowmlp_tc_dgrad_kernel(const __grid_constant__ KParams p, const __grid_constant_
     __syncthreads();
     float* dst = g.vec_partial + ((size_t)blockIdx.x * p.d.n_chunks + chunk) * g.vec_len;
     // which: 0 db1 (n1 cols), 1 db2, 2 dgamma, 3 dbeta (n2 cols)
-    for (int e = tid; e < 4 * 128; e += NT) {
+    for (int e = tid; e < 4 * 128; e += TNT) {
       const int which = e >> 7, col = e & 127;
       const int n = which == 0 ? n1 : n2, cp = which == 0 ? cp1 : cp2;
       const int real = which == 0 ? dh : dout;
@@ -130,7 +157,7 @@ rowmlp_tc_dgrad_kernel(const __grid_constant__ KParams p, const __grid_constant_
   if (PIPE && (int)blockIdx.x < g.total_tiles) {
     int r0, c0, ch0;
     tile_range<TM>(p.d, blockIdx.x / p.d.batch, r0, c0, ch0);
-    load_row_idx<NT>(p, r0, c0, tid, nidx);
+    load_row_idx<TNT>(p, r0, c0, tid, nidx);
   }
 
   for (int t = blockIdx.x; t < g.total_tiles; t += gridDim.x) {
@@ -141,9 +168,9 @@ rowmlp_tc_dgrad_kernel(const __grid_constant__ KParams p, const __grid_constant_
 
     if (chunk != loaded_chunk) {
       if (loaded_chunk >= 0) flush_colsums(loaded_chunk);
-      stage_weight(p.d.w.w1 + (size_t)chunk * dh * p.k_total, dh, p.k_total, n1, g.k1, sW1);
-      stage_weight(p.d.w.w2 + (size_t)chunk * dout * dh, dout, dh, n2, k2, sW2);
-      stage_params(p.d, chunk, n1, n2, sPar, 2);  // beta is not needed backward
+      stage_weight<TNT>(p.d.w.w1 + (size_t)chunk * dh * p.k_total, dh, p.k_total, n1, g.k1, sW1);
+      stage_weight<TNT>(p.d.w.w2 + (size_t)chunk * dout * dh, dout, dh, n2, k2, sW2);
+      stage_params<TNT>(p.d, chunk, n1, n2, sPar, 2);  // beta is not needed backward
       loaded_chunk = chunk;
     }
 
@@ -158,7 +185,7 @@ rowmlp_tc_dgrad_kernel(const __grid_constant__ KParams p, const __grid_constant_
       int colv[4];
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        const int u = base + j * NT;
+        const int u = base + j * TNT;
         g0p[j] = g1p[j] = nullptr;
         gs[j] = 1.f;
         rowv[j] = -1, c4v[j] = 0, colv[j] = 0;
@@ -219,12 +246,12 @@ rowmlp_tc_dgrad_kernel(const __grid_constant__ KParams p, const __grid_constant_
       const int k_begin = kb0 * 64, k_end = min(g.k1, kbe * 64);
       if (PIPE) {  // one round covers all (<= 3) sources
         const int cidx[NLAM_MAX_SRC] = {nidx[0], nidx[1], nidx[2]};
-        gather_rows_pipe<64, NT>(p, b, cidx, sA, tid);
+        gather_rows_pipe<64, TNT>(p, b, cidx, sA, tid);
       } else if (F && FG) {
-        gather_rows_fast<(F ? FN : 64)>(p, b, row0, cnt, k_begin / (F ? FN : 64),
-                                        k_end / (F ? FN : 64), sA);
+        gather_rows_fast<(F ? FN : 64), TNT>(p, b, row0, cnt, k_begin / (F ? FN : 64),
+                                             k_end / (F ? FN : 64), sA);
       } else {
-        gather_rows(p, b, row0, cnt, k_begin, k_end, sA);
+        gather_rows<TNT>(p, b, row0, cnt, k_begin, k_end, sA);
       }
       fence_async_smem();
       __syncthreads();
@@ -249,7 +276,7 @@ rowmlp_tc_dgrad_kernel(const __grid_constant__ KParams p, const __grid_constant_
     // ---------------- dOut rows -> fp32 staging (coalesced), rows >= cnt are zero.
     // The first batch of loads was issued before waiting for GEMM 1 (dm0_*).
     dm_store(dm0_a, dm0_b, dm0_s, dm0_row, dm0_c4);
-    for (int base = tid + NT * 4; base < TM * (n2 >> 2); base += NT * 4) {
+    for (int base = tid + TNT * 4; base < TM * (n2 >> 2); base += TNT * 4) {
       float4 va[4], vb[4];
       float gs[4];
       int rowv[4], c4v[4];
@@ -264,7 +291,7 @@ rowmlp_tc_dgrad_kernel(const __grid_constant__ KParams p, const __grid_constant_
         const int bn = tn % p.d.batch;
         tile_range<TM>(p.d, tn / p.d.batch, r0n, cn, chn);
         if (PIPE) {
-          load_row_idx<NT>(p, r0n, cn, tid, nidx);
+          load_row_idx<TNT>(p, r0n, cn, tid, nidx);
           prefetch_rows_of(p, bn, nidx, (tid & 31) < 16);
         } else {
           prefetch_sources(p, bn, r0n, cn);
@@ -310,7 +337,7 @@ rowmlp_tc_dgrad_kernel(const __grid_constant__ KParams p, const __grid_constant_
       }
       umma_commit(&bars[0]);
     }
-    copy_tile_out(sT, g.a_img + (size_t)t * kb2 * a_blk, kb2 * a_blk);
+    copy_tile_out<TNT>(sT, g.a_img + (size_t)t * kb2 * a_blk, kb2 * a_blk);
     mbar_wait(&bars[0], ph_main);
     ph_main ^= 1;
     tc_fence_after();
@@ -328,10 +355,7 @@ rowmlp_tc_dgrad_kernel(const __grid_constant__ KParams p, const __grid_constant_
           for (int j = 0; j < 16; ++j)
             if (F || c0 + j < dout) s += v[j] + sB2[c0 + j];
         }
-      sLnx[r * 2 + hf] = s;
-      __syncthreads();
-      mean = (sLnx[r * 2] + (split2 ? sLnx[r * 2 + 1] : 0.f)) / (float)dout;
-      __syncthreads();
+      mean = row_allsum(s) / (float)dout;
       float qq = 0.f;
       if (act2)
         for (int cc = 0; cc < cp2; cc += 16) {
@@ -345,10 +369,7 @@ rowmlp_tc_dgrad_kernel(const __grid_constant__ KParams p, const __grid_constant_
               qq += dl * dl;
             }
         }
-      sLnx[r * 2 + hf] = qq;
-      __syncthreads();
-      rstd = rsqrtf((sLnx[r * 2] + (split2 ? sLnx[r * 2 + 1] : 0.f)) / (float)dout + LN_EPS);
-      __syncthreads();
+      rstd = rsqrtf(row_allsum(qq) / (float)dout + LN_EPS);
       // row means of dyhat and dyhat*yhat; column sums for dgamma / dbeta
       float s1 = 0.f, s2 = 0.f;
       if (act2) {
@@ -381,13 +402,8 @@ rowmlp_tc_dgrad_kernel(const __grid_constant__ KParams p, const __grid_constant_
           }
         }
       }
-      sLnx[r * 2 + hf] = s1;
-      __syncthreads();
-      m1 = (sLnx[r * 2] + (split2 ? sLnx[r * 2 + 1] : 0.f)) / (float)dout;
-      __syncthreads();
-      sLnx[r * 2 + hf] = s2;
-      __syncthreads();
-      m2 = (sLnx[r * 2] + (split2 ? sLnx[r * 2 + 1] : 0.f)) / (float)dout;
+      m1 = row_allsum(s1) / (float)dout;
+      m2 = row_allsum(s2) / (float)dout;
     }
     __syncthreads();  // every thread is done copying the a tile out of sT
     if (act2) {
@@ -444,7 +460,7 @@ rowmlp_tc_dgrad_kernel(const __grid_constant__ KParams p, const __grid_constant_
       }
       umma_commit(&bars[0]);
     }
-    copy_tile_out(sT, g.dy_img + (size_t)t * kbo * a_blk, kbo * a_blk);
+    copy_tile_out<TNT>(sT, g.dy_img + (size_t)t * kbo * a_blk, kbo * a_blk);
     mbar_wait(&bars[0], ph_main);
     ph_main ^= 1;
     tc_fence_after();
@@ -478,7 +494,7 @@ rowmlp_tc_dgrad_kernel(const __grid_constant__ KParams p, const __grid_constant_
     fence_async_smem();
     tc_fence_before();
     __syncthreads();
-    copy_tile_out(sT, g.dh_img + (size_t)t * kb2 * a_blk, kb2 * a_blk);
+    copy_tile_out<TNT>(sT, g.dh_img + (size_t)t * kb2 * a_blk, kb2 * a_blk);
 
     // ---------------- GEMM 4 + epilogue 4: dZ = dH . W1, 64 input columns at a time
     if (g.need_dz) {
@@ -502,19 +518,19 @@ rowmlp_tc_dgrad_kernel(const __grid_constant__ KParams p, const __grid_constant_
         float* fdst = (F && FG) ? p.d_src[fs] : nullptr;
         const bool fres = F && FG && fdst && (fs == p.d.residual_src) && p.g0;
         const int32_t* didx = fdst ? p.d_src_idx[fs] : nullptr;
-        int orow_i[8];
+        int orow_i[ONP];
         if (didx && fs != p.reduce_src) {  // scatter targets, fetched while the MMA runs
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const int row = (tid >> 4) + 16 * i;
+          for (int i = 0; i < ONP; ++i) {
+            const int row = (tid >> 4) + ORP * i;
             orow_i[i] = row < cnt ? __ldg(didx + row0 + row) : 0;
           }
         }
-        float4 e[8];
+        float4 e[ONP];
         if (fres) {  // residual rows requested early: they arrive while the MMA runs
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const int row = (tid >> 4) + 16 * i;
+          for (int i = 0; i < ONP; ++i) {
+            const int row = (tid >> 4) + ORP * i;
             e[i] = make_float4(0.f, 0.f, 0.f, 0.f);
             if (row < cnt) {
               const size_t gr = p.g0_idx ? (size_t)b * p.d.rows + __ldg(p.g0_idx + row0 + row)
@@ -527,8 +543,8 @@ rowmlp_tc_dgrad_kernel(const __grid_constant__ KParams p, const __grid_constant_
         ph_z ^= 1u << (kb & 1);
         tc_fence_after();
         // TMEM -> swizzled fp32 staging [128][64]
-        for (int cc = 0; cc < 32; cc += 16) {
-          const int c0 = hf * 32 + cc;
+        for (int cc = 0; cc < ZC; cc += 16) {
+          const int c0 = hf * ZC + cc;
           float v[16];
           tmem_ld16(tZ + (uint32_t)(kb & 1) * 64u + lane_addr + (uint32_t)c0, v);
 #pragma unroll
@@ -544,7 +560,7 @@ rowmlp_tc_dgrad_kernel(const __grid_constant__ KParams p, const __grid_constant_
             const int seg_lo = __ldg(p.d.agg.tile_seg + tile);
             const int seg_hi = __ldg(p.d.agg.tile_seg + tile + 1);
             float* ro = fdst + (size_t)b * p.d.agg.n_seg * FNN + col0 + (tid & 15) * 4;
-            for (int seg = seg_lo + (tid >> 4); seg < seg_hi; seg += 16) {
+            for (int seg = seg_lo + (tid >> 4); seg < seg_hi; seg += ORP) {
               const int r0 = __ldg(p.d.agg.seg_ptr + seg) - row0;
               const int r1 = __ldg(p.d.agg.seg_ptr + seg + 1) - row0;
               float4* o4 = reinterpret_cast<float4*>(ro + (size_t)seg * FNN);
@@ -561,8 +577,8 @@ rowmlp_tc_dgrad_kernel(const __grid_constant__ KParams p, const __grid_constant_
           } else if (fdst) {
             float* o = fdst + col0 + (tid & 15) * 4;
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              const int row = (tid >> 4) + 16 * i;
+            for (int i = 0; i < ONP; ++i) {
+              const int row = (tid >> 4) + ORP * i;
               if (row < cnt) {
                 float4 v = *reinterpret_cast<const float4*>(stg + stg_idx(row, tid & 15, 64));
                 if (fres) v.x += e[i].x, v.y += e[i].y, v.z += e[i].z, v.w += e[i].w;
@@ -573,7 +589,7 @@ rowmlp_tc_dgrad_kernel(const __grid_constant__ KParams p, const __grid_constant_
           }
         } else {
           // generic: coalesced per-source row stores
-          for (int u = tid; u < cnt * 16; u += NT) {
+          for (int u = tid; u < cnt * 16; u += TNT) {
             const int row = u >> 4, c4 = u & 15, kg = kb * 64 + c4 * 4;
             if (kg >= p.k_total) continue;
             int s = 0;
@@ -623,8 +639,8 @@ rowmlp_tc_dgrad_kernel(const __grid_constant__ KParams p, const __grid_constant_
 }
 
 // -------------------------------------------------------------------- wgrad
-template <int FN, bool FG>
-__global__ void __launch_bounds__(NT, 2)
+template <int FN, bool FG, int TNT>
+__global__ void __launch_bounds__(TNT, TNT == 256 ? 2 : 1)
 rowmlp_tc_wgrad_kernel(const __grid_constant__ KParams p, const __grid_constant__ BGeo g) {
   constexpr bool F = FN > 0;
   const int n1 = F ? FN : g.n1, n2 = F ? FN : g.n2;
@@ -666,8 +682,9 @@ rowmlp_tc_wgrad_kernel(const __grid_constant__ KParams p, const __grid_constant_
     tc_fence_after();
     const ParamLayout lay = p.lay;
     float* dst = g.partial + ((size_t)blockIdx.x * p.d.n_chunks + chunk) * g.p_total;
-    const int cpa = n1 >= 32 ? n1 / 2 : n1;
-    if (n1 >= 32 || hf == 0) {
+    constexpr int NG = TNT / 128;
+    const int cpa = n1 >= 16 * NG ? n1 / NG : n1;
+    if (n1 >= 16 * NG || hf == 0) {
       for (int mc = 0; mc < g.w_mchunks; ++mc) {
         const int kg = mc * 128 + r;  // input column
         for (int cc = 0; cc < cpa; cc += 16) {
@@ -685,8 +702,8 @@ rowmlp_tc_wgrad_kernel(const __grid_constant__ KParams p, const __grid_constant_
         }
       }
     }
-    const int cpb = n2 >= 32 ? n2 / 2 : n2;
-    if (n2 >= 32 || hf == 0) {
+    const int cpb = n2 >= 16 * NG ? n2 / NG : n2;
+    if (n2 >= 16 * NG || hf == 0) {
       for (int cc = 0; cc < cpb; cc += 16) {
         const int c0 = hf * cpb + cc;
         float v[16];
@@ -710,7 +727,7 @@ rowmlp_tc_wgrad_kernel(const __grid_constant__ KParams p, const __grid_constant_
   if (PIPE && (int)blockIdx.x < g.total_tiles) {
     int r0, c0, ch0;
     tile_range<TM>(p.d, blockIdx.x / p.d.batch, r0, c0, ch0);
-    load_row_idx<NT>(p, r0, c0, tid, nidx);
+    load_row_idx<TNT>(p, r0, c0, tid, nidx);
   }
 
   for (int t = blockIdx.x; t < g.total_tiles; t += gridDim.x) {
@@ -724,32 +741,32 @@ rowmlp_tc_wgrad_kernel(const __grid_constant__ KParams p, const __grid_constant_
     }
     if (PIPE) {
       const int cidx[NLAM_MAX_SRC] = {nidx[0], nidx[1], nidx[2]};
-      gather_rows_pipe<64, NT>(p, b, cidx, sZ, tid);
+      gather_rows_pipe<64, TNT>(p, b, cidx, sZ, tid);
     } else if (F && FG) {
-      gather_rows_fast<(F ? FN : 64)>(p, b, row0, cnt, 0, p.d.n_src, sZ);
+      gather_rows_fast<(F ? FN : 64), TNT>(p, b, row0, cnt, 0, p.d.n_src, sZ);
     } else {
-      gather_rows(p, b, row0, cnt, 0, g.k1, sZ);
+      gather_rows<TNT>(p, b, row0, cnt, 0, g.k1, sZ);
     }
-    copy_tile_in(g.a_img + (size_t)t * kb2 * a_blk, sAi, kb2 * a_blk);
-    copy_tile_in(g.dy_img + (size_t)t * kbo * a_blk, sDY, kbo * a_blk);
-    copy_tile_in(g.dh_img + (size_t)t * kb2 * a_blk, sDH, kb2 * a_blk);
+    copy_tile_in<TNT>(g.a_img + (size_t)t * kb2 * a_blk, sAi, kb2 * a_blk);
+    copy_tile_in<TNT>(g.dy_img + (size_t)t * kbo * a_blk, sDY, kbo * a_blk);
+    copy_tile_in<TNT>(g.dh_img + (size_t)t * kb2 * a_blk, sDH, kb2 * a_blk);
     {  // L2 prefetch of the next tile's rows and bf16 tile images
       const int tn = t + gridDim.x;
       if (tn < g.total_tiles) {
         int r0n, cn, chn;
         tile_range<TM>(p.d, tn / p.d.batch, r0n, cn, chn);
         if (PIPE) {
-          load_row_idx<NT>(p, r0n, cn, tid, nidx);
+          load_row_idx<TNT>(p, r0n, cn, tid, nidx);
           prefetch_rows_of(p, tn % p.d.batch, nidx, (tid & 31) < 16);
         } else {
           prefetch_sources(p, tn % p.d.batch, r0n, cn);
         }
         const int li = (int)(kb2 * a_blk) >> 7, lo = (int)(kbo * a_blk) >> 7;
-        for (int u = tid; u < li; u += NT) {
+        for (int u = tid; u < li; u += TNT) {
           prefetch_l2(g.a_img + (size_t)tn * kb2 * a_blk + (size_t)u * 128);
           prefetch_l2(g.dh_img + (size_t)tn * kb2 * a_blk + (size_t)u * 128);
         }
-        for (int u = tid; u < lo; u += NT)
+        for (int u = tid; u < lo; u += TNT)
           prefetch_l2(g.dy_img + (size_t)tn * kbo * a_blk + (size_t)u * 128);
       }
     }
@@ -811,7 +828,7 @@ static int make_bgeo(const KParams& p, BGeo& g) {
   g.off_w1 = o, o += al((uint32_t)g.kb1 * g.n1 * 128u);
   g.off_w2 = o, o += al((uint32_t)g.kb2 * g.n2 * 128u);
   g.off_par = o, o += (uint32_t)(g.n1 + 2 * g.n2) * 4u;
-  g.off_lnx = o, o += (uint32_t)TM * 2u * 4u;
+  g.off_lnx = o, o += (uint32_t)TM * 2u * 4u;  // [TM][2] (see row_allsum)
   g.off_bar = o, o += 64;
   g.smem_bytes = o;
   g.tiles_per_batch = n_tiles_of(d, TM);
@@ -997,15 +1014,18 @@ int tc_rowmlp_bwd(const nlam_rowmlp_bwd& bd, cudaStream_t st) {
                                                                     g.vec_len - ws.partial), st));
   const int fn = tc::fast_n(p);
   const int gd = ws.d_slots, gw = ws.w_slots;
-  auto launch = [&](auto kern, int&, int grid, uint32_t smem) -> int {
+  auto launch = [&](auto kern, int threads, int grid, uint32_t smem) -> int {
     NLAM_CUDA(ensure_dyn_smem((const void*)kern, (int)smem));
-    kern<<<grid, tc::NT, smem, st>>>(p, g);
+    kern<<<grid, threads, smem, st>>>(p, g);
     NLAM_CUDA(cudaGetLastError());
     count_launch();
     return 0;
   };
   const bool fg = tc::fast_gather(p);
-  static int md[5] = {0, 0, 0, 0, 0}, mw[5] = {0, 0, 0, 0, 0};
+  // d = 128: one CTA per SM anyway (shared memory) -> 512 threads = 16 warps, 32 columns of a
+  // row per thread like the d = 64 kernels (option "wide128" = 0: 256 threads)
+  const bool wide = fn == 128 && option_wide128() != 0 && g.smem_bytes > 113 * 1024 &&
+                    g.w_smem_bytes > 113 * 1024;
   int rc;
   const int mask = (bd.stage_mask & 7) ? bd.stage_mask : (7 | (bd.stage_mask & 8));
   const bool dmc = tc::use_dgrad_mc(p, g);
@@ -1016,23 +1036,27 @@ int tc_rowmlp_bwd(const nlam_rowmlp_bwd& bd, cudaStream_t st) {
                                 bd.params_accumulate, g.vec_partial, ws.d_slots, g.vec_len, p.lay,
                                 st, (mask & 8) != 0);
   }
-#define NLAM_BWD_PAIR(FNV, FGV, I)                                                          \
+#define NLAM_BWD_PAIR(FNV, FGV, TN)                                                         \
   rc = 0;                                                                                   \
   if (mask & 1)                                                                             \
     rc = dmc ? tc_rowmlp_dgrad_mc(p, g, st)                                                 \
-             : launch(tc::rowmlp_tc_dgrad_kernel<FNV, FGV>, md[I], gd, g.smem_bytes);       \
+             : launch(tc::rowmlp_tc_dgrad_kernel<FNV, FGV, TN>, TN, gd, g.smem_bytes);      \
   if (!rc && (mask & 2))                                                                    \
-    rc = launch(tc::rowmlp_tc_wgrad_kernel<FNV, FGV>, mw[I], gw, g.w_smem_bytes);
+    rc = launch(tc::rowmlp_tc_wgrad_kernel<FNV, FGV, TN>, TN, gw, g.w_smem_bytes);
   if (fn == 64 && fg) {
-    NLAM_BWD_PAIR(64, true, 1)
+    NLAM_BWD_PAIR(64, true, 256)
   } else if (fn == 64) {
-    NLAM_BWD_PAIR(64, false, 2)
+    NLAM_BWD_PAIR(64, false, 256)
+  } else if (fn == 128 && fg && wide) {
+    NLAM_BWD_PAIR(128, true, 512)
   } else if (fn == 128 && fg) {
-    NLAM_BWD_PAIR(128, true, 3)
+    NLAM_BWD_PAIR(128, true, 256)
+  } else if (fn == 128 && wide) {
+    NLAM_BWD_PAIR(128, false, 512)
   } else if (fn == 128) {
-    NLAM_BWD_PAIR(128, false, 4)
+    NLAM_BWD_PAIR(128, false, 256)
   } else {
-    NLAM_BWD_PAIR(0, false, 0)
+    NLAM_BWD_PAIR(0, false, 256)
   }
 #undef NLAM_BWD_PAIR
   if (rc) return rc;

@@ -71,27 +71,29 @@ __device__ __forceinline__ uint64_t make_desc_mn_sw128(uint32_t smem_addr, uint3
          (64ull << 32) | (1ull << 46) | (2ull << 61);
 }
 
+template <int TNT = NT>
 __device__ __forceinline__ void copy_tile_out(const uint8_t* s, uint8_t* g, int bytes) {
   const uint4* src = reinterpret_cast<const uint4*>(s);
   uint4* dst = reinterpret_cast<uint4*>(g);
-  for (int i = threadIdx.x; i < bytes / 16; i += 4 * NT) {  // 16 KB blocks
-    uint4 v[4];
+  for (int i = threadIdx.x; i < bytes / 16; i += 2 * TNT) {  // 16 KB blocks (1024 chunks)
+    uint4 v[2];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) v[j] = src[i + j * NT];
+    for (int j = 0; j < 2; ++j) v[j] = src[i + j * TNT];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) dst[i + j * NT] = v[j];
+    for (int j = 0; j < 2; ++j) dst[i + j * TNT] = v[j];
   }
 }
+template <int TNT = NT>
 __device__ __forceinline__ void copy_tile_in(const uint8_t* g, uint8_t* s, int bytes) {
-  // 16 KB blocks: 4 independent 128-bit loads per thread in flight
+  // 16 KB blocks (1024 chunks): 2 independent 128-bit loads per thread in flight
   const uint4* src = reinterpret_cast<const uint4*>(g);
   uint4* dst = reinterpret_cast<uint4*>(s);
-  for (int i = threadIdx.x; i < bytes / 16; i += 4 * NT) {
-    uint4 v[4];
+  for (int i = threadIdx.x; i < bytes / 16; i += 2 * TNT) {
+    uint4 v[2];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) v[j] = __ldg(src + i + j * NT);
+    for (int j = 0; j < 2; ++j) v[j] = __ldg(src + i + j * TNT);
 #pragma unroll
-    for (int j = 0; j < 4; ++j) dst[i + j * NT] = v[j];
+    for (int j = 0; j < 2; ++j) dst[i + j * TNT] = v[j];
   }
 }
 
