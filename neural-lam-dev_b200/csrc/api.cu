@@ -31,6 +31,8 @@ static std::atomic<int> g_tma{env_or("NLAM_TMA", 0)};
 int option_tma() { return g_tma.load(); }
 static std::atomic<int> g_wide128{env_or("NLAM_WIDE128", 1)};
 int option_wide128() { return g_wide128.load(); }
+static std::atomic<int> g_rb128{env_or("NLAM_RB128", 4)};
+int option_rb128() { return g_rb128.load(); }
 static std::atomic<int> g_bwd_nh{env_or("NLAM_BWD_NH", 2)};
 int option_bwd_nh() { return g_bwd_nh.load(); }
 int option_fwd_mc() { return g_fwd_mc.load(); }

@@ -20,6 +20,7 @@ int option_tma();        // 1: TMA row-gather kernels where every operand has a 
                          // measured 5 % slower than the register gather of the shadows)
 int option_bwd_nh();     // fused backward: threads per tile row, 2 (default) or 4 (measured 7 % slower)
 int option_wide128();    // 1 (default): d = 128 kernels with 512 threads per CTA
+int option_rb128();      // z blocks per gather round of the d = 128 input-gradient kernel: 4 (default) or 2
 int option_pdl();        // 1: launch with programmatic dependent launch (see launch_k)  // -1 / 1: fused dgrad + wgrad kernel where eligible, 0: two kernels
 
 // Programmatic dependent launch: a kernel launched with this attribute may start while

@@ -813,7 +813,9 @@ static int make_bgeo(const KParams& p, BGeo& g) {
   g.k2 = (d.d_hidden + 15) / 16 * 16;
   g.ko = (d.d_out + 15) / 16 * 16;
   g.kb1 = (g.k1 + 63) / 64, g.kb2 = (g.n1 + 63) / 64, g.kbo = (g.n2 + 63) / 64;
-  g.rb = (fast_n(p) == 128 && fast_gather(p)) ? 2 : 3;  // fast gather works on whole sources
+  // z blocks gathered per GEMM-1 round (the fast gather works on whole sources: 2 blocks each
+  // at d = 128, where the 64 KB staging region takes two sources per round)
+  g.rb = (fast_n(p) == 128 && fast_gather(p)) ? (option_rb128() == 2 ? 2 : 4) : 3;
   g.cY = g.n1, g.cZ = g.n1 + g.nmax;
   g.tmem_cols = pow2_cols(g.cZ + 128);
   const uint32_t blk = TM * 128u;
