@@ -415,7 +415,9 @@ int tc_rowmlp_fwd(const nlam_rowmlp& d, cudaStream_t st) {
                                      : launch(tc::rowmlp_tc_fwd_kernel<128, false, 512>, 512))
                                : (fg ? launch(tc::rowmlp_tc_fwd_kernel<128, true, 256>, 256)
                                      : launch(tc::rowmlp_tc_fwd_kernel<128, false, 256>, 256)))
-                       : launch(tc::rowmlp_tc_fwd_kernel<0, false, 256>, 256);
+           // non-square shapes with a 128-wide hidden layer (d = 128 output map): one CTA per SM too
+           : (wide && g.n1 == 128) ? launch(tc::rowmlp_tc_fwd_kernel<0, false, 512>, 512)
+                                   : launch(tc::rowmlp_tc_fwd_kernel<0, false, 256>, 256);
   if (rc) return rc;
   NLAM_CUDA(cudaGetLastError());
   count_launch();

@@ -1026,8 +1026,8 @@ int tc_rowmlp_bwd(const nlam_rowmlp_bwd& bd, cudaStream_t st) {
   const bool fg = tc::fast_gather(p);
   // d = 128: one CTA per SM anyway (shared memory) -> 512 threads = 16 warps, 32 columns of a
   // row per thread like the d = 64 kernels (option "wide128" = 0: 256 threads)
-  const bool wide = fn == 128 && option_wide128() != 0 && g.smem_bytes > 113 * 1024 &&
-                    g.w_smem_bytes > 113 * 1024;
+  const bool wide = (fn == 128 || (fn == 0 && g.n1 == 128)) && option_wide128() != 0 &&
+                    g.smem_bytes > 113 * 1024 && g.w_smem_bytes > 113 * 1024;
   int rc;
   const int mask = (bd.stage_mask & 7) ? bd.stage_mask : (7 | (bd.stage_mask & 8));
   const bool dmc = tc::use_dgrad_mc(p, g);
@@ -1057,6 +1057,8 @@ int tc_rowmlp_bwd(const nlam_rowmlp_bwd& bd, cudaStream_t st) {
     NLAM_BWD_PAIR(128, false, 512)
   } else if (fn == 128) {
     NLAM_BWD_PAIR(128, false, 256)
+  } else if (wide) {
+    NLAM_BWD_PAIR(0, false, 512)
   } else {
     NLAM_BWD_PAIR(0, false, 256)
   }
