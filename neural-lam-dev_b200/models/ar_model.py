@@ -82,9 +82,33 @@ class ARModel(nn.Module):
     def predict_step(self, prev_state, prev_prev_state, forcing):
         raise NotImplementedError("No prediction step implemented")
 
+    class _RolloutCache:
+        """Scope in which embeddings of static graph features are computed once
+        (BaseGraphModel.embed_static) instead of once per AR step."""
+
+        def __init__(self, model):
+            self.model = model
+
+        def __enter__(self):
+            self.outer = getattr(self.model, "_static_cache", None)
+            if self.outer is None:
+                self.model._static_cache = {}
+
+        def __exit__(self, *exc):
+            if self.outer is None:
+                self.model._static_cache = None
+            return False
+
+    def rollout_cache(self):
+        return ARModel._RolloutCache(self)
+
     def unroll_prediction(self, init_states, forcing_features, true_states):
         """ar_model.py:220-267: sequential rollout; the boundary is overwritten
         with the true state before feeding back."""
+        with self.rollout_cache():
+            return self._unroll_prediction(init_states, forcing_features, true_states)
+
+    def _unroll_prediction(self, init_states, forcing_features, true_states):
         prev_prev_state, prev_state = init_states[:, 0], init_states[:, 1]
         predictions, pred_stds = [], []
         for i in range(forcing_features.shape[1]):
@@ -160,13 +184,14 @@ class ARModel(nn.Module):
         inv_std = self._inv_std_buf if self.loss is metrics.wmse else None
         n_steps = forcing_features.shape[1]
         total = None
-        for i in range(n_steps):
-            net_output = self.net_output(prev_state, prev_prev_state, forcing_features[:, i])
-            new_state, loss_sum = ops.state_step(
-                net_output, prev_state, target_states[:, i], self.diff_std, self.diff_mean,
-                inv_std, self._interior_flat)
-            total = loss_sum if total is None else total + loss_sum
-            prev_prev_state, prev_state = prev_state, new_state
+        with self.rollout_cache():
+            for i in range(n_steps):
+                net_output = self.net_output(prev_state, prev_prev_state, forcing_features[:, i])
+                new_state, loss_sum = ops.state_step(
+                    net_output, prev_state, target_states[:, i], self.diff_std, self.diff_mean,
+                    inv_std, self._interior_flat)
+                total = loss_sum if total is None else total + loss_sum
+                prev_prev_state, prev_state = prev_state, new_state
         return total / float(init_states.shape[0] * n_steps * self._num_interior)
 
     def _masked_squared_loss(self, prediction, target, pred_std):

@@ -59,11 +59,37 @@ class BaseGraphModel(ARModel):
 
     def embed_static(self, embedder, features, batch_size):
         """`expand_to_batch(embedder(features), B)`; on the GPU as one autograd node whose
-        backward sums the batch slices of the incoming gradient inside the kernel."""
+        backward sums the batch slices of the incoming gradient inside the kernel.
+
+        The reference recomputes these embeddings of STATIC graph features in every
+        `predict_step`, i.e. `ar_steps` times per training step, although they depend on the
+        weights only (base_graph_model.py:125-152).  Inside an unrolled
+        rollout (`ARModel.rollout_cache`) they are computed once and reused: same values; the
+        gradients of the AR steps are summed by autograd before ONE embedder backward instead
+        of after `ar_steps` of them (fp32 re-association only)."""
+        cache = getattr(self, "_static_cache", None)
+        key = (id(embedder), int(batch_size))
+        if cache is not None and key in cache:
+            return cache[key]
         if (features.is_cuda and features.dim() == 2 and isinstance(embedder, utils.FusedMLP)
                 and self.args.hidden_layers == 1):
-            return ops.mlp_forward_expand(embedder, features, batch_size)
-        return self.expand_to_batch(embedder(features), batch_size)
+            out = ops.mlp_forward_expand(embedder, features, batch_size)
+        else:
+            out = self.expand_to_batch(embedder(features), batch_size)
+        if cache is not None:
+            cache[key] = out
+        return out
+
+    def embed_mesh_static(self, embedder, features):
+        """`embedder(features)` of static mesh-node features, cached like embed_static."""
+        cache = getattr(self, "_static_cache", None)
+        key = (id(embedder), -1)
+        if cache is not None and key in cache:
+            return cache[key]
+        out = embedder(features)
+        if cache is not None:
+            cache[key] = out
+        return out
 
     def net_output(self, prev_state, prev_prev_state, forcing):
         """Encode-process-decode up to the output map (base_graph_model.py:106-159)."""

@@ -36,7 +36,7 @@ class BaseHiGraphModel(BaseGraphModel):
     def embedd_mesh_nodes(self):
         """Only the bottom level; the rest is embedded in process_step
         (base_hi_graph_model.py:115-122)."""
-        return self.mesh_embedders[0](self.mesh_static_features[0])
+        return self.embed_mesh_static(self.mesh_embedders[0], self.mesh_static_features[0])
 
     def process_step(self, mesh_rep):
         """base_hi_graph_model.py:124-217."""

@@ -23,7 +23,7 @@ class GraphLAM(BaseGraphModel):
         return self.mesh_static_features.shape[0], 0
 
     def embedd_mesh_nodes(self):
-        return self.mesh_embedder(self.mesh_static_features)
+        return self.embed_mesh_static(self.mesh_embedder, self.mesh_static_features)
 
     def process_step(self, mesh_rep):
         """graph_lam.py:73-91: embed m2m edges, run the processor layers."""
