@@ -920,6 +920,8 @@ static int launch_fused(const KParams& p, const tc::BGeo& g, int grid, cudaStrea
 int tc_rowmlp_bwd_fused(const KParams& p, const tc::BGeo& g, cudaStream_t st) {
   // threads per tile row: 2 (16 warps per SM, 128 registers).  4 (32 warps, 64 registers,
   // ~0.4 KB of spills) is kept as an option: measured 3.55 vs 3.30 ms per GraphLAM step
+  // (also tried: 4 only for launches with at most one tile per context, which are pure
+  // latency -- HiLAM 151.6 vs 159.9 samples/s, so not even there)
   const bool nh4 = option_bwd_nh() == 4;
   int rc;
   if (tc_bwd_fused_kind(p) == 2) {
