@@ -69,31 +69,42 @@ class _GraphPlan:
         create_graph.py:506-519): ~11x fewer rows; m2m: ~2.4x; g2m (every grid node sends to
         ~1.2 mesh nodes): nothing to gain, tables not built."""
         self.sp = None
-        M, n_tiles = self.n_edges, self.a_n_tiles
-        send = self.send_sorted.cpu().numpy().astype(np.int64)
-        tile_of_row = np.repeat(np.arange(n_tiles, dtype=np.int64), np.diff(tile_ptr))
-        key = tile_of_row * max(self.n_send_idx, 1) + send
-        order = np.argsort(key, kind="stable")  # rows grouped by (tile, sender), ascending inside
-        ks = key[order]
-        starts = np.flatnonzero(np.r_[True, ks[1:] != ks[:-1]])
-        n_sp = int(starts.shape[0])
-        if n_sp > 0.6 * M:
+        tab = sender_partial_tables(self.send_sorted.cpu().numpy(), tile_ptr, self.n_send_idx)
+        if tab["n_sp"] > 0.6 * self.n_edges:
             return
         mk = lambda a: torch.tensor(np.asarray(a, dtype=np.int32), device=self.device)
-        sender = mk(send[order[starts]])
-        rowptr, perm, _ = ops.csr_build(sender, self.n_send_idx, False)
-        self.sp = {
-            "n_sp": n_sp,
-            "tile_ptr": mk(np.searchsorted(tile_of_row[order[starts]], np.arange(n_tiles + 1), "left")),
-            "row_ptr": mk(np.r_[starts, M]),
-            "rows": mk(order - tile_ptr[tile_of_row[order]]),  # tile-local row ids
-            "csr_rowptr": rowptr, "csr_perm": perm,
-        }
+        rowptr, perm, _ = ops.csr_build(mk(tab["sender"]), self.n_send_idx, False)
+        self.sp = {"n_sp": tab["n_sp"], "tile_ptr": mk(tab["tile_ptr"]), "row_ptr": mk(tab["row_ptr"]),
+                   "rows": mk(tab["rows"]), "csr_rowptr": rowptr, "csr_perm": perm}
 
     def aligned_tables(self, aggr):
         return {"tile_ptr": self.a_tile_ptr, "n_tiles": self.a_n_tiles,
                 "tile_seg": self.a_tile_seg, "seg_ptr": self.rowptr, "n_seg": self.num_rec,
                 "scale": self.inv_deg if aggr == "mean" else None, "out_idx": self.perm}
+
+
+def sender_partial_tables(send_sorted, tile_ptr, n_send):
+    """Host tables of the sender pre-reduction (see _GraphPlan._build_sender_partials).
+    send_sorted[M]: sender of every edge in receiver-sorted order; tile_ptr[n_tiles + 1]: row
+    ranges of the receiver-aligned tiles.  Partial q = one (tile, sender) pair; partials are
+    numbered tile by tile (tile t owns [tile_ptr_q[t], tile_ptr_q[t+1])), inside a tile by
+    sender id; its rows are rows[row_ptr[q] : row_ptr[q+1]] (tile-local ids, ascending), and
+    the row lists of tile t start at position tile_ptr[t] of `rows`."""
+    send = np.asarray(send_sorted, dtype=np.int64)
+    tile_ptr = np.asarray(tile_ptr, dtype=np.int64)
+    M, n_tiles = send.shape[0], tile_ptr.shape[0] - 1
+    tile_of_row = np.repeat(np.arange(n_tiles, dtype=np.int64), np.diff(tile_ptr))
+    key = tile_of_row * max(int(n_send), 1) + send
+    order = np.argsort(key, kind="stable")  # rows grouped by (tile, sender), ascending inside
+    ks = key[order]
+    starts = np.flatnonzero(np.r_[True, ks[1:] != ks[:-1]]) if M > 0 else np.zeros(0, np.int64)
+    return {
+        "n_sp": int(starts.shape[0]),
+        "sender": send[order[starts]],
+        "tile_ptr": np.searchsorted(tile_of_row[order[starts]], np.arange(n_tiles + 1), "left"),
+        "row_ptr": np.r_[starts, M],
+        "rows": order - tile_ptr[tile_of_row[order]],
+    }
 
 
 def _aligned_tiles(rowptr, max_rows=128):
