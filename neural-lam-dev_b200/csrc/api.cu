@@ -35,6 +35,8 @@ static std::atomic<int> g_rb128{env_or("NLAM_RB128", 4)};
 int option_rb128() { return g_rb128.load(); }
 static std::atomic<int> g_bwd_nh{env_or("NLAM_BWD_NH", 2)};
 int option_bwd_nh() { return g_bwd_nh.load(); }
+static std::atomic<int> g_fp32_split{env_or("NLAM_FP32_SPLIT", 1)};
+int option_fp32_split() { return g_fp32_split.load(); }
 int option_fwd_mc() { return g_fwd_mc.load(); }
 int option_dgrad_mc() { return g_dgrad_mc.load(); }
 int option_bwd_fused() { return g_bwd_fused.load(); }
@@ -69,6 +71,7 @@ extern "C" int nlam_set_option(const char* name, int value) {
   if (name && !strcmp(name, "tma")) return nlam::g_tma.store(value), 0;
   if (name && !strcmp(name, "bwd_nh")) return nlam::g_bwd_nh.store(value), 0;
   if (name && !strcmp(name, "wide128")) return nlam::g_wide128.store(value), 0;
+  if (name && !strcmp(name, "fp32_split")) return nlam::g_fp32_split.store(value), 0;
   nlam::set_error("nlam_set_option: unknown option");
   return 1;
 }
@@ -80,7 +83,10 @@ extern "C" int nlam_version(void) { return 1; }
 
 extern "C" int nlam_rowmlp_fwd(const nlam_rowmlp* d, void* stream) {
   NLAM_CHECK(d, "rowmlp_fwd: NULL descriptor");
-  if (d->precision == NLAM_FP32) return simt_rowmlp_fwd(*d, (cudaStream_t)stream);
+  if (d->precision == NLAM_FP32) {
+    if (tc::tc_split_supported(*d)) return tc_rowmlp_fwd(*d, (cudaStream_t)stream);
+    return simt_rowmlp_fwd(*d, (cudaStream_t)stream);
+  }
   if (d->precision == NLAM_BF16) {
     if (tc::tc_supported(*d)) return tc_rowmlp_fwd(*d, (cudaStream_t)stream);
     return simt_rowmlp_fwd(*d, (cudaStream_t)stream);  // widths the MMA path does not take
@@ -92,6 +98,7 @@ extern "C" int nlam_rowmlp_fwd(const nlam_rowmlp* d, void* stream) {
 extern "C" size_t nlam_rowmlp_bwd_workspace(const nlam_rowmlp* d) {
   if (!d) return 0;
   if (d->precision == NLAM_BF16 && tc::tc_supported(*d)) return tc_rowmlp_bwd_workspace(*d);
+  if (d->precision == NLAM_FP32 && tc::tc_split_supported(*d)) return tc_rowmlp_bwd_workspace(*d);
   return simt_rowmlp_bwd_workspace(*d);
 }
 
@@ -111,6 +118,8 @@ extern "C" size_t nlam_rowmlp_param_floats(const nlam_rowmlp* d) {
 extern "C" int nlam_rowmlp_bwd_run(const nlam_rowmlp_bwd* d, void* stream) {
   NLAM_CHECK(d, "rowmlp_bwd: NULL descriptor");
   if (d->fwd.precision == NLAM_BF16 && tc::tc_supported(d->fwd))
+    return tc_rowmlp_bwd(*d, (cudaStream_t)stream);
+  if (d->fwd.precision == NLAM_FP32 && tc::tc_split_supported(d->fwd))
     return tc_rowmlp_bwd(*d, (cudaStream_t)stream);
   if (d->fwd.precision == NLAM_FP32 || d->fwd.precision == NLAM_BF16)
     return simt_rowmlp_bwd(*d, (cudaStream_t)stream);

@@ -21,6 +21,7 @@ int option_tma();        // 1: TMA row-gather kernels where every operand has a 
 int option_bwd_nh();     // fused backward: threads per tile row, 2 (default) or 4 (measured 7 % slower)
 int option_wide128();    // 1 (default): d = 128 kernels with 512 threads per CTA
 int option_rb128();      // z blocks per gather round of the d = 128 input-gradient kernel: 4 (default) or 2
+int option_fp32_split();  // 1 (default): fp32 mode on the tensor cores (split bf16 operands) where the tiles fit
 int option_pdl();        // 1: launch with programmatic dependent launch (see launch_k)  // -1 / 1: fused dgrad + wgrad kernel where eligible, 0: two kernels
 
 // Programmatic dependent launch: a kernel launched with this attribute may start while
@@ -104,6 +105,7 @@ size_t simt_rowmlp_bwd_workspace(const nlam_rowmlp& d);
 // bf16 tcgen05 path
 namespace tc {
 bool tc_supported(const nlam_rowmlp& d);
+bool tc_split_supported(const nlam_rowmlp& d);  // precision fp32 on the tensor cores
 }
 int tc_rowmlp_fwd(const nlam_rowmlp& d, cudaStream_t st);
 int tc_rowmlp_bwd(const nlam_rowmlp_bwd& d, cudaStream_t st);

@@ -33,6 +33,7 @@ struct KParams {
   const int32_t* sp_row_ptr;
   const int32_t* sp_rows;
   int src0_batch_sum;       // d_src[0] = [1, rows, w] summed over the batch
+  int split;                // tensor-core kernels: fp32 operands as bf16 hi + lo tiles
   float* a_save;
   float* dy_save;
   float* dh_save;

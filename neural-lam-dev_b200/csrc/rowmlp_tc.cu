@@ -28,7 +28,8 @@ namespace tc {
 // TNT = threads per CTA: 256 (two CTAs per SM at d <= 64), or 512 for d = 128, where shared
 // memory allows one CTA per SM only -- 16 warps instead of 8, and 32 instead of 64 columns of
 // a row per thread (NG = TNT / 128 column groups per row).
-template <int FN, bool FG, int TNT>
+// SP: fp32 operands as split bf16 tiles, three UMMAs per product (rowmlp_tc.cuh, put8).
+template <int FN, bool FG, int TNT, bool SP = false>
 __global__ void __launch_bounds__(TNT, TNT == 256 ? 2 : 1)
 rowmlp_tc_fwd_kernel(const __grid_constant__ KParams p, const __grid_constant__ Geo g) {
   constexpr bool F = FN > 0;  // square fast path: sizes are compile-time constants
@@ -65,8 +66,8 @@ rowmlp_tc_fwd_kernel(const __grid_constant__ KParams p, const __grid_constant__ 
   uint32_t ph0 = 0, ph1 = 0;
   int loaded_chunk = -1;
   if (p.d.n_chunks == 1) {  // single weight set: staged while the previous kernel drains
-    stage_weight<TNT>(p.d.w.w1, dh, p.k_total, n1, g.k1, sW1);
-    stage_weight<TNT>(p.d.w.w2, dout, dh, n2, k2, sW2);
+    stage_weight<TNT, SP>(p.d.w.w1, dh, p.k_total, n1, g.k1, sW1);
+    stage_weight<TNT, SP>(p.d.w.w2, dout, dh, n2, k2, sW2);
     stage_params<TNT>(p.d, 0, n1, n2, sPar);
     loaded_chunk = 0;
   }
@@ -78,6 +79,9 @@ rowmlp_tc_fwd_kernel(const __grid_constant__ KParams p, const __grid_constant__ 
   const uint32_t idesc1 = make_idesc_bf16(TM, n1);
   const uint32_t idesc2 = make_idesc_bf16(TM, n2);
   const uint32_t a_blk = TM * 128u;
+  // split mode: byte offsets of the lo tiles behind their hi tiles
+  const uint32_t a_lo = (uint32_t)g.kb1 * a_blk, a2_lo = (uint32_t)g.kb2 * a_blk;
+  const uint32_t w1_lo = (uint32_t)g.kb1 * (uint32_t)n1 * 128u, w2_lo = (uint32_t)g.kb2 * (uint32_t)n2 * 128u;
 
   // epilogue ownership: TMEM lane quarter q, row r, column half hf
   const int q = warp & 3, hf = warp >> 2, r = q * 32 + lane;
@@ -110,8 +114,8 @@ rowmlp_tc_fwd_kernel(const __grid_constant__ KParams p, const __grid_constant__ 
     tile_range<TM>(p.d, tile, row0, cnt, chunk);
 
     if (chunk != loaded_chunk) {  // (re)load the weight set of this chunk
-      stage_weight<TNT>(p.d.w.w1 + (size_t)chunk * dh * p.k_total, dh, p.k_total, n1, g.k1, sW1);
-      stage_weight<TNT>(p.d.w.w2 + (size_t)chunk * dout * dh, dout, dh, n2, k2, sW2);
+      stage_weight<TNT, SP>(p.d.w.w1 + (size_t)chunk * dh * p.k_total, dh, p.k_total, n1, g.k1, sW1);
+      stage_weight<TNT, SP>(p.d.w.w2 + (size_t)chunk * dout * dh, dout, dh, n2, k2, sW2);
       stage_params<TNT>(p.d, chunk, n1, n2, sPar);
       loaded_chunk = chunk;
     }
@@ -121,9 +125,9 @@ rowmlp_tc_fwd_kernel(const __grid_constant__ KParams p, const __grid_constant__ 
       const int cidx[NLAM_MAX_SRC] = {nidx[0], nidx[1], nidx[2]};
       gather_rows_pipe<64, TNT>(p, b, cidx, sA, tid);
     } else if (F && FG) {
-      gather_rows_fast<(F ? FN : 64), TNT>(p, b, row0, cnt, 0, p.d.n_src, sA);
+      gather_rows_fast<(F ? FN : 64), TNT, SP>(p, b, row0, cnt, 0, p.d.n_src, sA, a_lo);
     } else {
-      gather_rows<TNT>(p, b, row0, cnt, 0, g.k1, sA);
+      gather_rows<TNT, SP>(p, b, row0, cnt, 0, g.k1, sA, a_lo);
     }
     {  // next tile: row indices (pipelined gather) and L2 prefetch of its input rows
       const int tn = t + gridDim.x;
@@ -150,6 +154,12 @@ rowmlp_tc_fwd_kernel(const __grid_constant__ KParams p, const __grid_constant__ 
         const uint32_t kb = ks >> 2, kin = (ks & 3) * 32;
         umma_bf16(tH, make_desc_k_sw128(a0 + kb * a_blk + kin),
                   make_desc_k_sw128(w0 + kb * w_blk + kin), idesc1, ks > 0);
+        if (SP) {
+          umma_bf16(tH, make_desc_k_sw128(a0 + kb * a_blk + kin),
+                    make_desc_k_sw128(w0 + w1_lo + kb * w_blk + kin), idesc1, 1u);
+          umma_bf16(tH, make_desc_k_sw128(a0 + a_lo + kb * a_blk + kin),
+                    make_desc_k_sw128(w0 + kb * w_blk + kin), idesc1, 1u);
+        }
       }
       umma_commit(&bars[0]);
     }
@@ -164,15 +174,8 @@ rowmlp_tc_fwd_kernel(const __grid_constant__ KParams p, const __grid_constant__ 
         float v[16];
         tmem_ld16(tH + lane_addr + (uint32_t)c0, v);
 #pragma unroll
-        for (int j = 0; j < 16; ++j) v[j] = silu_fast(v[j] + sPar[c0 + j]);
-#pragma unroll
-        for (int h8 = 0; h8 < 2; ++h8) {
-          uint4 pk = make_uint4(pack_bf16(v[h8 * 8 + 0], v[h8 * 8 + 1]),
-                                pack_bf16(v[h8 * 8 + 2], v[h8 * 8 + 3]),
-                                pack_bf16(v[h8 * 8 + 4], v[h8 * 8 + 5]),
-                                pack_bf16(v[h8 * 8 + 6], v[h8 * 8 + 7]));
-          *reinterpret_cast<uint4*>(sA2 + sw128_off(r, c0 + h8 * 8, a_blk)) = pk;
-        }
+        for (int j = 0; j < 16; ++j) v[j] = silu_sel<SP>(v[j] + sPar[c0 + j]);
+        put16<SP>(sA2, a2_lo, r, c0, a_blk, v);
       }
     }
     fence_async_smem();
@@ -188,6 +191,12 @@ rowmlp_tc_fwd_kernel(const __grid_constant__ KParams p, const __grid_constant__ 
         const uint32_t kb = ks >> 2, kin = (ks & 3) * 32;
         umma_bf16(tY, make_desc_k_sw128(a0 + kb * a_blk + kin),
                   make_desc_k_sw128(w0 + kb * w_blk + kin), idesc2, ks > 0);
+        if (SP) {
+          umma_bf16(tY, make_desc_k_sw128(a0 + kb * a_blk + kin),
+                    make_desc_k_sw128(w0 + w2_lo + kb * w_blk + kin), idesc2, 1u);
+          umma_bf16(tY, make_desc_k_sw128(a0 + a2_lo + kb * a_blk + kin),
+                    make_desc_k_sw128(w0 + kb * w_blk + kin), idesc2, 1u);
+        }
       }
       umma_commit(&bars[1]);
     }
@@ -344,8 +353,24 @@ bool tc_supported(const nlam_rowmlp& d) {
   return k <= 384;
 }
 
+int make_geo(const KParams& p, Geo& g);
+int make_bgeo_probe(const KParams& p);  // rowmlp_tc_bwd.cu
+
+// fp32 on the tensor cores (split operands): the doubled tiles must fit shared memory in all
+// three kernels, else the FFMA path takes the problem
+bool tc_split_supported(const nlam_rowmlp& d) {
+  if (option_fp32_split() == 0 || !tc_supported(d)) return false;
+  KParams p{};
+  if (fill_params(d, p)) return false;
+  p.split = 1;
+  Geo g{};
+  return make_geo(p, g) == 0 && make_bgeo_probe(p) == 0;
+}
+
 int make_geo(const KParams& p, Geo& g) {
   const nlam_rowmlp& d = p.d;
+  const uint32_t P = p.split ? 2u : 1u;  // operand tiles: hi (+ lo)
+  g.parts = (int)P;
   g.n1 = pad_n(d.d_hidden), g.n2 = pad_n(d.d_out);
   g.k1 = (p.k_total + 15) / 16 * 16;
   g.k2 = (d.d_hidden + 15) / 16 * 16;
@@ -354,8 +379,8 @@ int make_geo(const KParams& p, Geo& g) {
   g.tmem_cols = 32;
   while (g.tmem_cols < cols) g.tmem_cols *= 2;
   g.stg_ld = g.n2 + 4;
-  const uint32_t a_bytes = (uint32_t)g.kb1 * TM * 128u;
-  const uint32_t a2_bytes = (uint32_t)g.kb2 * TM * 128u;
+  const uint32_t a_bytes = P * (uint32_t)g.kb1 * TM * 128u;
+  const uint32_t a2_bytes = P * (uint32_t)g.kb2 * TM * 128u;
   const uint32_t stg_bytes = (uint32_t)TM * g.stg_ld * 4u;
   const uint32_t lnx_bytes = 2u * TM * 4u * 4u;  // [2][TM][<= 4 column groups]
   uint32_t r0 = a_bytes > a2_bytes ? a_bytes : a2_bytes;
@@ -363,8 +388,8 @@ int make_geo(const KParams& p, Geo& g) {
   auto al = [](uint32_t x) { return (x + 1023u) & ~1023u; };
   g.off_lnx = stg_bytes;
   uint32_t o = al(r0);
-  g.off_w1 = o, o += al((uint32_t)g.kb1 * g.n1 * 128u);
-  g.off_w2 = o, o += al((uint32_t)g.kb2 * g.n2 * 128u);
+  g.off_w1 = o, o += al(P * (uint32_t)g.kb1 * g.n1 * 128u);
+  g.off_w2 = o, o += al(P * (uint32_t)g.kb2 * g.n2 * 128u);
   g.off_par = o, o += (uint32_t)(g.n1 + 3 * g.n2) * 4u;
   g.off_bar = o, o += 64;
   g.smem_bytes = o;
@@ -386,9 +411,10 @@ int tc_rowmlp_fwd(const nlam_rowmlp& d, cudaStream_t st) {
              "rowmlp: bf16 shadow outputs need 16-byte aligned fp32 outputs and d_out %% 4 == 0");
   NLAM_CHECK(!d.out_bf16 || d.out, "rowmlp: out_bf16 needs out");
   NLAM_CHECK(!d.out_res_bf16 || d.out_res, "rowmlp: out_res_bf16 needs out_res");
+  p.split = d.precision == NLAM_FP32;  // fp32 operands: split bf16 tiles, 3 UMMAs per product
   tc::Geo g{};
   if (tc::make_geo(p, g)) return 1;
-  {  // four tiles in flight per SM with shared weights, when there is enough work
+  if (!p.split) {  // four tiles in flight per SM with shared weights, when there is enough work
     const int mc_env = option_fwd_mc();
     // measured on MEPS shapes: +16 % on the 3-source edge MLPs (gather-latency bound),
     // -12 % on the 2-source node MLP, so only the former take this path by default
@@ -409,6 +435,20 @@ int tc_rowmlp_fwd(const nlam_rowmlp& d, cudaStream_t st) {
   const bool fg = tc::fast_gather(p);
   // d = 128: one CTA per SM (shared memory) -> 512 threads (option "wide128" = 0: 256)
   const bool wide = option_wide128() != 0 && per_sm == 1;
+  if (p.split) {  // the hi/lo tiles of a d = 64 edge MLP take 160 KB: one wide CTA per SM
+    NLAM_CHECK(!d.out_bf16 && !d.out_res_bf16 && !d.agg.out_bf16, "rowmlp(fp32): no bf16 shadow outputs");
+    const bool w = per_sm == 1;
+    int rc = fn == 64 ? (fg ? (w ? launch(tc::rowmlp_tc_fwd_kernel<64, true, 512, true>, 512)
+                                 : launch(tc::rowmlp_tc_fwd_kernel<64, true, 256, true>, 256))
+                            : (w ? launch(tc::rowmlp_tc_fwd_kernel<64, false, 512, true>, 512)
+                                 : launch(tc::rowmlp_tc_fwd_kernel<64, false, 256, true>, 256)))
+                      : (w ? launch(tc::rowmlp_tc_fwd_kernel<0, false, 512, true>, 512)
+                           : launch(tc::rowmlp_tc_fwd_kernel<0, false, 256, true>, 256));
+    if (rc) return rc;
+    NLAM_CUDA(cudaGetLastError());
+    count_launch();
+    return 0;
+  }
   int rc = fn == 64    ? (fg ? launch(tc::rowmlp_tc_fwd_kernel<64, true, 256>, 256)
                              : launch(tc::rowmlp_tc_fwd_kernel<64, false, 256>, 256))
            : fn == 128 ? (wide ? (fg ? launch(tc::rowmlp_tc_fwd_kernel<128, true, 512>, 512)

@@ -21,6 +21,7 @@ struct Geo {
   uint32_t smem_bytes;
   int total_tiles;     // batch * tiles
   int tiles_per_batch;
+  int parts;           // 1 = bf16 operands, 2 = fp32 operands split into bf16 hi + lo tiles
 };
 
 inline int pad_n(int n) { return n <= 16 ? 16 : n <= 32 ? 32 : n <= 64 ? 64 : n <= 128 ? 128 : -1; }
@@ -37,28 +38,68 @@ __device__ __forceinline__ float silu_fast(float x) {
   return fmaf(h, tanh_fast(h), h);
 }
 
+// ---- fp32 mode on the bf16 tensor cores (template flag SP, "split"): every fp32 operand
+// x is held as two bf16 tiles hi = bf16(x), lo = bf16(x - hi), the lo tile `lo_off` bytes
+// after the hi tile, and every product A.B is issued as three UMMAs into the same fp32
+// accumulator: A_hi.B_hi + A_hi.B_lo + A_lo.B_hi.  The dropped terms are O(2^-17) of a
+// product, so the result carries ~16 mantissa bits: inside the fp32 parity tolerance
+// (1e-4 outputs / 1e-3 gradients), at 3x the (small) tensor time of the bf16 mode.
+template <bool SP>
+__device__ __forceinline__ void put8(uint8_t* dst, uint32_t lo_off, float a0, float a1, float a2,
+                                     float a3, float a4, float a5, float a6, float a7) {
+  const uint4 hi = make_uint4(pack_bf16(a0, a1), pack_bf16(a2, a3), pack_bf16(a4, a5),
+                              pack_bf16(a6, a7));
+  *reinterpret_cast<uint4*>(dst) = hi;
+  if (SP) {
+    auto rest = [](float x, float y, uint32_t h) {  // bf16 -> fp32 is a 16-bit shift
+      return pack_bf16(x - __uint_as_float(h << 16), y - __uint_as_float(h & 0xffff0000u));
+    };
+    *reinterpret_cast<uint4*>(dst + lo_off) =
+        make_uint4(rest(a0, a1, hi.x), rest(a2, a3, hi.y), rest(a4, a5, hi.z), rest(a6, a7, hi.w));
+  }
+}
+template <bool SP>
+__device__ __forceinline__ void put16(uint8_t* tile, uint32_t lo_off, int row, int c0,
+                                      uint32_t blk, const float (&v)[16]) {
+#pragma unroll
+  for (int h8 = 0; h8 < 2; ++h8)
+    put8<SP>(tile + sw128_off(row, c0 + h8 * 8, blk), lo_off, v[h8 * 8 + 0], v[h8 * 8 + 1],
+             v[h8 * 8 + 2], v[h8 * 8 + 3], v[h8 * 8 + 4], v[h8 * 8 + 5], v[h8 * 8 + 6],
+             v[h8 * 8 + 7]);
+}
+// SiLU and its derivative: the split mode needs fp32-accurate ones (ex2 + rcp)
+template <bool SP>
+__device__ __forceinline__ float silu_sel(float x) {
+  return SP ? __fdividef(x, 1.0f + __expf(-x)) : silu_fast(x);
+}
+
 // W[n][k] fp32 (nn.Linear layout) -> bf16 K-major SW128 blocks of [n_pad rows][64]
 // (TNT = threads of the calling CTA, here and in the helpers below)
-template <int TNT = NT>
+template <int TNT = NT, bool SP = false>
 __device__ __forceinline__ void stage_weight(const float* __restrict__ W, int n_real, int k_real, int n_pad,
                              int k_pad, uint8_t* dst) {
   const int nch = k_pad >> 3;
   const uint32_t blk = (uint32_t)n_pad * 128u;
+  const uint32_t lo_off = (uint32_t)((k_pad + 63) >> 6) * blk;
   for (int u = threadIdx.x; u < n_pad * nch; u += TNT) {
     const int n = u / nch, c = u % nch, k0 = c * 8;
     float v[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j)
       v[j] = (n < n_real && k0 + j < k_real) ? __ldg(W + (size_t)n * k_real + k0 + j) : 0.f;
-    uint4 pk = make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]),
-                          pack_bf16(v[6], v[7]));
-    *reinterpret_cast<uint4*>(dst + sw128_off(n, k0, blk)) = pk;
+    put8<SP>(dst + sw128_off(n, k0, blk), lo_off, v[0], v[1], v[2], v[3], v[4], v[5], v[6], v[7]);
   }
 }
 
 
 __device__ __forceinline__ float silu_grad_fast(float x) {
   const float s = fmaf(0.5f, tanh_fast(0.5f * x), 0.5f);  // sigmoid(x)
+  return s * fmaf(x, 1.0f - s, 1.0f);
+}
+template <bool SP>
+__device__ __forceinline__ float silu_grad_sel(float x) {
+  if (!SP) return silu_grad_fast(x);
+  const float s = __fdividef(1.0f, 1.0f + __expf(-x));
   return s * fmaf(x, 1.0f - s, 1.0f);
 }
 
@@ -69,9 +110,10 @@ __device__ __forceinline__ float silu_grad_fast(float x) {
 // GU with all row-index loads, then all 128-bit data loads, issued before any
 // use, so that GU*2 loads per thread are in flight (memory-level parallelism).
 constexpr int GU = 6;
-template <int TNT = NT>
+template <int TNT = NT, bool SP = false>
 __device__ __forceinline__ void gather_rows(const KParams& p, int b, int row0, int cnt,
-                                            int k_begin, int k_end, uint8_t* sA) {
+                                            int k_begin, int k_end, uint8_t* sA,
+                                            uint32_t lo_off = 0) {
   const int nch = (k_end - k_begin) >> 3;
   const int total = TM * nch;
   const uint32_t a_blk = TM * 128u;
@@ -136,9 +178,8 @@ __device__ __forceinline__ void gather_rows(const KParams& p, int b, int row0, i
 #pragma unroll
     for (int j = 0; j < GU; ++j) {
       if (nval[j] == 1) continue;
-      uint4 pk = make_uint4(pack_bf16(x[j].x, x[j].y), pack_bf16(x[j].z, x[j].w),
-                            pack_bf16(y[j].x, y[j].y), pack_bf16(y[j].z, y[j].w));
-      *reinterpret_cast<uint4*>(sA + sw128_off(rowv[j], k0v[j] - (k_begin & ~63), a_blk)) = pk;
+      put8<SP>(sA + sw128_off(rowv[j], k0v[j] - (k_begin & ~63), a_blk), lo_off, x[j].x, x[j].y,
+               x[j].z, x[j].w, y[j].x, y[j].y, y[j].z, y[j].w);
     }
   }
 }
@@ -147,9 +188,10 @@ __device__ __forceinline__ void gather_rows(const KParams& p, int b, int row0, i
 // 16-byte aligned.  Thread (rl, c) handles chunk c of rows rl, rl+RPP, ...: no
 // divisions, all row indices then all 2*NP 128-bit loads issued before use.
 // Source s lands at A-tile columns [(s - s_begin)*FN, ...).
-template <int FN, int TNT = NT>
+template <int FN, int TNT = NT, bool SP = false>
 __device__ __forceinline__ void gather_rows_fast(const KParams& p, int b, int row0, int cnt,
-                                                 int s_begin, int s_end, uint8_t* sA) {
+                                                 int s_begin, int s_end, uint8_t* sA,
+                                                 uint32_t lo_off = 0) {
   constexpr int CPR = FN / 8;    // 16-byte bf16 chunks per source row
   constexpr int RPP = TNT / CPR;  // rows per pass
   constexpr int NP = TM / RPP;   // passes
@@ -167,7 +209,7 @@ __device__ __forceinline__ void gather_rows_fast(const KParams& p, int b, int ro
       ridx[i] = row < cnt ? (idx ? __ldg(idx + row0 + row) : row0 + row) : -1;
     }
     const int kcol_s = (s - s_begin) * FN + c * 8;
-    if (src.shadow) {  // bf16 shadow rows: 16-byte chunks copied as they are
+    if (!SP && src.shadow) {  // bf16 shadow rows: 16-byte chunks copied as they are
       const uint4* sb = reinterpret_cast<const uint4*>(
           reinterpret_cast<const __nv_bfloat16*>(src.shadow) + (long long)b * src.shadow_batch_stride) + c;
       uint4 q[NP];
@@ -196,9 +238,8 @@ __device__ __forceinline__ void gather_rows_fast(const KParams& p, int b, int ro
 #pragma unroll
     for (int i = 0; i < NP; ++i) {
       const int row = i * RPP + rl;
-      uint4 pk = make_uint4(pack_bf16(x[i].x, x[i].y), pack_bf16(x[i].z, x[i].w),
-                            pack_bf16(y[i].x, y[i].y), pack_bf16(y[i].z, y[i].w));
-      *reinterpret_cast<uint4*>(sA + sw128_off(row, kcol, a_blk)) = pk;
+      put8<SP>(sA + sw128_off(row, kcol, a_blk), lo_off, x[i].x, x[i].y, x[i].z, x[i].w, y[i].x,
+               y[i].y, y[i].z, y[i].w);
     }
   }
 }

@@ -33,7 +33,9 @@ namespace tc {
 constexpr int MAXCH = 4;  // 16-column chunks per thread (n <= 128, two column halves)
 
 // TNT = threads per CTA (256, or 512 at d = 128 where one CTA fits per SM; see rowmlp_tc.cu)
-template <int FN, bool FG, int TNT>
+// SP: fp32 operands as split bf16 tiles (rowmlp_tc.cuh, put8): every tile below has a lo twin
+// right behind it, every product is three UMMAs, the HBM tile images carry both parts.
+template <int FN, bool FG, int TNT, bool SP = false>
 __global__ void __launch_bounds__(TNT, TNT == 256 ? 2 : 1)
 rowmlp_tc_dgrad_kernel(const __grid_constant__ KParams p, const __grid_constant__ BGeo g) {
   constexpr bool F = FN > 0;  // square fast path: sizes are compile-time constants
@@ -76,6 +78,11 @@ rowmlp_tc_dgrad_kernel(const __grid_constant__ KParams p, const __grid_constant_
   int loaded_chunk = -1;
 
   const uint32_t a_blk = TM * 128u;
+  constexpr uint32_t P = SP ? 2u : 1u;
+  // split mode: byte offsets of the lo tiles (z round region, a / dH tile, dY tile, W1, W2)
+  const uint32_t z_lo = (uint32_t)min(g.kb1, g.rb) * a_blk;
+  const uint32_t t2_lo = (uint32_t)kb2 * a_blk, to_lo = (uint32_t)kbo * a_blk;
+  const uint32_t w1_lo = (uint32_t)g.kb1 * (uint32_t)n1 * 128u, w2_lo = (uint32_t)kb2 * (uint32_t)n2 * 128u;
   const uint32_t idesc1 = make_idesc_bf16(TM, n1);
   const uint32_t idesc2 = make_idesc_bf16(TM, n2);
   const uint32_t idesc3 = make_idesc_bf16(TM, n1, 0, 1);  // B = W2 viewed MN-major
@@ -104,7 +111,7 @@ rowmlp_tc_dgrad_kernel(const __grid_constant__ KParams p, const __grid_constant_
       __syncthreads();
       tot = sLnx[r * 2] + sLnx[r * 2 + 1];
     } else {
-      sLnx[r * 2 + hf] = v;
+      if (hf < 2) sLnx[r * 2 + hf] = v;  // (four groups, narrow output: group 0 holds the row)
       __syncthreads();
       tot = sLnx[r * 2] + (split2 ? sLnx[r * 2 + 1] : 0.f);
     }
@@ -168,8 +175,8 @@ rowmlp_tc_dgrad_kernel(const __grid_constant__ KParams p, const __grid_constant_
 
     if (chunk != loaded_chunk) {
       if (loaded_chunk >= 0) flush_colsums(loaded_chunk);
-      stage_weight<TNT>(p.d.w.w1 + (size_t)chunk * dh * p.k_total, dh, p.k_total, n1, g.k1, sW1);
-      stage_weight<TNT>(p.d.w.w2 + (size_t)chunk * dout * dh, dout, dh, n2, k2, sW2);
+      stage_weight<TNT, SP>(p.d.w.w1 + (size_t)chunk * dh * p.k_total, dh, p.k_total, n1, g.k1, sW1);
+      stage_weight<TNT, SP>(p.d.w.w2 + (size_t)chunk * dout * dh, dout, dh, n2, k2, sW2);
       stage_params<TNT>(p.d, chunk, n1, n2, sPar, 2);  // beta is not needed backward
       loaded_chunk = chunk;
     }
@@ -248,10 +255,10 @@ rowmlp_tc_dgrad_kernel(const __grid_constant__ KParams p, const __grid_constant_
         const int cidx[NLAM_MAX_SRC] = {nidx[0], nidx[1], nidx[2]};
         gather_rows_pipe<64, TNT>(p, b, cidx, sA, tid);
       } else if (F && FG) {
-        gather_rows_fast<(F ? FN : 64), TNT>(p, b, row0, cnt, k_begin / (F ? FN : 64),
-                                             k_end / (F ? FN : 64), sA);
+        gather_rows_fast<(F ? FN : 64), TNT, SP>(p, b, row0, cnt, k_begin / (F ? FN : 64),
+                                                 k_end / (F ? FN : 64), sA, z_lo);
       } else {
-        gather_rows<TNT>(p, b, row0, cnt, k_begin, k_end, sA);
+        gather_rows<TNT, SP>(p, b, row0, cnt, k_begin, k_end, sA, z_lo);
       }
       fence_async_smem();
       __syncthreads();
@@ -263,6 +270,12 @@ rowmlp_tc_dgrad_kernel(const __grid_constant__ KParams p, const __grid_constant_
           const uint32_t kb = ks >> 2, kin = (ks & 3) * 32;
           umma_bf16(tH, make_desc_k_sw128(a0 + (kb - kb0) * a_blk + kin),
                     make_desc_k_sw128(w0 + kb * w_blk + kin), idesc1, ks > 0);
+          if (SP) {
+            umma_bf16(tH, make_desc_k_sw128(a0 + (kb - kb0) * a_blk + kin),
+                      make_desc_k_sw128(w0 + w1_lo + kb * w_blk + kin), idesc1, 1u);
+            umma_bf16(tH, make_desc_k_sw128(a0 + z_lo + (kb - kb0) * a_blk + kin),
+                      make_desc_k_sw128(w0 + kb * w_blk + kin), idesc1, 1u);
+          }
         }
         umma_commit(&bars[0]);
       }
@@ -310,15 +323,8 @@ rowmlp_tc_dgrad_kernel(const __grid_constant__ KParams p, const __grid_constant_
         float v[16];
         tmem_ld16(tH + lane_addr + (uint32_t)c0, v);
 #pragma unroll
-        for (int j = 0; j < 16; ++j) v[j] = silu_fast(v[j] + sPar[c0 + j]);
-#pragma unroll
-        for (int h8 = 0; h8 < 2; ++h8) {
-          uint4 pk = make_uint4(pack_bf16(v[h8 * 8 + 0], v[h8 * 8 + 1]),
-                                pack_bf16(v[h8 * 8 + 2], v[h8 * 8 + 3]),
-                                pack_bf16(v[h8 * 8 + 4], v[h8 * 8 + 5]),
-                                pack_bf16(v[h8 * 8 + 6], v[h8 * 8 + 7]));
-          *reinterpret_cast<uint4*>(sT + sw128_off(r, c0 + h8 * 8, a_blk)) = pk;
-        }
+        for (int j = 0; j < 16; ++j) v[j] = silu_sel<SP>(v[j] + sPar[c0 + j]);
+        put16<SP>(sT, t2_lo, r, c0, a_blk, v);
       }
     }
     fence_async_smem();
@@ -334,10 +340,16 @@ rowmlp_tc_dgrad_kernel(const __grid_constant__ KParams p, const __grid_constant_
         const uint32_t kb = ks >> 2, kin = (ks & 3) * 32;
         umma_bf16(tY, make_desc_k_sw128(a0 + kb * a_blk + kin),
                   make_desc_k_sw128(w0 + kb * w_blk + kin), idesc2, ks > 0);
+        if (SP) {
+          umma_bf16(tY, make_desc_k_sw128(a0 + kb * a_blk + kin),
+                    make_desc_k_sw128(w0 + w2_lo + kb * w_blk + kin), idesc2, 1u);
+          umma_bf16(tY, make_desc_k_sw128(a0 + t2_lo + kb * a_blk + kin),
+                    make_desc_k_sw128(w0 + kb * w_blk + kin), idesc2, 1u);
+        }
       }
       umma_commit(&bars[0]);
     }
-    copy_tile_out<TNT>(sT, g.a_img + (size_t)t * kb2 * a_blk, kb2 * a_blk);
+    copy_tile_out<TNT>(sT, g.a_img + (size_t)t * P * kb2 * a_blk, P * kb2 * a_blk);
     mbar_wait(&bars[0], ph_main);
     ph_main ^= 1;
     tc_fence_after();
@@ -433,14 +445,7 @@ rowmlp_tc_dgrad_kernel(const __grid_constant__ KParams p, const __grid_constant_
             for (int j = 0; j < 16; ++j) v[j] = (F || c0 + j < dout) ? dmv[j] : 0.f;
           }
           acc_db2[ci] += warp_colsum16(v, lane);
-#pragma unroll
-          for (int h8 = 0; h8 < 2; ++h8) {
-            uint4 pk = make_uint4(pack_bf16(v[h8 * 8 + 0], v[h8 * 8 + 1]),
-                                  pack_bf16(v[h8 * 8 + 2], v[h8 * 8 + 3]),
-                                  pack_bf16(v[h8 * 8 + 4], v[h8 * 8 + 5]),
-                                  pack_bf16(v[h8 * 8 + 6], v[h8 * 8 + 7]));
-            *reinterpret_cast<uint4*>(sT + sw128_off(r, c0 + h8 * 8, a_blk)) = pk;
-          }
+          put16<SP>(sT, to_lo, r, c0, a_blk, v);
         }
       }
     }
@@ -457,10 +462,16 @@ rowmlp_tc_dgrad_kernel(const __grid_constant__ KParams p, const __grid_constant_
         const uint32_t kb = ks >> 2, kin = (ks & 3) * 32;
         umma_bf16(tY, make_desc_k_sw128(a0 + kb * a_blk + kin),
                   make_desc_mn_sw128(w0 + (uint32_t)ks * 2048u, lbo), idesc3, ks > 0);
+        if (SP) {
+          umma_bf16(tY, make_desc_k_sw128(a0 + kb * a_blk + kin),
+                    make_desc_mn_sw128(w0 + w2_lo + (uint32_t)ks * 2048u, lbo), idesc3, 1u);
+          umma_bf16(tY, make_desc_k_sw128(a0 + to_lo + kb * a_blk + kin),
+                    make_desc_mn_sw128(w0 + (uint32_t)ks * 2048u, lbo), idesc3, 1u);
+        }
       }
       umma_commit(&bars[0]);
     }
-    copy_tile_out<TNT>(sT, g.dy_img + (size_t)t * kbo * a_blk, kbo * a_blk);
+    copy_tile_out<TNT>(sT, g.dy_img + (size_t)t * P * kbo * a_blk, P * kbo * a_blk);
     mbar_wait(&bars[0], ph_main);
     ph_main ^= 1;
     tc_fence_after();
@@ -478,23 +489,16 @@ rowmlp_tc_dgrad_kernel(const __grid_constant__ KParams p, const __grid_constant_
           tmem_ld16(tH + lane_addr + (uint32_t)c0, h);
 #pragma unroll
           for (int j = 0; j < 16; ++j)
-            v[j] = (F || c0 + j < dh) ? v[j] * silu_grad_fast(h[j] + sPar[c0 + j]) : 0.f;
+            v[j] = (F || c0 + j < dh) ? v[j] * silu_grad_sel<SP>(h[j] + sPar[c0 + j]) : 0.f;
           acc_db1[ci] += warp_colsum16(v, lane);
-#pragma unroll
-          for (int h8 = 0; h8 < 2; ++h8) {
-            uint4 pk = make_uint4(pack_bf16(v[h8 * 8 + 0], v[h8 * 8 + 1]),
-                                  pack_bf16(v[h8 * 8 + 2], v[h8 * 8 + 3]),
-                                  pack_bf16(v[h8 * 8 + 4], v[h8 * 8 + 5]),
-                                  pack_bf16(v[h8 * 8 + 6], v[h8 * 8 + 7]));
-            *reinterpret_cast<uint4*>(sT + sw128_off(r, c0 + h8 * 8, a_blk)) = pk;
-          }
+          put16<SP>(sT, t2_lo, r, c0, a_blk, v);
         }
       }
     }
     fence_async_smem();
     tc_fence_before();
     __syncthreads();
-    copy_tile_out<TNT>(sT, g.dh_img + (size_t)t * kb2 * a_blk, kb2 * a_blk);
+    copy_tile_out<TNT>(sT, g.dh_img + (size_t)t * P * kb2 * a_blk, P * kb2 * a_blk);
 
     // ---------------- GEMM 4 + epilogue 4: dZ = dH . W1, 64 input columns at a time
     if (g.need_dz) {
@@ -506,6 +510,13 @@ rowmlp_tc_dgrad_kernel(const __grid_constant__ KParams p, const __grid_constant_
           const uint32_t kbb = ks >> 2, kin = (ks & 3) * 32;
           umma_bf16(tZ + (uint32_t)(kb & 1) * 64u, make_desc_k_sw128(a0 + kbb * a_blk + kin),
                     make_desc_mn_sw128(w0 + (uint32_t)ks * 2048u, 0), idesc4, ks > 0);
+          if (SP) {
+            umma_bf16(tZ + (uint32_t)(kb & 1) * 64u, make_desc_k_sw128(a0 + kbb * a_blk + kin),
+                      make_desc_mn_sw128(w0 + w1_lo + (uint32_t)ks * 2048u, 0), idesc4, 1u);
+            umma_bf16(tZ + (uint32_t)(kb & 1) * 64u,
+                      make_desc_k_sw128(a0 + t2_lo + kbb * a_blk + kin),
+                      make_desc_mn_sw128(w0 + (uint32_t)ks * 2048u, 0), idesc4, 1u);
+          }
         }
         umma_commit(&bars[1 + (kb & 1)]);
       };
@@ -639,7 +650,7 @@ rowmlp_tc_dgrad_kernel(const __grid_constant__ KParams p, const __grid_constant_
 }
 
 // -------------------------------------------------------------------- wgrad
-template <int FN, bool FG, int TNT>
+template <int FN, bool FG, int TNT, bool SP = false>
 __global__ void __launch_bounds__(TNT, TNT == 256 ? 2 : 1)
 rowmlp_tc_wgrad_kernel(const __grid_constant__ KParams p, const __grid_constant__ BGeo g) {
   constexpr bool F = FN > 0;
@@ -668,6 +679,8 @@ rowmlp_tc_wgrad_kernel(const __grid_constant__ KParams p, const __grid_constant_
   const uint32_t tW2 = tmem_base + (uint32_t)(g.w_mchunks * n1);
   uint32_t ph = 0;
   const uint32_t a_blk = TM * 128u;
+  constexpr uint32_t P = SP ? 2u : 1u;
+  const uint32_t z_lo = (uint32_t)g.kb1 * a_blk, t2_lo = (uint32_t)kb2 * a_blk, to_lo = (uint32_t)kbo * a_blk;
   const uint32_t idesc_w1 = make_idesc_bf16(TM, n1, 1, 1);
   const uint32_t idesc_w2 = make_idesc_bf16(TM, n2, 1, 1);
   const int q = warp & 3, hf = warp >> 2, r = q * 32 + lane;
@@ -722,7 +735,7 @@ rowmlp_tc_wgrad_kernel(const __grid_constant__ KParams p, const __grid_constant_
     __syncthreads();
   };
 
-  constexpr bool PIPE = F && FG && FN == 64;
+  constexpr bool PIPE = F && FG && FN == 64 && TNT == 256 && !SP;
   int nidx[NLAM_MAX_SRC] = {-1, -1, -1};
   if (PIPE && (int)blockIdx.x < g.total_tiles) {
     int r0, c0, ch0;
@@ -743,13 +756,13 @@ rowmlp_tc_wgrad_kernel(const __grid_constant__ KParams p, const __grid_constant_
       const int cidx[NLAM_MAX_SRC] = {nidx[0], nidx[1], nidx[2]};
       gather_rows_pipe<64, TNT>(p, b, cidx, sZ, tid);
     } else if (F && FG) {
-      gather_rows_fast<(F ? FN : 64), TNT>(p, b, row0, cnt, 0, p.d.n_src, sZ);
+      gather_rows_fast<(F ? FN : 64), TNT, SP>(p, b, row0, cnt, 0, p.d.n_src, sZ, z_lo);
     } else {
-      gather_rows<TNT>(p, b, row0, cnt, 0, g.k1, sZ);
+      gather_rows<TNT, SP>(p, b, row0, cnt, 0, g.k1, sZ, z_lo);
     }
-    copy_tile_in<TNT>(g.a_img + (size_t)t * kb2 * a_blk, sAi, kb2 * a_blk);
-    copy_tile_in<TNT>(g.dy_img + (size_t)t * kbo * a_blk, sDY, kbo * a_blk);
-    copy_tile_in<TNT>(g.dh_img + (size_t)t * kb2 * a_blk, sDH, kb2 * a_blk);
+    copy_tile_in<TNT>(g.a_img + (size_t)t * P * kb2 * a_blk, sAi, P * kb2 * a_blk);
+    copy_tile_in<TNT>(g.dy_img + (size_t)t * P * kbo * a_blk, sDY, P * kbo * a_blk);
+    copy_tile_in<TNT>(g.dh_img + (size_t)t * P * kb2 * a_blk, sDH, P * kb2 * a_blk);
     {  // L2 prefetch of the next tile's rows and bf16 tile images
       const int tn = t + gridDim.x;
       if (tn < g.total_tiles) {
@@ -761,13 +774,13 @@ rowmlp_tc_wgrad_kernel(const __grid_constant__ KParams p, const __grid_constant_
         } else {
           prefetch_sources(p, tn % p.d.batch, r0n, cn);
         }
-        const int li = (int)(kb2 * a_blk) >> 7, lo = (int)(kbo * a_blk) >> 7;
+        const int li = (int)(P * kb2 * a_blk) >> 7, lo = (int)(P * kbo * a_blk) >> 7;
         for (int u = tid; u < li; u += TNT) {
-          prefetch_l2(g.a_img + (size_t)tn * kb2 * a_blk + (size_t)u * 128);
-          prefetch_l2(g.dh_img + (size_t)tn * kb2 * a_blk + (size_t)u * 128);
+          prefetch_l2(g.a_img + (size_t)tn * P * kb2 * a_blk + (size_t)u * 128);
+          prefetch_l2(g.dh_img + (size_t)tn * P * kb2 * a_blk + (size_t)u * 128);
         }
         for (int u = tid; u < lo; u += TNT)
-          prefetch_l2(g.dy_img + (size_t)tn * kbo * a_blk + (size_t)u * 128);
+          prefetch_l2(g.dy_img + (size_t)tn * P * kbo * a_blk + (size_t)u * 128);
       }
     }
     fence_async_smem();
@@ -776,15 +789,29 @@ rowmlp_tc_wgrad_kernel(const __grid_constant__ KParams p, const __grid_constant_
       tc_fence_after();
       const uint32_t z0 = smem_u32(sZ), a0 = smem_u32(sAi), y0 = smem_u32(sDY), h0 = smem_u32(sDH);
       for (int mc = 0; mc < g.w_mchunks; ++mc)
-        for (int ks = 0; ks < TM / 16; ++ks)
-          umma_bf16(tmem_base + (uint32_t)(mc * n1),
-                    make_desc_mn_sw128(z0 + (uint32_t)mc * 2u * a_blk + (uint32_t)ks * 2048u, a_blk),
-                    make_desc_mn_sw128(h0 + (uint32_t)ks * 2048u, a_blk), idesc_w1,
-                    (!first || ks > 0) ? 1u : 0u);
-      for (int ks = 0; ks < TM / 16; ++ks)
-        umma_bf16(tW2, make_desc_mn_sw128(a0 + (uint32_t)ks * 2048u, a_blk),
-                  make_desc_mn_sw128(y0 + (uint32_t)ks * 2048u, a_blk), idesc_w2,
+        for (int ks = 0; ks < TM / 16; ++ks) {
+          const uint32_t za = z0 + (uint32_t)mc * 2u * a_blk + (uint32_t)ks * 2048u;
+          const uint32_t hb = h0 + (uint32_t)ks * 2048u;
+          umma_bf16(tmem_base + (uint32_t)(mc * n1), make_desc_mn_sw128(za, a_blk),
+                    make_desc_mn_sw128(hb, a_blk), idesc_w1, (!first || ks > 0) ? 1u : 0u);
+          if (SP) {
+            umma_bf16(tmem_base + (uint32_t)(mc * n1), make_desc_mn_sw128(za, a_blk),
+                      make_desc_mn_sw128(hb + t2_lo, a_blk), idesc_w1, 1u);
+            umma_bf16(tmem_base + (uint32_t)(mc * n1), make_desc_mn_sw128(za + z_lo, a_blk),
+                      make_desc_mn_sw128(hb, a_blk), idesc_w1, 1u);
+          }
+        }
+      for (int ks = 0; ks < TM / 16; ++ks) {
+        const uint32_t aa = a0 + (uint32_t)ks * 2048u, yb = y0 + (uint32_t)ks * 2048u;
+        umma_bf16(tW2, make_desc_mn_sw128(aa, a_blk), make_desc_mn_sw128(yb, a_blk), idesc_w2,
                   (!first || ks > 0) ? 1u : 0u);
+        if (SP) {
+          umma_bf16(tW2, make_desc_mn_sw128(aa, a_blk), make_desc_mn_sw128(yb + to_lo, a_blk),
+                    idesc_w2, 1u);
+          umma_bf16(tW2, make_desc_mn_sw128(aa + t2_lo, a_blk), make_desc_mn_sw128(yb, a_blk),
+                    idesc_w2, 1u);
+        }
+      }
       umma_commit(&bars[0]);
     }
     first = false;
@@ -807,6 +834,8 @@ static int pow2_cols(int c) {
 
 static int make_bgeo(const KParams& p, BGeo& g) {
   const nlam_rowmlp& d = p.d;
+  const uint32_t P = p.split ? 2u : 1u;  // operand tiles: hi (+ lo), see rowmlp_tc.cuh put8
+  g.parts = (int)P;
   g.n1 = pad_n(d.d_hidden), g.n2 = pad_n(d.d_out);
   g.nmax = g.n1 > g.n2 ? g.n1 : g.n2;
   g.k1 = (p.k_total + 15) / 16 * 16;
@@ -816,19 +845,20 @@ static int make_bgeo(const KParams& p, BGeo& g) {
   // z blocks gathered per GEMM-1 round (the fast gather works on whole sources: 2 blocks each
   // at d = 128, where the 64 KB staging region takes two sources per round)
   g.rb = (fast_n(p) == 128 && fast_gather(p)) ? (option_rb128() == 2 ? 2 : 4) : 3;
+  if (p.split) g.rb = 2;  // hi + lo of two blocks = the 64 KB the fp32 staging tile may need
   g.cY = g.n1, g.cZ = g.n1 + g.nmax;
   g.tmem_cols = pow2_cols(g.cZ + 128);
   const uint32_t blk = TM * 128u;
   const int rb = g.kb1 < g.rb ? g.kb1 : g.rb;
-  uint32_t r0 = (uint32_t)rb * blk;
+  uint32_t r0 = P * (uint32_t)rb * blk;
   const uint32_t stg_bytes = (uint32_t)TM * (g.n2 > 64 ? g.n2 : 64) * 4u;
   if (stg_bytes > r0) r0 = stg_bytes;
   auto al = [](uint32_t x) { return (x + 1023u) & ~1023u; };
   uint32_t o = al(r0);
   const int kbt = g.kb2 > g.kbo ? g.kb2 : g.kbo;
-  g.off_t = o, o += (uint32_t)kbt * blk;
-  g.off_w1 = o, o += al((uint32_t)g.kb1 * g.n1 * 128u);
-  g.off_w2 = o, o += al((uint32_t)g.kb2 * g.n2 * 128u);
+  g.off_t = o, o += P * (uint32_t)kbt * blk;
+  g.off_w1 = o, o += al(P * (uint32_t)g.kb1 * g.n1 * 128u);
+  g.off_w2 = o, o += al(P * (uint32_t)g.kb2 * g.n2 * 128u);
   g.off_par = o, o += (uint32_t)(g.n1 + 2 * g.n2) * 4u;
   g.off_lnx = o, o += (uint32_t)TM * 2u * 4u;  // [TM][2] (see row_allsum)
   g.off_bar = o, o += 64;
@@ -840,10 +870,10 @@ static int make_bgeo(const KParams& p, BGeo& g) {
   // wgrad
   g.w_mchunks = (g.kb1 + 1) / 2;
   g.w_tmem_cols = pow2_cols(g.w_mchunks * g.n1 + g.n2);
-  o = (uint32_t)g.kb1 * blk;
-  g.w_off_a = o, o += (uint32_t)g.kb2 * blk;
-  g.w_off_dy = o, o += (uint32_t)g.kbo * blk;
-  g.w_off_dh = o, o += (uint32_t)g.kb2 * blk;
+  o = P * (uint32_t)g.kb1 * blk;
+  g.w_off_a = o, o += P * (uint32_t)g.kb2 * blk;
+  g.w_off_dy = o, o += P * (uint32_t)g.kbo * blk;
+  g.w_off_dh = o, o += P * (uint32_t)g.kb2 * blk;
   o += blk;  // MN-major M=128 views may run one (ignored) block past a tile
   g.w_off_bar = o, o += 64;
   g.w_smem_bytes = o;
@@ -852,6 +882,11 @@ static int make_bgeo(const KParams& p, BGeo& g) {
              "rowmlp_bwd(bf16): %u / %u bytes of shared memory, %d / %d TMEM columns", g.smem_bytes,
              g.w_smem_bytes, g.tmem_cols, g.w_tmem_cols);
   return 0;
+}
+
+int make_bgeo_probe(const KParams& p) {
+  BGeo g{};
+  return make_bgeo(p, g);
 }
 
 static int grid_for(uint32_t smem, int tmem_cols, int total_tiles) {
@@ -875,7 +910,7 @@ static int wgrad_grid(const BGeo& g) {
 static bool use_dgrad_mc(const KParams& p, const BGeo& g) {
   // default off: in the full train step the two-CTA kernel is ~1 % faster (B200, MEPS)
   const int env = option_dgrad_mc();
-  if (env == 0) return false;
+  if (env == 0 || p.split) return false;
   if (!tc_dgrad_mc_supported(p, g)) return false;
   // measured: +4 % on the 3-source edge MLPs, -6 % on the 2-source node MLP
   return env > 0 || (g.total_tiles > 296 && p.d.n_src == 3);
@@ -884,7 +919,7 @@ static bool use_dgrad_mc(const KParams& p, const BGeo& g) {
 // one kernel for input and weight gradients (rowmlp_tc_bwd_fused.cu): square 64-wide MLPs
 // `need_dz`: -1 unknown (workspace sizing), else whether a source gradient is requested
 static bool use_bwd_fused(const KParams& p, int need_dz) {
-  if (option_bwd_fused() == 0) return false;
+  if (option_bwd_fused() == 0 || p.split) return false;
   const int kind = tc_bwd_fused_kind(p);
   return kind == 2 || (kind == 1 && need_dz == 0);
 }
@@ -899,9 +934,9 @@ static TcBwdWs tc_bwd_ws(const KParams& p, const BGeo& g, bool fused) {
   const size_t blk_f = TM * 128 / 4;  // floats per 16 KB block
   size_t o = 0;
   // fused: no bf16 tile images, one partial slot per CTA
-  w.a_img = o, o += fused ? 0 : al((size_t)g.total_tiles * g.kb2 * blk_f);
-  w.dy_img = o, o += fused ? 0 : al((size_t)g.total_tiles * g.kbo * blk_f);
-  w.dh_img = o, o += fused ? 0 : al((size_t)g.total_tiles * g.kb2 * blk_f);
+  w.a_img = o, o += fused ? 0 : al((size_t)g.total_tiles * g.parts * g.kb2 * blk_f);
+  w.dy_img = o, o += fused ? 0 : al((size_t)g.total_tiles * g.parts * g.kbo * blk_f);
+  w.dh_img = o, o += fused ? 0 : al((size_t)g.total_tiles * g.parts * g.kb2 * blk_f);
   w.d_slots = fused ? (p.src0_batch_sum ? tc_bwd_fused_grid_bsum(g) : tc_bwd_fused_grid(g))
               : use_dgrad_mc(p, g) ? tc_dgrad_mc_grid(g)
                                    : grid_for(g.smem_bytes, g.tmem_cols, g.total_tiles);
@@ -917,6 +952,7 @@ static TcBwdWs tc_bwd_ws(const KParams& p, const BGeo& g, bool fused) {
 bool tc_rowmlp_bwd_is_fused(const nlam_rowmlp_bwd& bd) {
   KParams p{};
   if (fill_params(bd.fwd, p)) return false;
+  p.split = bd.fwd.precision == NLAM_FP32;
   int need_dz = 0;
   for (int s = 0; s < bd.fwd.n_src; ++s) need_dz |= bd.d_src[s] != nullptr;
   return tc::use_bwd_fused(p, need_dz);
@@ -925,6 +961,7 @@ bool tc_rowmlp_bwd_is_fused(const nlam_rowmlp_bwd& bd) {
 size_t tc_rowmlp_bwd_workspace(const nlam_rowmlp& d) {
   KParams p{};
   if (fill_params(d, p)) return 0;
+  p.split = d.precision == NLAM_FP32;
   tc::BGeo g{};
   if (tc::make_bgeo(p, g)) return 0;
   // the kernel choice may depend on which gradients the run asks for: size for either
@@ -941,6 +978,7 @@ int tc_rowmlp_bwd(const nlam_rowmlp_bwd& bd, cudaStream_t st) {
   const nlam_rowmlp& d = bd.fwd;
   KParams p{};
   if (fill_params(d, p)) return 1;
+  p.split = d.precision == NLAM_FP32;  // fp32 operands: split bf16 tiles, 3 UMMAs per product
   NLAM_CHECK(bd.d_params, "rowmlp_bwd: d_params is NULL");
   if (d.rows == 0) {
     if (!bd.params_accumulate)
@@ -1045,7 +1083,9 @@ int tc_rowmlp_bwd(const nlam_rowmlp_bwd& bd, cudaStream_t st) {
              : launch(tc::rowmlp_tc_dgrad_kernel<FNV, FGV, TN>, TN, gd, g.smem_bytes);      \
   if (!rc && (mask & 2))                                                                    \
     rc = launch(tc::rowmlp_tc_wgrad_kernel<FNV, FGV, TN>, TN, gw, g.w_smem_bytes);
-  if (fn == 64 && fg) {
+  if (p.split) {
+    rc = 0;
+  } else if (fn == 64 && fg) {
     NLAM_BWD_PAIR(64, true, 256)
   } else if (fn == 64) {
     NLAM_BWD_PAIR(64, false, 256)
@@ -1063,6 +1103,28 @@ int tc_rowmlp_bwd(const nlam_rowmlp_bwd& bd, cudaStream_t st) {
     NLAM_BWD_PAIR(0, false, 256)
   }
 #undef NLAM_BWD_PAIR
+#define NLAM_BWD_PAIR_SP(FNV, FGV, TN)                                                          \
+  rc = 0;                                                                                       \
+  if (mask & 1) rc = launch(tc::rowmlp_tc_dgrad_kernel<FNV, FGV, TN, true>, TN, gd, g.smem_bytes); \
+  if (!rc && (mask & 2))                                                                        \
+    rc = launch(tc::rowmlp_tc_wgrad_kernel<FNV, FGV, TN, true>, TN, gw, g.w_smem_bytes);
+  if (p.split) {  // same thread count for both kernels (the column-sum layout depends on it)
+    const bool w = g.smem_bytes > 113 * 1024 && g.w_smem_bytes > 113 * 1024;
+    if (fn == 64 && fg && w) {
+      NLAM_BWD_PAIR_SP(64, true, 512)
+    } else if (fn == 64 && fg) {
+      NLAM_BWD_PAIR_SP(64, true, 256)
+    } else if (fn == 64 && w) {
+      NLAM_BWD_PAIR_SP(64, false, 512)
+    } else if (fn == 64) {
+      NLAM_BWD_PAIR_SP(64, false, 256)
+    } else if (w) {
+      NLAM_BWD_PAIR_SP(0, false, 512)
+    } else {
+      NLAM_BWD_PAIR_SP(0, false, 256)
+    }
+  }
+#undef NLAM_BWD_PAIR_SP
   if (rc) return rc;
   if (!(mask & 4)) return 0;
   return launch_reduce_params(g.partial, ws.w_slots, d.n_chunks, g.p_total, bd.d_params,

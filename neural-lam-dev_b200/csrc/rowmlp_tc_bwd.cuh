@@ -14,6 +14,7 @@ struct BGeo {
   uint32_t off_t, off_w1, off_w2, off_par, off_lnx, off_bar, smem_bytes;
   int total_tiles, tiles_per_batch;
   int need_dz;           // any source gradient requested
+  int parts;             // 1 = bf16 operands, 2 = fp32 operands split into bf16 hi + lo tiles
   // scratch
   uint8_t* a_img;
   uint8_t* dy_img;
