@@ -508,22 +508,28 @@ def run_ours(a):
             layers = layer_edges_per_s(model, a.batch, device, peaks)
         if a.precision == "bf16" and is_default_case(a) and not a.no_fp32_line:
             # the fp32 half of configs[1] ("bf16/fp32"): same model, weights and batches in
-            # the fp32 parity mode (FFMA kernels, rtol 1e-4 vs the reference), eager steps
+            # the fp32 parity mode (rtol 1e-4 outputs / 1e-3 gradients vs the reference): fp32
+            # operands as split bf16 tiles on the tensor cores, three UMMAs per product
+            # (NLAM_FP32_SPLIT=0: the FFMA kernels); same CUDA-graph trainer as the headline
             ops.set_precision("fp32")
-            tr32 = train.DataParallelTrainer(model, rank, world, use_cuda_graph=False)
-            for i in range(2):
+            tr32 = train.DataParallelTrainer(model, rank, world, use_cuda_graph=bool(a.cuda_graph))
+            for i in range(4):
                 tr32.step(dev_batches[i % n_rot])
             torch.cuda.synchronize()
+            l0 = L.nlam_launch_count()
             e0.record()
-            n32 = 4
+            n32 = 10
             for i in range(n32):
                 l32 = tr32.step(dev_batches[i % n_rot])
             e1.record()
             torch.cuda.synchronize()
             ms32 = e0.elapsed_time(e1) / n32
+            fam = ops.kernel_family((a.hidden_dim,) * 3, a.hidden_dim, a.hidden_dim, "fp32")
             fp32_mode = {"value": a.batch / (ms32 / 1e3), "unit": UNIT, "ms_per_step": ms32,
                          "steps": n32, "dtype": "f32", "loss": float(l32.item()),
-                         "note": "fp32 parity mode (FFMA row-MLP kernels), eager, device-resident"}
+                         "kernels": "tcgen05, split bf16 operands (3 UMMAs per product)"
+                                    if fam == 2 else "fp32 FFMA",
+                         "note": "fp32 parity mode, device-resident batches"}
             ops.set_precision(a.precision)
 
     cpu = None

@@ -35,7 +35,8 @@ extern "C" {
 #define NLAM_TILE_ROWS 64 /* rows of a row-MLP tile (chunk tables use it) */
 
 /* precision modes */
-#define NLAM_FP32 0 /* fp32 FFMA everywhere (parity mode, rtol 1e-4) */
+#define NLAM_FP32 0 /* fp32 parity mode (rtol 1e-4): tcgen05 with split bf16 operands where the
+                       tiles fit (nlam_rowmlp_path == 2), fp32 FFMA kernels elsewhere */
 #define NLAM_BF16 1 /* bf16 tcgen05 MMA, fp32 accumulate/storage (2e-2)  */
 
 /* One gathered input of a row-MLP: row r of batch b is
@@ -267,7 +268,10 @@ int nlam_version(void);
  * previous one (every kernel waits with griddepcontrol.wait before reading its inputs).
  * "tma" (default 0, env NLAM_TMA): forward edge kernel whose operands arrive by
  * cp.async.bulk.tensor tile::gather4 from the bf16 shadows; "bwd_nh" (default 2, env
- * NLAM_BWD_NH): threads per tile row of the fused backward kernel (2 or 4). */
+ * NLAM_BWD_NH): threads per tile row of the fused backward kernel (2 or 4).  "wide128"
+ * (default 1, env NLAM_WIDE128): 512-thread CTAs for the d = 128 kernels.  "fp32_split"
+ * (default 1, env NLAM_FP32_SPLIT): precision NLAM_FP32 on the tcgen05 kernels with split
+ * bf16 operands where the tiles fit (see nlam_rowmlp_path); 0 = fp32 FFMA kernels. */
 int nlam_set_option(const char* name, int value);
 /* Number of kernels this library has launched in this process (monotonic;
  * bench.py reports the delta over its timed region as "gpu_launches"). */
@@ -282,6 +286,15 @@ int nlam_csr_build(const int32_t* key, int64_t n_edges, int32_t n_keys, int32_t*
                    int32_t* perm, float* inv_deg, int32_t* workspace, void* stream);
 
 int nlam_rowmlp_fwd(const nlam_rowmlp* desc, void* stream);
+/* Kernel family nlam_rowmlp_fwd / nlam_rowmlp_bwd_run take for this descriptor: 0 = fp32
+ * FFMA kernels; 1 = bf16 tcgen05 kernels (precision NLAM_BF16); 2 = precision NLAM_FP32 on
+ * the tcgen05 kernels -- every fp32 operand is held as two bf16 tiles (hi = bf16(x), lo =
+ * bf16(x - hi)) and every product is three UMMAs into one fp32 accumulator, ~16 mantissa
+ * bits; taken when the doubled tiles fit shared memory (all d_hidden <= 64 shapes of the
+ * models) and option "fp32_split" (default 1, env NLAM_FP32_SPLIT) is on.  Families 1 and 2
+ * support fused aggregation / row scatter (agg, out_idx, reduce_src ...), family 0 does not.
+ * Only widths, alignment and precision of the descriptor are inspected. */
+int nlam_rowmlp_path(const nlam_rowmlp* desc);
 size_t nlam_rowmlp_bwd_workspace(const nlam_rowmlp* desc);
 size_t nlam_rowmlp_param_floats(const nlam_rowmlp* desc); /* per chunk */
 /* Kernels nlam_rowmlp_bwd_run launches for this descriptor: 3 = input gradients,

@@ -37,10 +37,20 @@ def load_checkpoint(model, path_or_dict, optimizer=None, map_location="cpu"):
     return ckpt
 
 
-def save_checkpoint(model, path, optimizer=None, **extra):
-    """Write a checkpoint with the reference's layout (`state_dict`,
-    `optimizer_states`), loadable by either code base."""
-    ckpt = {"state_dict": {k: v.detach().cpu() for k, v in model.state_dict().items()}}
+def save_checkpoint(model, path, optimizer=None, epoch=0, global_step=0, **extra):
+    """Write `state_dict` / `optimizer_states` under the key names of the reference's
+    (Lightning) checkpoints, plus the bookkeeping keys Lightning's loader reads first
+    (`pytorch-lightning_version`, `epoch`, `global_step`, `lr_schedulers`).
+
+    Interop is one-directional by design: reference checkpoints load here
+    (`load_checkpoint`), and the reference can take these weights with
+    `model.load_state_dict(torch.load(path)["state_dict"])`.  A full Lightning resume
+    (`trainer.fit(ckpt_path=...)`) additionally wants `loops`, `callbacks` and
+    `hyper_parameters`, which only a Lightning trainer can produce; they are not written
+    (the trainer and its callbacks are out of scope)."""
+    ckpt = {"state_dict": {k: v.detach().cpu() for k, v in model.state_dict().items()},
+            "pytorch-lightning_version": "2.0.0", "epoch": int(epoch),
+            "global_step": int(global_step), "lr_schedulers": []}
     if optimizer is not None:
         ckpt["optimizer_states"] = [optimizer.state_dict()]
     ckpt.update(extra)

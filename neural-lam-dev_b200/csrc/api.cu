@@ -95,6 +95,13 @@ extern "C" int nlam_rowmlp_fwd(const nlam_rowmlp* d, void* stream) {
   return 1;
 }
 
+extern "C" int nlam_rowmlp_path(const nlam_rowmlp* d) {
+  if (!d) return 0;
+  if (d->precision == NLAM_BF16) return tc::tc_supported(*d) ? 1 : 0;
+  if (d->precision == NLAM_FP32) return tc::tc_split_supported(*d) ? 2 : 0;
+  return 0;
+}
+
 extern "C" size_t nlam_rowmlp_bwd_workspace(const nlam_rowmlp* d) {
   if (!d) return 0;
   if (d->precision == NLAM_BF16 && tc::tc_supported(*d)) return tc_rowmlp_bwd_workspace(*d);

@@ -160,6 +160,7 @@ SYMBOLS = {
     "nlam_rowmlp_fwd": (ctypes.c_int, [ctypes.POINTER(RowMlp), ctypes.c_void_p]),
     "nlam_rowmlp_bwd_workspace": (ctypes.c_size_t, [ctypes.POINTER(RowMlp)]),
     "nlam_rowmlp_param_floats": (ctypes.c_size_t, [ctypes.POINTER(RowMlp)]),
+    "nlam_rowmlp_path": (ctypes.c_int, [ctypes.POINTER(RowMlp)]),
     "nlam_rowmlp_bwd_stages": (ctypes.c_int, [ctypes.POINTER(RowMlpBwd)]),
     "nlam_rowmlp_bwd_run": (ctypes.c_int, [ctypes.POINTER(RowMlpBwd), ctypes.c_void_p]),
     "nlam_rowmlp_bwd_flush": (ctypes.c_int, [ctypes.c_void_p]),

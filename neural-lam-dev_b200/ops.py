@@ -875,12 +875,32 @@ def split_mlp_forward(module, x):
     return out.reshape(*lead, blocks[-1].d_out)
 
 
+def kernel_family(widths, d_hidden, d_out, precision):
+    """nlam_rowmlp_path for an MLP over sources of these widths: 0 = fp32 FFMA kernels, 1 =
+    bf16 tcgen05, 2 = fp32 on tcgen05 (split bf16 operands).  Only widths matter."""
+    lib = L.load()
+    desc = L.RowMlp()
+    desc.n_src = len(widths)
+    for i, w in enumerate(widths):
+        desc.src[i].ptr, desc.src[i].width, desc.src[i].ld = 256, w, w  # (never dereferenced)
+    desc.batch, desc.rows, desc.n_chunks, desc.residual_src = 1, 128, 1, -1
+    desc.d_hidden, desc.d_out, desc.precision = d_hidden, d_out, _PREC[precision]
+    return lib.nlam_rowmlp_path(ctypes.byref(desc))
+
+
 def _use_aligned(plan, We, Wa, precision):
-    """Fused-aggregation path: bf16 tensor-core kernels, square d in {64, 128},
-    one weight set, and a graph whose in-degrees fit a 128-row tile."""
-    return (precision == "bf16" and plan.alignable and We.n_chunks == 1 and Wa.n_chunks == 1
+    """Fused-aggregation path: tensor-core kernels (bf16, or the fp32 split mode where its
+    tiles fit), square d in {64, 128}, one weight set, and a graph whose in-degrees fit a
+    128-row tile."""
+    if not (plan.alignable and We.n_chunks == 1 and Wa.n_chunks == 1
             and We.d_hidden == We.d_out and We.d_out in (64, 128) and We.k == 3 * We.d_out
-            and not _state.get("disable_aligned", False))
+            and not _state.get("disable_aligned", False)):
+        return False
+    if precision == "bf16":
+        return True
+    d = We.d_out
+    return (kernel_family((d, d, d), d, d, precision) == 2
+            and kernel_family((d, d), Wa.d_hidden, Wa.d_out, precision) == 2)
 
 
 class _InteractionNetFn(torch.autograd.Function):
