@@ -760,9 +760,10 @@ rowmlp_tc_wgrad_kernel(const __grid_constant__ KParams p, const __grid_constant_
     } else {
       gather_rows<TNT, SP>(p, b, row0, cnt, 0, g.k1, sZ, z_lo);
     }
-    copy_tile_in<TNT>(g.a_img + (size_t)t * P * kb2 * a_blk, sAi, P * kb2 * a_blk);
-    copy_tile_in<TNT>(g.dy_img + (size_t)t * P * kbo * a_blk, sDY, P * kbo * a_blk);
-    copy_tile_in<TNT>(g.dh_img + (size_t)t * P * kb2 * a_blk, sDH, P * kb2 * a_blk);
+    constexpr int CU = (SP && TNT == 512) ? 4 : 2;  // split tiles are multiples of 32 KB
+    copy_tile_in<TNT, CU>(g.a_img + (size_t)t * P * kb2 * a_blk, sAi, P * kb2 * a_blk);
+    copy_tile_in<TNT, CU>(g.dy_img + (size_t)t * P * kbo * a_blk, sDY, P * kbo * a_blk);
+    copy_tile_in<TNT, CU>(g.dh_img + (size_t)t * P * kb2 * a_blk, sDH, P * kb2 * a_blk);
     {  // L2 prefetch of the next tile's rows and bf16 tile images
       const int tn = t + gridDim.x;
       if (tn < g.total_tiles) {

@@ -84,17 +84,18 @@ __device__ __forceinline__ void copy_tile_out(const uint8_t* s, uint8_t* g, int 
     for (int j = 0; j < 2; ++j) dst[i + j * TNT] = v[j];
   }
 }
-template <int TNT = NT>
+template <int TNT = NT, int U = 2>
 __device__ __forceinline__ void copy_tile_in(const uint8_t* g, uint8_t* s, int bytes) {
-  // 16 KB blocks (1024 chunks): 2 independent 128-bit loads per thread in flight
+  // blocks of U * TNT chunks (16 KB; 32 KB for the split-mode tiles of a 512-thread CTA):
+  // U independent 128-bit loads per thread in flight
   const uint4* src = reinterpret_cast<const uint4*>(g);
   uint4* dst = reinterpret_cast<uint4*>(s);
-  for (int i = threadIdx.x; i < bytes / 16; i += 2 * TNT) {
-    uint4 v[2];
+  for (int i = threadIdx.x; i < bytes / 16; i += U * TNT) {
+    uint4 v[U];
 #pragma unroll
-    for (int j = 0; j < 2; ++j) v[j] = __ldg(src + i + j * TNT);
+    for (int j = 0; j < U; ++j) v[j] = __ldg(src + i + j * TNT);
 #pragma unroll
-    for (int j = 0; j < 2; ++j) dst[i + j * TNT] = v[j];
+    for (int j = 0; j < U; ++j) dst[i + j * TNT] = v[j];
   }
 }
 

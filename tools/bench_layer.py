@@ -18,9 +18,12 @@ from neural_lam_b200.interaction_net import InteractionNet  # noqa: E402
 def main():
     which = sys.argv[1] if len(sys.argv) > 1 else "m2g"
     red = {"sp": 1, "bs": 0}
+    prec = "bf16"
     for kv in sys.argv[2:]:
         k, v = kv.split("=")
-        if k in red:
+        if k == "prec":  # prec=fp32 [fp32_split=0]
+            prec = v
+        elif k in red:
             red[k] = int(v)
         else:
             lib.load().nlam_set_option(k.encode(), int(v))
@@ -36,17 +39,18 @@ def main():
           "m2m": graph["m2m_edge_index"]}[which]
     if isinstance(ei, (list, tuple)):
         ei = ei[0]
-    ops.set_precision("bf16")
+    ops.set_precision(prec)
     torch.manual_seed(0)
     net = InteractionNet(ei.clone(), d, update_edges=(which == "m2m")).to(dev)
     M = ei.shape[1]
     n_rec = int(net.num_rec)
     n_send = int(ei[0].max() - ei[0].min()) + 1
-    mk = lambda *s: ops.make_shadow(torch.randn(*s, device=dev).requires_grad_())
+    mk = lambda *s: ((ops.make_shadow if prec == "bf16" else (lambda x: x))(
+        torch.randn(*s, device=dev).requires_grad_()))
     rec = mk(B, n_rec, d)
     send = rec if which == "m2m" else mk(B, n_send, d)
     edge = mk(B, M, d) if which == "m2m" else ops.expand_with_shadow(mk(M, d), B)
-    print(f"{which}: M={M} n_send={n_send} n_rec={n_rec} B={B}")
+    print(f"{which} {prec}: M={M} n_send={n_send} n_rec={n_rec} B={B}")
     for mode in ("fwd", "fwd+bwd"):
         ts = []
         for it in range(13):
