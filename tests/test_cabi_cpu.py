@@ -62,3 +62,25 @@ def test_state_dict_keys_match_reference_contract(built):
     keys = list(net.state_dict())
     assert "edge_mlp.mlps.1.2.weight" in keys and "aggr_mlp.mlps.0.3.bias" in keys
     assert "edge_index" not in keys  # non-persistent buffer
+
+
+def test_kernel_family_selection(built):
+    """nlam_rowmlp_path is host arithmetic (widths, shared-memory budgets): which kernel family
+    takes an MLP in each precision mode, and that option fp32_split switches the fp32 mode
+    between the split-operand tensor-core kernels and the FFMA kernels."""
+    from neural_lam_b200 import ops
+    fam = ops.kernel_family
+    assert fam((64, 64, 64), 64, 64, "bf16") == 1 and fam((128,) * 3, 128, 128, "bf16") == 1
+    # fp32 on the tensor cores: every d = 64 shape of the models, narrow embedder inputs, the
+    # d_out = 17 output map; hi + lo tiles of a d = 128 MLP do not fit shared memory -> FFMA
+    assert fam((64, 64, 64), 64, 64, "fp32") == 2 and fam((64, 64), 64, 64, "fp32") == 2
+    assert fam((3,), 64, 64, "fp32") == 2 and fam((64,), 64, 17, "fp32") == 2
+    assert fam((16, 16, 16), 16, 16, "fp32") == 2
+    assert fam((128,) * 3, 128, 128, "fp32") == 0 and fam((128, 128), 128, 128, "fp32") == 0
+    l = built.load()
+    try:
+        assert l.nlam_set_option(b"fp32_split", 0) == 0
+        assert fam((64, 64, 64), 64, 64, "fp32") == 0
+    finally:
+        l.nlam_set_option(b"fp32_split", 1)
+    assert l.nlam_set_option(b"no_such_option", 1) == 1
