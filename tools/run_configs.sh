@@ -1,5 +1,6 @@
 #!/bin/bash
-# BASELINE.json configs[2..4] through bench.py at N GPUs of this box:  tools/run_configs.sh N [tag]
+# BASELINE.json configs[2..4] (and with `all` configs[1]) through bench.py at N GPUs of this box:
+#   tools/run_configs.sh N [tag] [all]
 # Writes gpurun_out/bench_<tag>_c{3,4,5}_<N>gpu.json (one JSON line each).
 N=${1:-1}
 TAG=${2:-r2}
@@ -22,6 +23,7 @@ try:
     d=json.load(open('$out.json')); print(round(d['value'],1),'samples/s', round(d['ms_per_step'],2),'ms/step e2e',round(d['e2e']['value'],1))
 except Exception as e: print('no json', e)")"
 }
+if [ "$3" = "all" ]; then run c2; fi  # configs[1], the bench default
 run c3 $C3
 run c4 $C4
 run c5 $C5
