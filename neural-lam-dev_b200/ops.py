@@ -31,7 +31,8 @@ _PREC = {"fp32": L.FP32, "bf16": L.BF16}
 
 
 def set_precision(mode):
-    """'fp32' (FFMA, parity mode) or 'bf16' (tcgen05 MMA, fp32 accumulate)."""
+    """'fp32' (parity mode: tcgen05 with split bf16 operands where the tiles fit, FFMA kernels
+    elsewhere -- see kernel_family) or 'bf16' (tcgen05 MMA, fp32 accumulate)."""
     assert mode in _PREC
     _state["precision"] = mode
 
