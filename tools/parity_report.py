@@ -1,6 +1,9 @@
 """bf16-mode parity report (GPU): this repo's deviation from the reference's fp32 goldens next
 to the reference's OWN bf16-autocast deviation (tests/golden/bf16_yardstick.pt), per quantity.
-    python tools/parity_report.py > profiles/parity_bf16_r2.txt"""
+    python tools/parity_report.py > profiles/parity_bf16_r2.txt
+With `fp32` as argument: the fp32 mode (split-operand tensor-core kernels where they apply, then
+again with option fp32_split = 0 = FFMA kernels) against the same goldens.
+    python tools/parity_report.py fp32 > profiles/parity_fp32_r2.txt"""
 import os
 import sys
 import tempfile
@@ -26,7 +29,43 @@ def rel_l2(a, b):
     return ((a.double() - b.double()).norm() / (b.double().norm() + 1e-30)).item()
 
 
+def fp32_report():
+    from neural_lam_b200 import lib
+    dev = torch.device("cuda:0")
+    MODELS = load_golden("models.pt")
+    meps = load_golden("meps_grads.pt")
+    ops.set_precision("fp32")
+    for split in (1, 0):
+        lib.load().nlam_set_option(b"fp32_split", split)
+        print(f"#### fp32 mode, option fp32_split = {split} "
+              f"({'tcgen05, split bf16 operands where the tiles fit' if split else 'FFMA kernels'})")
+        for name, entry_ in MODELS.items():
+            case = entry_["case"]
+            with tempfile.TemporaryDirectory() as root:
+                ds, args, batch = build_model_case(case, root)
+                model = models.MODELS[case["model"]](args, nl_config.default_config(), ds)
+            model.load_state_dict(entry_["state_dict"])
+            model = model.to(dev)
+            batch = tuple(t.to(dev) for t in batch)
+            loss = model.training_step(batch)
+            loss.backward()
+            want = entry_.get("param_grads") or meps[name]["param_grads"]
+            got = {n: p.grad.detach().float().cpu() for n, p in model.named_parameters()}
+            d = int(getattr(args, "hidden_dim", 0))
+            fam = ops.kernel_family((d, d, d), d, d, "fp32")
+            all_g = torch.cat([got[n].reshape(-1) for n in want])
+            all_w = torch.cat([want[n].reshape(-1) for n in want])
+            worst = max((rel_max(got[n], want[n]), n) for n in want)
+            print(f"== {name} (d={d}, edge-MLP kernel family {fam}): loss "
+                  f"{abs(loss.item() - entry_['loss'].item()) / abs(entry_['loss'].item()):.2e};  "
+                  f"all gradients L2 {rel_l2(all_g, all_w):.2e};  worst parameter max-norm "
+                  f"{worst[0]:.2e} ({worst[1]});  bound 1e-3")
+    lib.load().nlam_set_option(b"fp32_split", 1)
+
+
 def main():
+    if len(sys.argv) > 1 and sys.argv[1] == "fp32":
+        return fp32_report()
     dev = torch.device("cuda:0")
     MODELS = load_golden("models.pt")
     yard = load_golden("bf16_yardstick.pt")["cases"]
