@@ -653,11 +653,17 @@ def rowmlp_bwd_raw(srcs, W, batch, rows, residual, tiles, precision, g0, need_sr
                 (4, f"reduce_params_{precision}|{shape}", 2 * w_bytes, 0),
             )
         else:
+            # two kernels: the a / dY / dH tile images that travel between them through HBM
+            # (`img` bytes per row: bf16, or hi + lo bf16 in the fp32 split mode) are the
+            # implementation's traffic, not the algorithm's
+            algo_d = src_bytes + w_bytes + dout_bytes + (
+                dsrc_bytes if algo_dsrc_bytes is None else algo_dsrc_bytes)
             stages = (
-                (1, f"rowmlp_dgrad_{precision}{agg}|{shape}",
-                 src_bytes + w_bytes + dout_bytes + dsrc_bytes + rows_all * img,
-                 2 * fl if dsrc else fl + fl // 2),
-                (2, f"rowmlp_wgrad_{precision}{agg}|{shape}", src_bytes + rows_all * img, fl),
+                (1, f"rowmlp_dgrad_{precision}{agg}|{shape}", algo_d,
+                 2 * fl if dsrc else fl + fl // 2,
+                 src_bytes + w_bytes + dout_bytes + dsrc_bytes + rows_all * img),
+                (2, f"rowmlp_wgrad_{precision}{agg}|{shape}", src_bytes + w_bytes, fl,
+                 src_bytes + rows_all * img),
                 (4, f"reduce_params_{precision}|{shape}", 2 * w_bytes, 0),
             )
         for mask, tag, nbytes, flops, *impl_b in stages:
