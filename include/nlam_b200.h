@@ -271,7 +271,9 @@ int nlam_version(void);
  * NLAM_BWD_NH): threads per tile row of the fused backward kernel (2 or 4).  "wide128"
  * (default 1, env NLAM_WIDE128): 512-thread CTAs for the d = 128 kernels.  "fp32_split"
  * (default 1, env NLAM_FP32_SPLIT): precision NLAM_FP32 on the tcgen05 kernels with split
- * bf16 operands where the tiles fit (see nlam_rowmlp_path); 0 = fp32 FFMA kernels. */
+ * bf16 operands where the tiles fit (see nlam_rowmlp_path); 0 = fp32 FFMA kernels.
+ * "small512" (default 1, env NLAM_SMALL512): 512-thread forward CTAs for d = 64 launches
+ * of at most 148 tiles (the small levels of the hierarchical meshes). */
 int nlam_set_option(const char* name, int value);
 /* Number of kernels this library has launched in this process (monotonic;
  * bench.py reports the delta over its timed region as "gpu_launches"). */

@@ -449,8 +449,14 @@ int tc_rowmlp_fwd(const nlam_rowmlp& d, cudaStream_t st) {
     count_launch();
     return 0;
   }
-  int rc = fn == 64    ? (fg ? launch(tc::rowmlp_tc_fwd_kernel<64, true, 256>, 256)
-                             : launch(tc::rowmlp_tc_fwd_kernel<64, false, 256>, 256))
+  // launches that cannot fill the SMs anyway (levels >= 1 of the hierarchical meshes): 16
+  // warps per tile, 16 columns of a row per thread -> shorter epilogues on the one tile an
+  // SM gets (option "small512")
+  const bool small = option_small512() != 0 && g.total_tiles <= 148;
+  int rc = fn == 64    ? (small ? (fg ? launch(tc::rowmlp_tc_fwd_kernel<64, true, 512>, 512)
+                                      : launch(tc::rowmlp_tc_fwd_kernel<64, false, 512>, 512))
+                          : fg  ? launch(tc::rowmlp_tc_fwd_kernel<64, true, 256>, 256)
+                                : launch(tc::rowmlp_tc_fwd_kernel<64, false, 256>, 256))
            : fn == 128 ? (wide ? (fg ? launch(tc::rowmlp_tc_fwd_kernel<128, true, 512>, 512)
                                      : launch(tc::rowmlp_tc_fwd_kernel<128, false, 512>, 512))
                                : (fg ? launch(tc::rowmlp_tc_fwd_kernel<128, true, 256>, 256)
