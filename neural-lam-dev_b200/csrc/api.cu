@@ -35,6 +35,8 @@ static std::atomic<int> g_rb128{env_or("NLAM_RB128", 4)};
 int option_rb128() { return g_rb128.load(); }
 static std::atomic<int> g_bwd_nh{env_or("NLAM_BWD_NH", 2)};
 int option_bwd_nh() { return g_bwd_nh.load(); }
+static std::atomic<int> g_bwd_spread{env_or("NLAM_BWD_SPREAD", 1)};
+int option_bwd_spread() { return g_bwd_spread.load(); }
 static std::atomic<int> g_small512{env_or("NLAM_SMALL512", 1)};
 int option_small512() { return g_small512.load(); }
 static std::atomic<int> g_fp32_split{env_or("NLAM_FP32_SPLIT", 1)};
@@ -75,6 +77,7 @@ extern "C" int nlam_set_option(const char* name, int value) {
   if (name && !strcmp(name, "wide128")) return nlam::g_wide128.store(value), 0;
   if (name && !strcmp(name, "fp32_split")) return nlam::g_fp32_split.store(value), 0;
   if (name && !strcmp(name, "small512")) return nlam::g_small512.store(value), 0;
+  if (name && !strcmp(name, "bwd_spread")) return nlam::g_bwd_spread.store(value), 0;
   nlam::set_error("nlam_set_option: unknown option");
   return 1;
 }

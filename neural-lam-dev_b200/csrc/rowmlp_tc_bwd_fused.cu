@@ -900,6 +900,10 @@ int tc_bwd_fused_kind(const KParams& p) {
 }
 
 int tc_bwd_fused_grid(const tc::BGeo& g) {
+  // a launch that cannot fill the SMs anyway (the small levels of the hierarchical meshes) is
+  // pure latency: one tile per CTA, so that no tile shares its SM's issue slots with a second
+  // context (option "bwd_spread")
+  if (option_bwd_spread() != 0 && g.total_tiles <= 148) return g.total_tiles;
   int grid = (g.total_tiles + tc::FU_CTX - 1) / tc::FU_CTX;
   return grid > 148 ? 148 : grid;
 }
