@@ -610,10 +610,47 @@ struct RParams {
   int vec_slots, vec_len;
   ParamLayout lay;
 };
+// Few partial slots (the small launches of the hierarchical models): one thread per output
+// element sums all slots itself, 256 outputs per block -- 8x fewer blocks, no shared memory.
+constexpr int RP_WIDE_MAX = 32;
+__host__ __device__ inline bool rp_wide(const RParams& p) {
+  return p.splits <= RP_WIDE_MAX && p.vec_slots <= RP_WIDE_MAX && p.p_main == p.p_total;
+}
+__host__ __device__ inline int rp_blocks(const RParams& p) {
+  return rp_wide(p) ? (p.p_total + 255) / 256 : (p.p_total + 31) / 32;
+}
+__device__ __forceinline__ int rp_vec_index(const RParams& p, int j) {
+  int v = -1;
+  if (p.vec_partial) {  // is j a bias / LayerNorm-affine entry?
+    const ParamLayout& L = p.lay;
+    if (j >= L.off_b1() && j < L.off_w2()) v = j - L.off_b1();
+    else if (j >= L.off_b2() && j < L.off_b2() + L.d_out) v = L.d_hidden + j - L.off_b2();
+    else if (L.has_ln && j >= L.off_lng()) v = L.d_hidden + L.d_out + j - L.off_lng();
+  }
+  return v;
+}
 __device__ __forceinline__ void reduce_params_block(const RParams& p, int bx, int chunk) {
+  if (rp_wide(p)) {
+    const int j = bx * 256 + threadIdx.x;
+    if (j >= p.p_total) return;
+    const int v = rp_vec_index(p, j);
+    const float* src = v >= 0 ? p.vec_partial + (size_t)chunk * p.vec_len + v
+                              : p.partial + (size_t)chunk * p.p_total + j;
+    const size_t step = (size_t)p.n_chunks * (v >= 0 ? p.vec_len : p.p_total);
+    const int n = v >= 0 ? p.vec_slots : p.splits;
+    float x[RP_WIDE_MAX];
+#pragma unroll
+    for (int i = 0; i < RP_WIDE_MAX; ++i) x[i] = i < n ? src[(size_t)i * step] : 0.f;  // all in flight
+    float t = 0.f;
+#pragma unroll
+    for (int i = 0; i < RP_WIDE_MAX; ++i) t += x[i];  // slot order (deterministic)
+    float* o = p.out + (size_t)chunk * p.p_total + j;
+    *o = p.accumulate ? *o + t : t;
+    return;
+  }
   // Block = 32 consecutive output elements (coalesced 128-byte rows of the partial
-  // matrix) x 8 warps; warp w sums partials w, w+8, ...; the 8 sub-sums are then
-  // combined in a fixed order (deterministic).
+  // matrix) x 8 warps; warp w sums partials w, w+8, ... (four independent sub-sums, so four
+  // loads are in flight); the 8 sub-sums are then combined in a fixed order (deterministic).
   __shared__ float red[8][33];
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const int j = bx * 32 + lane;
@@ -630,8 +667,16 @@ __device__ __forceinline__ void reduce_params_block(const RParams& p, int bx, in
       for (int sp = w; sp < p.vec_slots; sp += 8)
         s += p.vec_partial[((size_t)sp * p.n_chunks + chunk) * p.vec_len + v];
     } else if (j < p.p_main) {
-      for (int sp = w; sp < p.splits; sp += 8)
-        s += p.partial[((size_t)sp * p.n_chunks + chunk) * p.p_total + j];
+      const float* src = p.partial + (size_t)chunk * p.p_total + j;
+      const size_t step = (size_t)p.n_chunks * p.p_total;
+      float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+      int sp = w;
+      for (; sp + 24 < p.splits; sp += 32) {
+        s0 += src[(size_t)sp * step], s1 += src[(size_t)(sp + 8) * step];
+        s2 += src[(size_t)(sp + 16) * step], s3 += src[(size_t)(sp + 24) * step];
+      }
+      for (; sp < p.splits; sp += 8) s0 += src[(size_t)sp * step];
+      s = (s0 + s1) + (s2 + s3);
     } else {
       const int q = j - p.p_main;  // [2][d_out]
       const int n = p.batch * p.n_tiles;
@@ -673,7 +718,7 @@ __global__ void __launch_bounds__(256) reduce_params_batch_kernel(const __grid_c
   while (j + 1 < b.n && (int)blockIdx.x >= b.blk_off[j + 1]) ++j;
   const RParams& p = b.job[j];
   const int local = blockIdx.x - b.blk_off[j];
-  const int bpc = (p.p_total + 31) / 32;
+  const int bpc = rp_blocks(p);
   reduce_params_block(p, local % bpc, local / bpc);
 }
 
@@ -703,7 +748,7 @@ static int queue_or_launch_reduce(const RParams& rp, bool defer, cudaStream_t st
     g_rq[wave].push_back(rp);
     return 0;
   }
-  dim3 rgrid((rp.p_total + 31) / 32, rp.n_chunks);
+  dim3 rgrid(rp_blocks(rp), rp.n_chunks);
   NLAM_CUDA(launch_k(reduce_params_kernel, rgrid, 256, 0, st, rp));
   NLAM_CUDA(cudaGetLastError());
   count_launch();
@@ -726,7 +771,7 @@ int reduce_params_flush(cudaStream_t st) {
     for (int j = 0; j < b.n; ++j) {
       b.job[j] = jobs[i + j];
       b.blk_off[j] = off;
-      off += (b.job[j].p_total + 31) / 32 * b.job[j].n_chunks;
+      off += rp_blocks(b.job[j]) * b.job[j].n_chunks;
     }
     b.blk_off[b.n] = off;
     if (off == 0) continue;
