@@ -274,8 +274,9 @@ int nlam_version(void);
  * bf16 operands where the tiles fit (see nlam_rowmlp_path); 0 = fp32 FFMA kernels.
  * "small512" (default 1, env NLAM_SMALL512): 512-thread forward CTAs for d = 64 launches
  * of at most 148 tiles (the small levels of the hierarchical meshes); "bwd_spread" (default
- * 1, env NLAM_BWD_SPREAD): fused backward launches of at most 148 tiles run one tile per CTA
- * instead of two per CTA. */
+ * 2, env NLAM_BWD_SPREAD): fused backward launches of at most 148 tiles run one tile per CTA
+ * instead of two (1), on the single-context variant of the kernel with four threads per
+ * tile row (2); 0 = as every other launch. */
 int nlam_set_option(const char* name, int value);
 /* Number of kernels this library has launched in this process (monotonic;
  * bench.py reports the delta over its timed region as "gpu_launches"). */

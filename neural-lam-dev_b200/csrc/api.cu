@@ -35,7 +35,7 @@ static std::atomic<int> g_rb128{env_or("NLAM_RB128", 4)};
 int option_rb128() { return g_rb128.load(); }
 static std::atomic<int> g_bwd_nh{env_or("NLAM_BWD_NH", 2)};
 int option_bwd_nh() { return g_bwd_nh.load(); }
-static std::atomic<int> g_bwd_spread{env_or("NLAM_BWD_SPREAD", 1)};
+static std::atomic<int> g_bwd_spread{env_or("NLAM_BWD_SPREAD", 2)};
 int option_bwd_spread() { return g_bwd_spread.load(); }
 static std::atomic<int> g_small512{env_or("NLAM_SMALL512", 1)};
 int option_small512() { return g_small512.load(); }

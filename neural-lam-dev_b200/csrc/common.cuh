@@ -21,7 +21,8 @@ int option_tma();        // 1: TMA row-gather kernels where every operand has a 
 int option_bwd_nh();     // fused backward: threads per tile row, 2 (default) or 4 (measured 7 % slower)
 int option_wide128();    // 1 (default): d = 128 kernels with 512 threads per CTA
 int option_rb128();      // z blocks per gather round of the d = 128 input-gradient kernel: 4 (default) or 2
-int option_bwd_spread();  // 1 (default): fused backward launches of <= 148 tiles run one tile per CTA (HiLAM +3.2 %)
+int option_bwd_spread();  // fused backward launches of <= 148 tiles: 1 = one tile per CTA (HiLAM +3.2 %),
+                          // 2 (default) = and on the single-context kernel with 4 threads per row (+4.9 %)
 int option_small512();    // 1 (default): 512-thread forward CTAs for d = 64 launches of <= 148 tiles (HiLAM +2.6 %)
 int option_fp32_split();  // 1 (default): fp32 mode on the tensor cores (split bf16 operands) where the tiles fit
 int option_pdl();        // 1: launch with programmatic dependent launch (see launch_k)  // -1 / 1: fused dgrad + wgrad kernel where eligible, 0: two kernels

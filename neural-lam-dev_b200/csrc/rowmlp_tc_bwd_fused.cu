@@ -78,13 +78,17 @@ __device__ __forceinline__ void unpack8(const uint4& q, float* v) {
 
 // FG = true : every source is 64 wide and 16-byte aligned (vector gather; source gradients)
 // FG = false: arbitrary source widths with k_total <= 64 (embedders; no source gradients)
-template <bool FG, int NH>
-__global__ void __launch_bounds__(FuCfg<NH>::NT, 1)
+// NCTX = contexts that run (2; 1 = the variant for launches of at most one tile per SM, which
+// are pure latency: NH = 4 threads per row WITHOUT a second context, i.e. 512 threads at 128
+// registers -- half the per-thread epilogue work of NH = 2 and none of the spills of the
+// two-context NH = 4 variant).  The shared-memory / TMEM layout is the two-context one.
+template <bool FG, int NH, int NCTX = FU_CTX>
+__global__ void __launch_bounds__(NCTX * FuCfg<NH>::CT, 1)
 rowmlp_tc_bwd_fused_kernel(const __grid_constant__ KParams p, const __grid_constant__ BGeo g) {
   extern __shared__ __align__(1024) uint8_t sm[];
   if (smem_u32(sm) & 1023u) __trap();
   constexpr int FN = FU_FN;
-  constexpr int FU_CT = FuCfg<NH>::CT, FU_NT = FuCfg<NH>::NT;
+  constexpr int FU_CT = FuCfg<NH>::CT, FU_NT = NCTX * FuCfg<NH>::CT;
   constexpr int CPT = FuCfg<NH>::CPT, CH = FuCfg<NH>::CH;
   constexpr uint32_t FU_OFF_IDX = fu_off_idx(NH), FU_OFF_BAR = fu_off_bar(NH);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -150,7 +154,7 @@ rowmlp_tc_bwd_fused_kernel(const __grid_constant__ KParams p, const __grid_const
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const int stride = gridDim.x * FU_CTX;
+  const int stride = gridDim.x * NCTX;
   const int mch = FG ? (n_src + 1) / 2 : 1;  // 128-row chunks of dW1^T
 
   // per-thread column sums
@@ -815,8 +819,9 @@ rowmlp_tc_bwd_fused_kernel(const __grid_constant__ KParams p, const __grid_const
     const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
     const int c0 = cq * 16;
     // a context without tiles (last CTA of a small launch) never wrote its accumulators
-    const bool two = p.src0_batch_sum ? (int)(blockIdx.x + gridDim.x) < g.tiles_per_batch
-                                      : (int)(blockIdx.x + gridDim.x) < g.total_tiles;
+    const bool two = NCTX == 2 &&
+                     (p.src0_batch_sum ? (int)(blockIdx.x + gridDim.x) < g.tiles_per_batch
+                                       : (int)(blockIdx.x + gridDim.x) < g.total_tiles);
     float v[16], w[16];
     tmem_ld16(tmem_base + 128u + lane_addr + (uint32_t)c0, v);
     tmem_ld16(tmem_base + 256u + 128u + lane_addr + (uint32_t)c0, w);
@@ -868,7 +873,7 @@ rowmlp_tc_bwd_fused_kernel(const __grid_constant__ KParams p, const __grid_const
         for (int gI = 0; gI < FU_NT / 16; ++gI) s += sDm[gI * 64 + col];
       } else {
 #pragma unroll
-        for (int c = 0; c < FU_CTX; ++c)
+        for (int c = 0; c < NCTX; ++c)
 #pragma unroll
           for (int qq = 0; qq < 4; ++qq)
             s += sRed[((c * 4 * NH + h * 4 + qq) * 4 + which) * 32 + cc];
@@ -913,27 +918,34 @@ int tc_bwd_fused_grid_bsum(const tc::BGeo& g) {
   return grid > 148 ? 148 : grid;
 }
 
-template <bool FG, int NH>
+template <bool FG, int NH, int NCTX = tc::FU_CTX>
 static int launch_fused(const KParams& p, const tc::BGeo& g, int grid, cudaStream_t st) {
-  NLAM_CUDA(ensure_dyn_smem((const void*)tc::rowmlp_tc_bwd_fused_kernel<FG, NH>, (int)tc::fu_smem(NH)));
-  NLAM_CUDA(launch_k(tc::rowmlp_tc_bwd_fused_kernel<FG, NH>, grid, tc::FuCfg<NH>::NT, tc::fu_smem(NH),
-                     st, p, g));
+  NLAM_CUDA(ensure_dyn_smem((const void*)tc::rowmlp_tc_bwd_fused_kernel<FG, NH, NCTX>, (int)tc::fu_smem(NH)));
+  NLAM_CUDA(launch_k(tc::rowmlp_tc_bwd_fused_kernel<FG, NH, NCTX>, grid, NCTX * tc::FuCfg<NH>::CT,
+                     tc::fu_smem(NH), st, p, g));
   return 0;
 }
 
 int tc_rowmlp_bwd_fused(const KParams& p, const tc::BGeo& g, cudaStream_t st) {
   // threads per tile row: 2 (16 warps per SM, 128 registers).  4 (32 warps, 64 registers,
   // ~0.4 KB of spills) is kept as an option: measured 3.55 vs 3.30 ms per GraphLAM step
-  // (also tried: 4 only for launches with at most one tile per context, which are pure
-  // latency -- HiLAM 151.6 vs 159.9 samples/s, so not even there)
+  // (also tried: the two-context NH = 4 kernel only for launches with at most one tile per
+  // context, which are pure latency -- HiLAM 151.6 vs 159.9 samples/s; what does help there
+  // is NH = 4 WITHOUT the second context, below: 170.1 -> 178.5)
   const bool nh4 = option_bwd_nh() == 4;
+  // one tile per CTA (tc_bwd_fused_grid): a single context with four threads per row
+  const bool solo = option_bwd_spread() == 2 && !p.src0_batch_sum && g.total_tiles <= 148;
   int rc;
   if (tc_bwd_fused_kind(p) == 2) {
     const int grid = p.src0_batch_sum ? tc_bwd_fused_grid_bsum(g) : tc_bwd_fused_grid(g);
-    rc = nh4 ? launch_fused<true, 4>(p, g, grid, st) : launch_fused<true, 2>(p, g, grid, st);
+    rc = solo  ? launch_fused<true, 4, 1>(p, g, grid, st)
+         : nh4 ? launch_fused<true, 4>(p, g, grid, st)
+               : launch_fused<true, 2>(p, g, grid, st);
   } else {
     const int grid = tc_bwd_fused_grid(g);
-    rc = nh4 ? launch_fused<false, 4>(p, g, grid, st) : launch_fused<false, 2>(p, g, grid, st);
+    rc = solo  ? launch_fused<false, 4, 1>(p, g, grid, st)
+         : nh4 ? launch_fused<false, 4>(p, g, grid, st)
+               : launch_fused<false, 2>(p, g, grid, st);
   }
   if (rc) return rc;
   NLAM_CUDA(cudaGetLastError());
