@@ -84,3 +84,19 @@ def test_kernel_family_selection(built):
     finally:
         l.nlam_set_option(b"fp32_split", 1)
     assert l.nlam_set_option(b"no_such_option", 1) == 1
+
+
+def test_documented_options_are_accepted(built):
+    """Every option name the header documents for nlam_set_option is accepted (set to its
+    documented default here), and nothing else is."""
+    defaults = {"fwd_mc": -1, "dgrad_mc": 0, "bwd_fused": -1, "pdl": 1, "tma": 0, "bwd_nh": 2,
+                "wide128": 1, "fp32_split": 1, "small512": 1, "bwd_spread": 2}
+    header = open(os.path.join(ROOT, "include", "nlam_b200.h")).read()
+    doc = header[header.index("Kernel-selection knobs"):header.index("int nlam_set_option")]
+    named = set(re.findall(r'"([a-z0-9_]+)"', doc))
+    assert named == set(defaults), named ^ set(defaults)
+    l = built.load()
+    for name, value in defaults.items():
+        assert l.nlam_set_option(name.encode(), value) == 0, name
+    assert l.nlam_set_option(b"bwd_spred", 1) == 1
+    assert b"unknown option" in l.nlam_last_error()
