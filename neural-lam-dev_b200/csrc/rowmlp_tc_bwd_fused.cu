@@ -27,6 +27,12 @@
 // accumulators -- an M=64 UMMA writes row i to lane 32*(i/16) + i%16, so dW1^T rows
 // 128..191 sit in lanes 0-15 of every 32-lane quarter and dW2^T in lanes 16-31.
 //
+// Instantiations <FG, NH, NCTX>: NH = threads per tile row, NCTX = contexts that run.
+// <*, 2, 2> is the kernel described above.  <*, 4, 1> = ONE context of 512 threads (four
+// threads per row, 128 registers) for launches of at most 148 tiles, which get one tile per
+// CTA: the small levels of the hierarchical meshes, where the latency of a single tile is all
+// that counts.  <*, 4, 2> (1024 threads, 64 registers, spills) is an option only.
+//
 // Reference: autograd of utils.make_mlp / InteractionNet.message / aggr_mlp
 // (utils.py:191-214, interaction_net.py:106,117-121).
 #include "rowmlp_tc_bwd.cuh"
